@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- far-field points/s of the NF->FF hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2]
+
+One "step" = one pass of the hot path over one batch: every batch item (wavelength /
+polarisation) of the workload goes aperture fields -> far-field power map P.
+
+  cfg3 (default; the configuration the north-star target is quoted on):
+       4096^2 aperture -> 1024^2 far field (every 4th fftshifted FFT bin), 3 wavelengths
+  cfg2 2048^2 aperture -> 512^2 far field, 532 nm, TE+TM (2 items)
+
+value  = far-field points/s with the aperture fields already resident in HBM
+e2e    = same metric through FarfieldPlan.run_host(): pinned host fields -> H2D ->
+         kernels -> D2H of P, every step
+N > 1  : one process per GPU (torchrun), weak scaling -- every rank owns a full batch of its
+         own apertures (far-field tiles of different sources); one NCCL all-gather of the P
+         tiles per step is inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import apertures  # noqa: E402
+
+WORKLOADS = {
+    "cfg3": dict(M=4096, stride=4, items=[(450e-9, 1.466, False), (532e-9, 1.4607, False), (635e-9, 1.457, False)],
+                 name="cfg3: 4096x4096 aperture -> 1024x1024 far field (every 4th FFT bin), 450/532/635 nm"),
+    "cfg2": dict(M=2048, stride=4, items=[(532e-9, 1.4607, False), (532e-9, 1.4607, True)],
+                 name="cfg2: 2048x2048 aperture -> 512x512 far field (every 4th FFT bin), 532 nm, TE+TM"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _cpu_item(args):
+    """One batch item through the oracle's restatement of the reference CPU path
+    (4x fft2(fftshift) + radiated-power helper), single thread, float64."""
+    M, wl, ng, rot, seed = args
+    from oracle import farfield_oracle as fo
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, seed, wl, ng, rotate=rot)
+    t0 = time.perf_counter()
+    P, total, *_ = fo.farfield_reference_path(Ex, Ey, Hx, Hy, x, y, wl, ng)
+    return time.perf_counter() - t0, float(total)
+
+
+def cpu_reference(workload, sample_M, steps=1, warmup=0, parallel=True):
+    """Time the CPU reference path on a bounded sample: the same workload with the aperture
+    reduced to sample_M^2 samples (stride kept), all batch items; one process per item."""
+    import multiprocessing as mp
+    w = WORKLOADS[workload]
+    items = [(sample_M, wl, ng, rot, 100 + i) for i, (wl, ng, rot) in enumerate(w["items"])]
+    procs = min(len(items), os.cpu_count() or 1) if parallel else 1
+    K = sample_M // w["stride"]
+    times = []
+    ctx = mp.get_context("fork")
+    for it in range(warmup + steps):
+        # timed region = the transform itself inside each worker (input synthesis excluded);
+        # items run concurrently, so a pass costs the slowest item
+        if procs > 1:
+            with ctx.Pool(procs) as pool:
+                dt = max(r[0] for r in pool.map(_cpu_item, items))
+        else:
+            dt = sum(_cpu_item(a)[0] for a in items)
+        if it >= warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    pts = len(items) * K * K
+    return dict(value=pts / t, unit="far-field points/s", cores=procs, kind="port",
+                sample="%d items, aperture %dx%d -> %dx%d requested bins (the numpy path computes all %d^2 bins: "
+                       "%.3g bins/s); oracle/farfield_oracle.py restating nearfield_farfield.py, float64, "
+                       "%d process(es) x 1 thread, %.2f s per pass"
+                       % (len(items), sample_M, sample_M, K, K, sample_M, len(items) * sample_M ** 2 / t, procs, t)), t
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    pure Python and cannot travel to the GPU box) with one process per batch item."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    sample_M = min(w["M"], 2048)
+    base, t = cpu_reference(args.workload, sample_M, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "far-field points/sec (NF->FF)", "value": base["value"],
+        "unit": "far-field points/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
+        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": base["sample"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "far-field points/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from metalens_b200 import _lib
+    from metalens_b200.farfield import FarfieldPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # CPU baseline first (rank 0, N=1 only): it forks worker processes, so run it before CUDA is touched
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        wl_M = WORKLOADS[args.workload]["M"]
+        cpu, _ = cpu_reference(args.workload, min(wl_M, 2048) if not args.quick_cpu else 512, steps=1, warmup=0)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    w = WORKLOADS[args.workload]
+    M, s = w["M"], w["stride"]
+    K = M // s
+    n_items = len(w["items"])
+    peaks = measured_peaks()
+
+    # synthetic apertures (seeded per rank: every rank owns different sources), pinned on the host
+    pinned, dev_fields, plans = [], [], []
+    for i, (wl, ng, rot) in enumerate(w["items"]):
+        Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 1000 * rank + i + 1, wl, ng, rotate=rot)
+        pin = torch.empty((4, M, M), dtype=torch.complex64).pin_memory()
+        for f, a in enumerate((Ex, Ey, Hx, Hy)):
+            pin[f].copy_(torch.from_numpy(a))
+        pinned.append(pin)
+        dev_fields.append(pin.cuda())
+        d = x[1] - x[0]
+        plans.append(FarfieldPlan((M, M), d, d, wl, ng, stride=s, method=args.method))
+        del Ex, Ey, Hx, Hy
+    gathered = torch.empty((world * n_items, K, K), dtype=torch.float32, device="cuda") if world > 1 else None
+    local_P = torch.empty((n_items, K, K), dtype=torch.float32, device="cuda")
+
+    def step_device():
+        for i, plan in enumerate(plans):
+            P, _ = plan.run([dev_fields[i][f] for f in range(4)])
+            local_P[i].copy_(P)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local_P)
+
+    def step_host():
+        out = None
+        for i, plan in enumerate(plans):
+            out = plan.run_host(pinned[i])
+            local_P[i].copy_(plan.P)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local_P)
+            torch.cuda.synchronize()
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.25)
+        l0 = lib.mlb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        launches = lib.mlb_launch_count() - l0
+        dev_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms, wall = t[0].item(), t[1].item() / 1e3
+        barrier()
+        return dev_ms / 1e3, wall, launches, clocks
+
+    # ---- headline: device-resident
+    dev_s, _, launches, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    pts_per_step = world * n_items * K * K
+    value = pts_per_step * args.steps / dev_s
+
+    # ---- e2e: pinned host -> H2D -> kernels -> D2H every step
+    e2e_steps = max(3, min(args.steps, 10))
+    _, e2e_wall, _, _ = timed(step_host, e2e_steps, 2)
+    e2e_value = pts_per_step * e2e_steps / e2e_wall
+    h2d = n_items * plans[0].h2d_bytes
+    d2h = n_items * plans[0].d2h_bytes
+
+    # ---- per-kernel timing of one item for the roofline (CUDA events on the launching stream)
+    def kernel_time(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    import ctypes as C
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    kernels = {}
+    nplan = len(plans)
+    rr = [0]
+
+    def rot():              # rotate over the batch items so inputs (3 x 537 MB) exceed L2 between launches
+        rr[0] = (rr[0] + 1) % nplan
+        return rr[0]
+
+    p0 = plans[0]
+    if p0.method == "fold":
+        def run_fold():
+            i = rot()
+            pj, k1 = _lib.ptr_array([dev_fields[i][f] for f in range(4)])
+            pg, k2 = _lib.ptr_array(plans[i].G)
+            lib.mlb_fold(pj, M, M, M, s, s, M // 2, M // 2, pg, plans[i].G[0].shape[1], 4, st())
+        t_fold = kernel_time(run_fold)
+        kernels["fold"] = dict(seconds=t_fold, bytes=4 * 8 * (M * M + K * K), flops=0)
+    R = p0.Rx
+
+    def run_s1():
+        i = rot()
+        ops = plans[i].G if plans[i].method == "fold" else [dev_fields[i][f] for f in range(4)]
+        pa, k1 = _lib.ptr_array(ops)
+        pu, k2 = _lib.ptr_array(plans[i].UT)
+        lib.mlb_cgemm_tn(pa, ops[0].shape[-1], plans[i].AxT.data_ptr(), plans[i].AxT.shape[1], pu,
+                         plans[i].UT[0].shape[1], plans[i].Ry, K, plans[i].Rx, 4, st())
+
+    def run_s2():
+        i = rot()
+        pu, k2 = _lib.ptr_array(plans[i].UT)
+        pf, k3 = _lib.ptr_array(plans[i].Fhat)
+        lib.mlb_cgemm_tn(pu, plans[i].UT[0].shape[1], plans[i].Ay.data_ptr(), plans[i].Ay.shape[1], pf,
+                         plans[i].Fhat[0].shape[1], K, K, plans[i].Ry, 4, st())
+    kernels["cgemm_stage1"] = dict(seconds=kernel_time(run_s1), flops=4 * 8.0 * R * R * K,
+                                   bytes=8 * (4 * R * R + R * K + 4 * R * K))
+    kernels["cgemm_stage2"] = dict(seconds=kernel_time(run_s2), flops=4 * 8.0 * R * K * K,
+                                   bytes=8 * (4 * R * K + R * K + 4 * K * K))
+    kernels["epilogue"] = dict(seconds=kernel_time(lambda: plans[rot()].power()), flops=0, bytes=36 * K * K)
+    dom = max(kernels, key=lambda k: kernels[k]["seconds"])
+    kd = kernels[dom]
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12       # nominal fp32 FMA pipe, TFLOP/s at max clock
+    if dom == "fold" or dom == "epilogue":
+        ach = kd["bytes"] / kd["seconds"] / 1e9
+        roof = dict(kernel=dom, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=ach / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"])
+    else:
+        ach = kd["flops"] / kd["seconds"] / 1e12
+        roof = dict(kernel=dom, bound="fp32-fma (SIMT; not a tensor-core kernel)", achieved=ach, peak=fp32_peak,
+                    unit="TFLOP/s", frac=ach / fp32_peak, traffic=None,
+                    peak_source="nominal 148 SM x 128 FMA/clk x 2 x 1.965 GHz; bf16 tensor peak %s TF/s for context"
+                                % peaks["bf16_tflops"])
+    step_kernel_s = sum(k["seconds"] for k in kernels.values())
+    roof["share_of_step"] = kd["seconds"] / step_kernel_s
+    if "fold" in kernels:
+        a = kernels["fold"]["bytes"] / kernels["fold"]["seconds"] / 1e9
+        roof["fold_hbm"] = dict(achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
+
+    if rank == 0:
+        line = {
+            "metric": "far-field points/sec (NF->FF)", "value": value, "unit": "far-field points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (complex64 fields, fp32 accumulate, f64 twiddle phases/epilogue)",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "method": p0.method, "batch_items_per_gpu": n_items,
+                       "aperture": [M, M], "far_field": [K, K], "l2": "inputs larger than L2 (%.0f MB per step)"
+                       % (n_items * 32 * M * M / 1e6), "parallelism": "far-field tiles sharded, %d rank(s)" % world},
+            "e2e": {"value": e2e_value, "unit": "far-field points/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": {k: dict(ms=v["seconds"] * 1e3, gbs=v["bytes"] / v["seconds"] / 1e9,
+                                tflops=v["flops"] / v["seconds"] / 1e12) for k, v in kernels.items()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--method", default="auto", choices=["auto", "dense", "fold"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick-cpu", action="store_true", help="tiny cpu_baseline sample (debug)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+/*
+ * metalens_b200 -- C-ABI of the B200-native near-field -> far-field engine.
+ *
+ * The reference (sbyrnes321/metalens) is pure Python; it has no FFI.  Its drop-in
+ * boundary is the Python call surface (nearfield_farfield.farfield_from_nearfield,
+ * nearfield.build_nearfield, GratingCollection/HexGridSet.build_interpolators).
+ * This header is the compute boundary underneath that surface: the Python host
+ * package `metalens_b200` binds exactly these symbols through ctypes
+ * (metalens_b200/_lib.py) and nothing else.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name starts with `h_`;
+ *    complex data is interleaved (re,im) float pairs ("c64"), 16-byte aligned,
+ *    with an even leading dimension (in complex elements);
+ *  - every function is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - return value 0 = OK, negative = error; mlb_last_error() gives the message
+ *    (thread-local);
+ *  - no hidden allocation: workspaces are passed in by the caller.
+ */
+#ifndef METALENS_B200_H
+#define METALENS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLB_VERSION 100          /* 0.1.0 */
+#define MLB_OK 0
+#define MLB_ERR_ARG (-1)
+#define MLB_ERR_CUDA (-2)
+#define MLB_ERR_UNSUPPORTED (-3)
+
+typedef struct mlb_c64 { float re, im; } mlb_c64;
+
+/* ---- plumbing ------------------------------------------------------------ */
+int mlb_version(void);
+const char *mlb_last_error(void);
+/* out[0]=sm major, [1]=sm minor, [2]=SM count, [3]=max dynamic smem per block (bytes) */
+int mlb_device_caps(int device, int *out4);
+/* number of kernels this library has launched since load (bench "gpu_launches") */
+long long mlb_launch_count(void);
+
+/* ---- A1/A4: separable aperture sum --------------------------------------- */
+/*
+ * Twiddle table  out[m*ld + i] = exp(i*pi*scale*coord[m]*u[i]),  m<n_coord, i<n_u,
+ * phases formed in float64 and reduced exactly (sincospi) before rounding to fp32
+ * (SURVEY H1).  With scale = -2*n_glass/wavelength, coord = x' and u = ux this is
+ * the kernel e^{-ik x' ux} of nearfield_farfield.py:97-120; with scale = -2/N,
+ * coord = 0..N-1 and u = integer bin numbers it is the exact DFT twiddle of
+ * numpy.fft (nearfield_farfield.py:111-116).
+ */
+int mlb_twiddle_build(const double *coord, int n_coord, const double *u, int n_u,
+                      double scale, mlb_c64 *out, int ld, void *stream);
+
+/*
+ * Tiled complex reduction (fp32 SIMT, 1-D TMA bulk copies into shared memory):
+ *     C_b[r*ldc + c] = sum_{k<depth} At_b[k*lda + r] * B[k*ldb + c]      b < batch<=4
+ * Both operands are stored with the contracted index as the ROW index, which is
+ * how the aperture (J[m1][m2]), the twiddles and the stage-1 output naturally lie.
+ *   stage 1:  At = field J_f (Mx x My),  B = AxT (Mx x Kx)  -> UT_f (My x Kx)
+ *   stage 2:  At = UT_f (My x Kx),       B = Ay  (My x Ky)  -> Fhat_f (Kx x Ky)
+ * Replaces the caller-side fft2(fftshift(.)) of nearfield_farfield.py:18-20 for an
+ * arbitrary direction-cosine grid.
+ */
+int mlb_cgemm_tn(const mlb_c64 *const *h_At, int lda, const mlb_c64 *B, int ldb,
+                 mlb_c64 *const *h_C, int ldc, int rows, int cols, int depth,
+                 int batch, void *stream);
+
+/*
+ * Aperture fold for FFT-bin-stride grids: when the far-field grid is every s-th
+ * FFT bin, the M-point sum collapses exactly to an (M/s)-point sum of the folded
+ * aperture
+ *     G_f[p1*ldg + p2] = sum_{t1<s1,t2<s2} J_f[((p1-h1) mod K1 + t1*K1)*ldj + (p2-h2) mod K2 + t2*K2]
+ * with K1 = M1/s1, K2 = M2/s2 and h = the fftshift origin (M - M/2).  Streaming,
+ * HBM-bound: reads 8*M1*M2 bytes per field once.
+ */
+int mlb_fold(const mlb_c64 *const *h_J, int ldj, int M1, int M2, int s1, int s2,
+             int h1, int h2, mlb_c64 *const *h_G, int ldg, int batch, void *stream);
+
+/* ---- A2/A3: radiated power ------------------------------------------------ */
+/*
+ * Fhat (4 x Kx x Ky c64: Ex,Ey,Hx,Hy aperture sums) -> P (Kx x Ky) following
+ * farfield_from_nearfield_helper, nearfield_farfield.py:135-189, in float64
+ * arithmetic: equivalent currents N,L; uz = sqrt(1-ux^2-uy^2) with NaN for
+ * evanescent bins; theta/phi components with the 1e-9 regulariser; Cartesian
+ * components at the exact ux==uy==0 bin; P = k^2/(32 pi^2 Z) (...)/(uz+1e-5) * 2.
+ * `amp_scale` multiplies every Fhat before use (dx*dy, and 1/len factors).
+ * P is written as float (p_is_double=0) or double (1).  If `block_sums` is not
+ * NULL, each block writes the sum of its finite P values to block_sums[blockIdx]
+ * (mlb_ff_epilogue_blocks() entries) for a deterministic total_P.
+ */
+int mlb_ff_epilogue_blocks(int Kx, int Ky);
+int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const double *ux, const double *uy,
+                    int Kx, int Ky, double amp_scale, double wavelength, double n_glass,
+                    double Z0, void *P, int ldp, int p_is_double, double *block_sums,
+                    void *stream);
+/* out[0] = scale * sum_{i<n} in[i], summed in a fixed order by one block */
+int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METALENS_B200_H */

@@ -1,0 +1,71 @@
+"""ctypes binding of libmetalens_b200.so (include/metalens_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, the
+product path raises.  Build the library with ``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C metalens_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmetalens_b200.so")
+
+
+class MetalensB200Error(RuntimeError):
+    pass
+
+
+_PP = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol declared in include/metalens_b200.h
+SIGNATURES = {
+    "mlb_version": (C.c_int, []),
+    "mlb_last_error": (C.c_char_p, []),
+    "mlb_device_caps": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "mlb_launch_count": (C.c_longlong, []),
+    "mlb_twiddle_build": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                    C.c_void_p, C.c_int, C.c_void_p]),
+    "mlb_cgemm_tn": (C.c_int, [_PP, C.c_int, C.c_void_p, C.c_int, _PP, C.c_int,
+                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mlb_fold": (C.c_int, [_PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                           _PP, C.c_int, C.c_int, C.c_void_p]),
+    "mlb_ff_epilogue_blocks": (C.c_int, [C.c_int, C.c_int]),
+    "mlb_ff_epilogue": (C.c_int, [_PP, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_double, C.c_double, C.c_double, C.c_double,
+                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_sum_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MetalensB200Error(
+            "metalens_b200: %s not found. The CUDA extension is the product; there is no CPU "
+            "fallback. Build it with `make -C metalens_b200/csrc` (needs nvcc, sm_100a)." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the .so disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mlb_last_error().decode("utf-8", "replace")
+        raise MetalensB200Error("%s failed (rc=%d): %s" % (what, rc, msg))
+
+
+def ptr_array(tensors):
+    """void*[len] of device pointers (host array, as the C-ABI's h_ arguments expect)."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return C.cast(arr, _PP), arr

@@ -1,0 +1,134 @@
+// Radiated-power epilogue: aperture sums (Ex,Ey,Hx,Hy) -> P(ux,uy).
+// Follows farfield_from_nearfield_helper (reference nearfield_farfield.py:135-189) in
+// float64 arithmetic; K^2 points x ~100 flop is negligible next to the aperture sum.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace mlb {
+
+struct EpiArgs {
+    const float2 *F[4];   // Ex, Ey, Hx, Hy aperture sums
+    const double *ux, *uy;
+    void *P;
+    double *block_sums;
+    double amp_scale, pref, Z;
+    int ldf, ldp, Kx, Ky, p_is_double;
+};
+
+struct cd { double re, im; };
+__device__ __forceinline__ cd cmul(cd a, double s) { return {a.re * s, a.im * s}; }
+__device__ __forceinline__ cd cadd(cd a, cd b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cd csub(cd a, cd b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ double cabs2(cd a) { return a.re * a.re + a.im * a.im; }
+
+constexpr int EPI_THREADS = 256;
+
+__global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
+    const long long n = (long long)blockIdx.x * EPI_THREADS + threadIdx.x;
+    const long long total = (long long)a.Kx * a.Ky;
+    double p = 0.0;
+    bool finite = false;
+    if (n < total) {
+        const int i = (int)(n / a.Ky), j = (int)(n % a.Ky);
+        const double ux = a.ux[i], uy = a.uy[j];
+        const size_t off = (size_t)i * a.ldf + j;
+        const float2 fex = a.F[0][off], fey = a.F[1][off], fhx = a.F[2][off], fhy = a.F[3][off];
+        const double s_ = a.amp_scale;
+        // (8.15) J = n x H, M = -n x E with n = +z  (reference :135-138)
+        const cd Nx = {-(double)fhy.x * s_, -(double)fhy.y * s_};
+        const cd Ny = {(double)fhx.x * s_, (double)fhx.y * s_};
+        const cd Lx = {(double)fey.x * s_, (double)fey.y * s_};
+        const cd Ly = {-(double)fex.x * s_, -(double)fex.y * s_};
+        // uz^2 exactly as numpy evaluates (1 - ux**2 - uy**2): no FMA contraction, so the
+        // evanescent (NaN) mask is bit-identical to the reference's (:153-155).
+        const double ux2 = __dmul_rn(ux, ux), uy2 = __dmul_rn(uy, uy);
+        const double uz2 = __dsub_rn(__dsub_rn(1.0, ux2), uy2);
+        const double uz = (uz2 < 0.0) ? CUDART_NAN : sqrt(uz2);
+        const double sinth = sqrt(__dadd_rn(ux2, uy2));
+        const double d = sinth + 1e-9;                                    // :158 regulariser
+        cd Nth, Nph, Lth, Lph;
+        if (ux == 0.0 && uy == 0.0) {                                     // :161-169
+            Nth = Nx; Nph = Ny; Lth = Lx; Lph = Ly;
+        } else {
+            const double cx = ux * uz / d, cy = uy * uz / d, px = ux / d, py = uy / d;
+            Nth = cadd(cmul(Nx, cx), cmul(Ny, cy));                       // :158
+            Nph = csub(cmul(Ny, px), cmul(Nx, py));                       // :159
+            Lth = cadd(cmul(Lx, cx), cmul(Ly, cy));                       // :166
+            Lph = csub(cmul(Ly, px), cmul(Lx, py));                       // :167
+        }
+        const cd t1 = cadd(Lph, cmul(Nth, a.Z));
+        const cd t2 = csub(Lth, cmul(Nph, a.Z));
+        p = a.pref * (cabs2(t1) + cabs2(t2)) / (uz + 1e-5) * 2.0;         // :184-189
+        const size_t po = (size_t)i * a.ldp + j;
+        if (a.p_is_double) reinterpret_cast<double *>(a.P)[po] = p;
+        else reinterpret_cast<float *>(a.P)[po] = (float)p;
+        finite = isfinite(p);
+    }
+    if (a.block_sums) {                                                   // :74 total_P over finite bins
+        double v = finite ? p : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __shared__ double ws[EPI_THREADS / 32];
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < EPI_THREADS / 32; ++w) s += ws[w];
+            a.block_sums[blockIdx.x] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) sum_f64_kernel(const double *__restrict__ in, int n, double scale,
+                                                       double *__restrict__ out) {
+    __shared__ double ws[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) v += in[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = ws[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) out[0] = v * scale;
+    }
+}
+
+}  // namespace mlb
+
+extern "C" int mlb_ff_epilogue_blocks(int Kx, int Ky) {
+    long long t = (long long)Kx * Ky;
+    return (int)((t + mlb::EPI_THREADS - 1) / mlb::EPI_THREADS);
+}
+
+extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const double *ux, const double *uy, int Kx,
+                               int Ky, double amp_scale, double wavelength, double n_glass, double Z0, void *P,
+                               int ldp, int p_is_double, double *block_sums, void *stream) {
+    MLB_REQUIRE(h_Fhat && ux && uy && P, "mlb_ff_epilogue: NULL pointer");
+    MLB_REQUIRE(Kx > 0 && Ky > 0 && ldf >= Ky && ldp >= Ky, "mlb_ff_epilogue: bad sizes");
+    MLB_REQUIRE(wavelength > 0 && n_glass > 0 && Z0 > 0, "mlb_ff_epilogue: bad physical constants");
+    mlb::EpiArgs a;
+    for (int f = 0; f < 4; ++f) {
+        MLB_REQUIRE(h_Fhat[f] != nullptr, "mlb_ff_epilogue: field %d is NULL", f);
+        a.F[f] = reinterpret_cast<const float2 *>(h_Fhat[f]);
+    }
+    a.ux = ux; a.uy = uy; a.P = P; a.block_sums = block_sums;
+    a.amp_scale = amp_scale;
+    a.Z = Z0 / n_glass;                                                    // :183
+    const double pi = 3.14159265358979323846;
+    const double k = 2 * pi * n_glass / wavelength;
+    a.pref = k * k / (32 * pi * pi * a.Z);                                  // :184
+    a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double;
+    mlb::ff_epilogue_kernel<<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
+    return mlb::check_launch("mlb_ff_epilogue");
+}
+
+extern "C" int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream) {
+    MLB_REQUIRE(in && out && n >= 0, "mlb_sum_f64: bad arguments");
+    mlb::sum_f64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, scale, out);
+    return mlb::check_launch("mlb_sum_f64");
+}

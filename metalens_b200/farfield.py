@@ -1,0 +1,348 @@
+"""Near-field -> far-field transform on the B200 (hot path A of SURVEY.md section 8).
+
+Python host side of the reference's ``nearfield_farfield.py``.  Three entry points:
+
+* :func:`farfield_from_nearfield` -- the reference's own signature and return tuple
+  (``nearfield_farfield.py:14-75``): takes ``fft2(fftshift(field))`` arrays, so only
+  the radiated-power epilogue (``:77-191``) runs on the GPU.  Strict drop-in.
+* :func:`farfield_from_fields` -- takes the real-space aperture fields and does the
+  aperture sum on the GPU as well (replaces the caller-side FFTs of ``:18-20``),
+  on the reference's FFT-bin grid, every ``stride``-th bin of it, or an arbitrary
+  direction-cosine grid.
+* :class:`FarfieldPlan` -- the reusable device-resident engine behind both: twiddle
+  tables, workspaces and kernel launches through the C-ABI (``include/metalens_b200.h``).
+
+torch is used only for device buffers, streams and copies; every arithmetic step
+is a kernel of ``libmetalens_b200.so``.  There is no CPU fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .units import Z0
+
+
+def fft_bin_direction_cosines(num, spacing, wavelength, n_glass):
+    """Un-shifted direction cosines of the FFT bins, same arithmetic as the reference
+    (nearfield_farfield.py:35-39) so the NaN mask of evanescent bins is bit-identical."""
+    lam = wavelength / n_glass
+    u = np.arange(num) * lam / (spacing * num)
+    u[u > u.max() / 2] -= lam / spacing
+    return u
+
+
+def _check_axis(pts, wavelength):
+    """Grid validation, nearfield_farfield.py:26-30 (AssertionError like the reference)."""
+    pts = np.asarray(pts, dtype=float)
+    steps = np.diff(pts)
+    assert 0 < steps[0] < wavelength / 2
+    assert steps.max() - steps.min() <= 1e-9 * np.abs(steps).max()
+
+
+def _even(n):
+    return n + (n & 1)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c64_buffer(rows, cols, device):
+    """Zeroed complex64 [rows][ld] device buffer with an even pitch; returns the
+    full (pitched) tensor -- its logical view is buf[:, :cols]."""
+    return torch.zeros((rows, _even(cols)), dtype=torch.complex64, device=device)
+
+
+class FarfieldPlan:
+    """Device-resident NF->FF engine for one aperture geometry and one far-field grid.
+
+    Parameters
+    ----------
+    shape : (Mx, My) aperture samples (axis 0 = x, axis 1 = y, C order; nearfield.py:117)
+    dxp, dyp : sample spacings
+    wavelength, n_glass : vacuum wavelength and substrate index (direction cosines are
+        *in glass*, nearfield_farfield.py:33-36)
+    stride : int or (sx, sy) -- far-field grid = every stride-th bin of the reference's
+        fftshifted FFT-bin grid (stride 1 = the reference grid itself)
+    ux, uy : explicit direction-cosine lists (arbitrary grid); excludes `stride`
+    method : 'auto' | 'dense' | 'fold'
+        dense -- two-stage separable tiled complex reduction over the full aperture
+        fold  -- exact aperture fold (HBM-bound) followed by the dense reduction on the
+                 folded (Mx/sx x My/sy) aperture; needs an FFT-bin-stride grid with
+                 sx | Mx//2 and sy | My//2
+    p_dtype : torch.float32 (north-star output type) or torch.float64
+    """
+
+    def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride=None, ux=None, uy=None,
+                 method="auto", p_dtype=torch.float32, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.Mx, self.My = int(shape[0]), int(shape[1])
+        self.dxp, self.dyp = float(dxp), float(dyp)
+        self.wavelength, self.n_glass = float(wavelength), float(n_glass)
+        assert p_dtype in (torch.float32, torch.float64)
+        self.p_dtype = p_dtype
+
+        if ux is None and uy is None:
+            stride = 1 if stride is None else stride
+            sx, sy = (stride, stride) if np.isscalar(stride) else stride
+            self.sx, self.sy = int(sx), int(sy)
+            ux = np.fft.fftshift(fft_bin_direction_cosines(self.Mx, self.dxp, wavelength, n_glass))[::self.sx]
+            uy = np.fft.fftshift(fft_bin_direction_cosines(self.My, self.dyp, wavelength, n_glass))[::self.sy]
+            self.fft_bin_grid = True
+        else:
+            assert stride is None and ux is not None and uy is not None
+            self.sx = self.sy = None
+            self.fft_bin_grid = False
+        self.ux = np.ascontiguousarray(ux, dtype=np.float64)
+        self.uy = np.ascontiguousarray(uy, dtype=np.float64)
+        self.Kx, self.Ky = self.ux.size, self.uy.size
+
+        can_fold = (self.fft_bin_grid and self.Mx % self.sx == 0 and self.My % self.sy == 0
+                    and (self.Mx // 2) % self.sx == 0 and (self.My // 2) % self.sy == 0
+                    and (self.sx > 1 or self.sy > 1))
+        if method == "auto":
+            method = "fold" if can_fold else "dense"
+        if method == "fold" and not can_fold:
+            raise ValueError("fold needs an FFT-bin-stride grid with stride dividing M and M//2")
+        assert method in ("dense", "fold")
+        self.method = method
+        self._build()
+
+    # ------------------------------------------------------------------ setup
+    def _twiddle(self, coord, u, scale):
+        """[len(coord)][even(len(u))] complex64 table exp(i*pi*scale*coord*u)."""
+        dev = self.device
+        c = torch.from_numpy(np.ascontiguousarray(coord, dtype=np.float64)).to(dev)
+        v = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(dev)
+        out = _c64_buffer(c.numel(), v.numel(), dev)
+        rc = self.lib.mlb_twiddle_build(c.data_ptr(), c.numel(), v.data_ptr(), v.numel(), float(scale),
+                                        out.data_ptr(), out.shape[1], _stream_ptr())
+        _lib.check(rc, "mlb_twiddle_build")
+        return out
+
+    def _build(self):
+        dev = self.device
+        Mx, My, Kx, Ky = self.Mx, self.My, self.Kx, self.Ky
+        if self.method == "dense":
+            # phase origin = the sample fftshift() moves to index 0: M - M//2
+            ox, oy = Mx - Mx // 2, My - My // 2
+            scale = -2.0 * self.n_glass / self.wavelength
+            self.AxT = self._twiddle((np.arange(Mx) - ox) * self.dxp, self.ux, scale)   # [Mx][Kx]
+            self.Ay = self._twiddle((np.arange(My) - oy) * self.dyp, self.uy, scale)    # [My][Ky]
+            self.Rx, self.Ry = Mx, My            # size of the aperture the reduction runs over
+            self.G = None
+        else:
+            # folded aperture (K1 x K2) and exact integer DFT twiddles exp(-2 pi i p q / K)
+            K1, K2 = Mx // self.sx, My // self.sy
+            assert K1 == Kx and K2 == Ky
+            qx = (np.arange(K1) - (Mx // 2) // self.sx) % K1     # un-shifted bin number of output q'
+            qy = (np.arange(K2) - (My // 2) // self.sy) % K2
+            self.AxT = self._twiddle(np.arange(K1), qx, -2.0 / K1)
+            self.Ay = self._twiddle(np.arange(K2), qy, -2.0 / K2)
+            self.Rx, self.Ry = K1, K2
+            self.G = [_c64_buffer(K1, K2, dev) for _ in range(4)]
+        self.UT = [_c64_buffer(self.Ry, Kx, dev) for _ in range(4)]      # stage-1 output, [m2][i]
+        self.Fhat = [_c64_buffer(Kx, Ky, dev) for _ in range(4)]         # aperture sums, [i][j]
+        self.P = torch.empty((Kx, Ky), dtype=self.p_dtype, device=dev)
+        self.nblocks = self.lib.mlb_ff_epilogue_blocks(Kx, Ky)
+        self.block_sums = torch.empty(self.nblocks, dtype=torch.float64, device=dev)
+        self.total = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.d_ux = torch.from_numpy(self.ux).to(dev)
+        self.d_uy = torch.from_numpy(self.uy).to(dev)
+        self.dux = float(self.ux[1] - self.ux[0]) if Kx > 1 else float("nan")
+        self.duy = float(self.uy[1] - self.uy[0]) if Ky > 1 else float("nan")
+        self._staging = None
+        self._pinned = None
+
+    # ------------------------------------------------------------------ run
+    def _as_operands(self, fields):
+        """Return 4 pitched complex64 device tensors [Mx][even(My)] for the kernels;
+        copies only when the caller's layout cannot be used in place."""
+        out = []
+        for idx, f in enumerate(fields):
+            assert f.is_cuda and f.dtype == torch.complex64 and tuple(f.shape[-2:]) == (self.Mx, self.My), \
+                "fields must be CUDA complex64 (Mx, My)"
+            ok = (f.stride(-1) == 1 and f.stride(-2) % 2 == 0 and f.stride(-2) >= self.My
+                  and f.data_ptr() % 16 == 0)
+            if ok:
+                out.append((f, f.stride(-2)))
+            else:
+                if self._staging is None:
+                    self._staging = [_c64_buffer(self.Mx, self.My, self.device) for _ in range(4)]
+                self._staging[idx][:, :self.My].copy_(f)
+                out.append((self._staging[idx], self._staging[idx].shape[1]))
+        lds = {ld for _, ld in out}
+        assert len(lds) == 1, "the four fields must share one row pitch"
+        return [t for t, _ in out], lds.pop()
+
+    def aperture_sums(self, fields):
+        """Stage 1 + stage 2 (+ fold): Fhat_f[i,j] = sum_{m1,m2} J_f[m1,m2] e^{-ik(x'ux_i + y'uy_j)}.
+        Returns the 4 pitched device tensors (logical view [:, :Ky])."""
+        lib, st = self.lib, _stream_ptr()
+        ops, ld = self._as_operands(fields)
+        if self.method == "fold":
+            pj, _k1 = _lib.ptr_array(ops)
+            pg, _k2 = _lib.ptr_array(self.G)
+            rc = lib.mlb_fold(pj, ld, self.Mx, self.My, self.sx, self.sy, self.Mx // 2, self.My // 2,
+                              pg, self.G[0].shape[1], 4, st)
+            _lib.check(rc, "mlb_fold")
+            ops, ld = self.G, self.G[0].shape[1]
+        # stage 1: UT_f[m2][i] = sum_{m1} J_f[m1][m2] * AxT[m1][i]
+        pa, _k3 = _lib.ptr_array(ops)
+        pu, _k4 = _lib.ptr_array(self.UT)
+        rc = lib.mlb_cgemm_tn(pa, ld, self.AxT.data_ptr(), self.AxT.shape[1], pu, self.UT[0].shape[1],
+                              self.Ry, self.Kx, self.Rx, 4, st)
+        _lib.check(rc, "mlb_cgemm_tn(stage 1)")
+        # stage 2: Fhat_f[i][j] = sum_{m2} UT_f[m2][i] * Ay[m2][j]
+        pf, _k5 = _lib.ptr_array(self.Fhat)
+        rc = lib.mlb_cgemm_tn(pu, self.UT[0].shape[1], self.Ay.data_ptr(), self.Ay.shape[1], pf,
+                              self.Fhat[0].shape[1], self.Kx, self.Ky, self.Ry, 4, st)
+        _lib.check(rc, "mlb_cgemm_tn(stage 2)")
+        return self.Fhat
+
+    def power(self, Fhat=None, amp_scale=None):
+        """Epilogue: aperture sums -> P (device), total_P (device scalar, float64)."""
+        Fhat = self.Fhat if Fhat is None else Fhat
+        amp = self.dxp * self.dyp if amp_scale is None else amp_scale
+        pf, _k = _lib.ptr_array(Fhat)
+        rc = self.lib.mlb_ff_epilogue(pf, Fhat[0].shape[1], self.d_ux.data_ptr(), self.d_uy.data_ptr(),
+                                      self.Kx, self.Ky, float(amp), self.wavelength, self.n_glass, Z0,
+                                      self.P.data_ptr(), self.P.shape[1],
+                                      1 if self.p_dtype == torch.float64 else 0,
+                                      self.block_sums.data_ptr(), _stream_ptr())
+        _lib.check(rc, "mlb_ff_epilogue")
+        rc = self.lib.mlb_sum_f64(self.block_sums.data_ptr(), self.nblocks, self.dux * self.duy,
+                                  self.total.data_ptr(), _stream_ptr())
+        _lib.check(rc, "mlb_sum_f64")
+        return self.P, self.total
+
+    def run(self, fields):
+        """Device-resident fields (4 CUDA complex64 (Mx,My) tensors) -> (P, total_P) on device."""
+        self.aperture_sums(fields)
+        return self.power()
+
+    def amplitudes(self):
+        """Complex aperture sums of the last run as a (4, Kx, Ky) device tensor."""
+        return torch.stack([f[:, :self.Ky] for f in self.Fhat])
+
+    def run_host(self, Ex, Ey=None, Hx=None, Hy=None):
+        """End-to-end call with HOST fields: H2D from pinned memory, kernels, D2H.
+
+        Pass four numpy arrays (Mx,My) (converted to complex64 into an internal pinned
+        buffer), or one pinned torch complex64 tensor (4,Mx,My) that is copied as is.
+        Returns (P numpy, total_P float)."""
+        if self._pinned is None:
+            self._dev_in = torch.empty((4, self.Mx, _even(self.My)), dtype=torch.complex64, device=self.device)
+            self._p_host = torch.empty((self.Kx, self.Ky), dtype=self.p_dtype).pin_memory()
+            self._t_host = torch.empty(1, dtype=torch.float64).pin_memory()
+            self._pinned = True
+        if isinstance(Ex, torch.Tensor) and Ey is None:
+            src = Ex
+            assert src.dtype == torch.complex64 and tuple(src.shape) == (4, self.Mx, self.My)
+        else:
+            if getattr(self, "_pin_in", None) is None:
+                self._pin_in = torch.empty((4, self.Mx, self.My), dtype=torch.complex64).pin_memory()
+            pin = self._pin_in.numpy()
+            for i, a in enumerate((Ex, Ey, Hx, Hy)):
+                pin[i] = a                  # dtype conversion to complex64 happens here
+            src = self._pin_in
+        self._dev_in[:, :, :self.My].copy_(src, non_blocking=True)
+        P, total = self.run([self._dev_in[i] for i in range(4)])
+        self._p_host.copy_(P, non_blocking=True)
+        self._t_host.copy_(total, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._p_host.numpy().copy(), float(self._t_host[0])
+
+    @property
+    def h2d_bytes(self):
+        return 4 * self.Mx * self.My * 8
+
+    @property
+    def d2h_bytes(self):
+        return self.Kx * self.Ky * self.P.element_size() + 8
+
+
+def _power_epilogue(lib, F, d_ux, d_uy, Kx, Ky, amp_scale, wavelength, n_glass, P, dudu):
+    """Launch mlb_ff_epilogue + the deterministic total_P reduction; returns the
+    device scalar total_P (float64)."""
+    dev = P.device
+    nblocks = lib.mlb_ff_epilogue_blocks(Kx, Ky)
+    block_sums = torch.empty(nblocks, dtype=torch.float64, device=dev)
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+    pf, _keep = _lib.ptr_array(F)
+    rc = lib.mlb_ff_epilogue(pf, F[0].shape[1], d_ux.data_ptr(), d_uy.data_ptr(), Kx, Ky,
+                             float(amp_scale), float(wavelength), float(n_glass), Z0,
+                             P.data_ptr(), P.shape[1], 1 if P.dtype == torch.float64 else 0,
+                             block_sums.data_ptr(), _stream_ptr())
+    _lib.check(rc, "mlb_ff_epilogue")
+    rc = lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, float(dudu), total.data_ptr(), _stream_ptr())
+    _lib.check(rc, "mlb_sum_f64")
+    return total
+
+
+def farfield_from_fields(Ex, Ey, Hx, Hy, xp_list, yp_list, wavelength, n_glass, stride=1,
+                         ux=None, uy=None, method="auto", p_dtype=torch.float64):
+    """Real-space aperture fields (host arrays) -> far field, aperture sum included.
+
+    With the default ``stride=1`` the result equals the reference chain
+    ``farfield_from_nearfield(fft2(fftshift(Ex)), ...)`` (nearfield_farfield.py:14-75):
+    same return tuple ``(P, total_P, ux (Kx,1), uy (1,Ky), dux, duy)``.
+    """
+    dxp = xp_list[1] - xp_list[0]
+    dyp = yp_list[1] - yp_list[0]
+    nx, ny = len(xp_list), len(yp_list)
+    assert Ex.shape == Ey.shape == Hx.shape == Hy.shape == (nx, ny)
+    _check_axis(xp_list, wavelength)
+    _check_axis(yp_list, wavelength)
+    if ux is not None:
+        plan = FarfieldPlan((nx, ny), dxp, dyp, wavelength, n_glass, ux=ux, uy=uy, method="dense", p_dtype=p_dtype)
+    else:
+        plan = FarfieldPlan((nx, ny), dxp, dyp, wavelength, n_glass, stride=stride, method=method, p_dtype=p_dtype)
+    P, total = plan.run_host(Ex, Ey, Hx, Hy)
+    return P, total, plan.ux.reshape(-1, 1), plan.uy.reshape(1, -1), plan.dux, plan.duy
+
+
+def farfield_from_nearfield(fftEx, fftEy, fftHx, fftHy, xp_list, yp_list, wavelength, n_glass):
+    """Drop-in for the reference's ``nearfield_farfield.farfield_from_nearfield``
+    (nearfield_farfield.py:14-75): same arguments (``fftEx = fft2(fftshift(Ex))`` ...),
+    same return tuple ``(P_here_times_r2_over_uz, total_P, ux, uy, dux, duy)``, same
+    AssertionErrors on shape / grid violations.  The power epilogue runs on the GPU in
+    float64; the reference's RAM chunk loop and its progress prints are not reproduced.
+    """
+    dxp = xp_list[1] - xp_list[0]
+    dyp = yp_list[1] - yp_list[0]
+    num_x, num_y = len(xp_list), len(yp_list)
+    assert fftEx.shape == fftEy.shape == fftHx.shape == fftHy.shape == (num_x, num_y)
+    _check_axis(xp_list, wavelength)
+    _check_axis(yp_list, wavelength)
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ux = fft_bin_direction_cosines(num_x, dxp, wavelength, n_glass)
+    uy = fft_bin_direction_cosines(num_y, dyp, wavelength, n_glass)
+    # common power-of-two normalisation so complex64 cannot under/overflow for any unit system
+    peak = max(float(np.abs(a).max()) for a in (fftEx, fftEy, fftHx, fftHy))
+    norm = 2.0 ** math.floor(math.log2(peak)) if peak > 0 and math.isfinite(peak) else 1.0
+    F = []
+    for a in (fftEx, fftEy, fftHx, fftHy):
+        buf = _c64_buffer(num_x, num_y, dev)
+        buf[:, :num_y].copy_(torch.from_numpy(np.ascontiguousarray(a / norm).astype(np.complex64)))
+        F.append(buf)
+    d_ux, d_uy = torch.from_numpy(ux).to(dev), torch.from_numpy(uy).to(dev)
+    P = torch.empty((num_x, num_y), dtype=torch.float64, device=dev)
+    ux_s = np.fft.fftshift(ux)                                                           # :69
+    uy_s = np.fft.fftshift(uy)                                                           # :70
+    dux = ux_s[1] - ux_s[0]                                                              # :71
+    duy = uy_s[1] - uy_s[0]                                                              # :72
+    total = _power_epilogue(lib, F, d_ux, d_uy, num_x, num_y, dxp * dyp * norm, wavelength, n_glass,
+                            P, dux * duy)                                                # :74
+    P = torch.roll(P, shifts=(num_x // 2, num_y // 2), dims=(0, 1)).cpu().numpy()       # fftshift, :68
+    ux2, uy2 = np.meshgrid(ux_s, uy_s, indexing="ij", sparse=True)                       # :73
+    return P, float(total.cpu()[0]), ux2, uy2, dux, duy

@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library loads and exports every symbol include/metalens_b200.h declares
+(no compute calls without a GPU), and the ctypes table covers the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "metalens_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mlb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from metalens_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+
+
+def test_ctypes_table_matches_header():
+    from metalens_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.mlb_version() == 100
+    assert lib.mlb_launch_count() >= 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from metalens_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.MetalensB200Error):
+        _lib.load()
+
+
+def test_no_cuda_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from metalens_b200 import farfield, MetalensB200Error
+    with pytest.raises(MetalensB200Error):
+        farfield.FarfieldPlan((8, 8), 1e-7, 1e-7, 532e-9, 1.46)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: the product package must not reference it."""
+    pkg = os.path.join(ROOT, "metalens_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f

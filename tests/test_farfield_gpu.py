@@ -1,0 +1,239 @@
+"""GPU parity tests for hot path A (NF->FF) through the C-ABI.
+
+Oracle = outputs of the unmodified reference (tests/golden) and oracle/farfield_oracle.py.
+Tolerance: north_star's 1e-5 (max|dP|/max|P_ref| over finite bins, identical NaN masks).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import apertures
+from parity import FF_TOL, field_error, power_map_error
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+WL = 532e-9
+NG = apertures.N_GLASS[532]
+
+CASES = {
+    "kat1_uniform": lambda: apertures.uniform(128, WL, NG),
+    "kat2_disc": lambda: apertures.disc(128, WL, NG),
+    "kat3_tilted": lambda: apertures.tilted_te(128, WL, NG),
+    "rand128_seed0": lambda: apertures.gaussian_random(128, 0, WL),
+    "rand_48x40_seed5": lambda: apertures.gaussian_random(48, 5, WL, My=40),
+    "rand_45x27_seed6": lambda: apertures.gaussian_random(45, 6, WL, My=27),
+    "lens256_seed1": lambda: apertures.focusing_lens(256, 1, WL, NG),
+    "lens256_seed1_rot": lambda: apertures.focusing_lens(256, 1, WL, NG, rotate=True),
+}
+
+
+def golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, "farfield_%s.npz" % name))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_dropin_farfield_from_nearfield(name, golden_dir):
+    """Reference signature: FFT'd fields in, reference return tuple out."""
+    from metalens_b200.farfield import farfield_from_nearfield
+    g = golden(golden_dir, name)
+    Ex, Ey, Hx, Hy, x, y = CASES[name]()
+    f = [np.fft.fft2(np.fft.fftshift(a.astype(complex))) for a in (Ex, Ey, Hx, Hy)]
+    P, total, ux, uy, dux, duy = farfield_from_nearfield(f[0], f[1], f[2], f[3], list(x), list(y), WL, NG)
+    assert P.dtype == np.float64 and P.shape == g["P"].shape
+    assert power_map_error(P, g["P"]) < FF_TOL
+    assert abs(total - g["total_P"]) <= FF_TOL * abs(g["total_P"])
+    assert ux.shape == (len(x), 1) and uy.shape == (1, len(y))
+    np.testing.assert_array_equal(ux.ravel(), g["ux"])
+    np.testing.assert_array_equal(uy.ravel(), g["uy"])
+    assert dux == g["dux"] and duy == g["duy"]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fields_to_farfield_all_bins(name, golden_dir):
+    """Aperture sum on the GPU (dense tiled reduction) on the reference's full FFT-bin grid,
+    including odd and non-square apertures."""
+    from metalens_b200.farfield import farfield_from_fields
+    g = golden(golden_dir, name)
+    Ex, Ey, Hx, Hy, x, y = CASES[name]()
+    P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=1)
+    assert power_map_error(P, g["P"]) < FF_TOL
+    assert abs(total - g["total_P"]) <= FF_TOL * abs(g["total_P"])
+    np.testing.assert_array_equal(ux.ravel(), g["ux"])
+
+
+@pytest.mark.parametrize("method", ["dense", "fold"])
+@pytest.mark.parametrize("name,stride", [("rand128_seed0", 4), ("lens256_seed1", 8), ("lens256_seed1_rot", 2),
+                                         ("rand_48x40_seed5", (4, 2))])
+def test_strided_bins(name, stride, method, golden_dir):
+    """BASELINE configs 2/3 shape: K < M, far-field grid = every s-th fftshifted reference bin."""
+    from metalens_b200.farfield import farfield_from_fields
+    g = golden(golden_dir, name)
+    Ex, Ey, Hx, Hy, x, y = CASES[name]()
+    sx, sy = (stride, stride) if np.isscalar(stride) else stride
+    P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=stride, method=method,
+                                                      p_dtype=torch.float32)
+    ref = g["P"][::sx, ::sy]
+    assert P.dtype == np.float32
+    assert power_map_error(P, ref) < FF_TOL
+    ref_total = ref[np.isfinite(ref)].sum() * dux * duy
+    assert abs(total - ref_total) <= FF_TOL * abs(ref_total)
+
+
+def test_arbitrary_direction_cosine_grid():
+    """A4: direct sum onto a grid that is NOT a subset of the FFT bins."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import farfield_from_fields
+    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(96, 11, WL, My=70)
+    ux = np.linspace(-0.83, 0.91, 53)
+    uy = np.linspace(-0.5, 0.77, 38)
+    ux[7] = 0.0
+    uy[5] = 0.0                                  # exercise the exact-DC special case
+    P, total, *_ = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, ux=ux, uy=uy)
+    P_ref, _ = fo.farfield_dense(Ex, Ey, Hx, Hy, x[1] - x[0], y[1] - y[0], ux, uy, WL, NG)
+    assert power_map_error(P, P_ref) < FF_TOL
+
+
+def test_complex_amplitudes_match_fft():
+    """The aperture sums themselves (not only P) equal fft2(fftshift(.)) -- phase origin (Q4)."""
+    from metalens_b200.farfield import FarfieldPlan
+    for M, My, seed in ((64, 64, 3), (45, 27, 6)):
+        fields = apertures.gaussian_random(M, seed, WL, My=My)
+        x, y = fields[4], fields[5]
+        plan = FarfieldPlan((M, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=1, method="dense")
+        dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in fields[:4]]
+        plan.run(dev)
+        amps = plan.amplitudes().cpu().numpy()
+        for k in range(4):
+            ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(fields[k].astype(complex))))
+            assert field_error(amps[k], ref) < 2e-6
+
+
+def test_cgemm_tn_ragged_shapes():
+    """C[r][c] = sum_k At[k][r] B[k][c] against torch for ragged sizes, both tile configs."""
+    import ctypes as C
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for rows, cols, depth, batch in ((1, 1, 1, 1), (33, 17, 5, 2), (130, 257, 77, 4), (640, 1280, 100, 4),
+                                     (129, 64, 16, 3)):
+        lda, ldb, ldc = rows + (rows & 1) + 2, cols + (cols & 1), cols + (cols & 1) + 4
+        At = [torch.randn(depth, lda, dtype=torch.complex64, generator=g).cuda() for _ in range(batch)]
+        B = torch.randn(depth, ldb, dtype=torch.complex64, generator=g).cuda()
+        Cs = [torch.full((rows, ldc), 7 + 7j, dtype=torch.complex64).cuda() for _ in range(batch)]
+        pa, k1 = _lib.ptr_array(At)
+        pc, k2 = _lib.ptr_array(Cs)
+        rc = lib.mlb_cgemm_tn(pa, lda, B.data_ptr(), ldb, pc, ldc, rows, cols, depth, batch,
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "mlb_cgemm_tn")
+        torch.cuda.synchronize()
+        for b in range(batch):
+            ref = (At[b][:, :rows].to(torch.complex128).T @ B[:, :cols].to(torch.complex128))
+            got = Cs[b][:, :cols].to(torch.complex128)
+            err = (got - ref).abs().max().item() / ref.abs().max().item()
+            assert err < 5e-6, (rows, cols, depth, b, err)
+            assert torch.all(Cs[b][:, cols:] == 7 + 7j)          # pitch padding untouched
+
+
+def test_cgemm_rejects_bad_arguments():
+    import ctypes as C
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    A = [torch.zeros(4, 3, dtype=torch.complex64).cuda()]
+    pa, k1 = _lib.ptr_array(A)
+    rc = lib.mlb_cgemm_tn(pa, 3, A[0].data_ptr(), 3, pa, 3, 3, 3, 4, 1, None)
+    assert rc != 0 and b"even" in lib.mlb_last_error()
+    with pytest.raises(_lib.MetalensB200Error):
+        _lib.check(rc, "mlb_cgemm_tn")
+
+
+def test_fold_matches_numpy():
+    import ctypes as C
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    for (M1, M2, s1, s2) in ((16, 24, 4, 2), (30, 21, 3, 7), (64, 64, 1, 4)):
+        K1, K2 = M1 // s1, M2 // s2
+        h1, h2 = M1 // 2, M2 // 2
+        J = [(rng.standard_normal((M1, M2)) + 1j * rng.standard_normal((M1, M2))).astype(np.complex64) for _ in range(4)]
+        ldj, ldg = M2 + (M2 & 1), K2 + (K2 & 1)
+        dJ = [torch.zeros(M1, ldj, dtype=torch.complex64).cuda() for _ in range(4)]
+        for d, a in zip(dJ, J):
+            d[:, :M2].copy_(torch.from_numpy(a))
+        dG = [torch.zeros(K1, ldg, dtype=torch.complex64).cuda() for _ in range(4)]
+        pj, k1 = _lib.ptr_array(dJ)
+        pg, k2 = _lib.ptr_array(dG)
+        rc = lib.mlb_fold(pj, ldj, M1, M2, s1, s2, h1, h2, pg, ldg, 4, None)
+        _lib.check(rc, "mlb_fold")
+        torch.cuda.synchronize()
+        for a, d in zip(J, dG):
+            r = np.roll(a.astype(complex), (h1, h2), axis=(0, 1))      # r[p] = a[p - h]
+            ref = r.reshape(s1, K1, s2, K2).sum(axis=(0, 2))
+            assert field_error(d[:, :K2].cpu().numpy(), ref) < 1e-6
+
+
+def test_twiddle_float64_phase_accuracy():
+    """H1: phases of ~1e4 rad must still be accurate to fp32 rounding."""
+    from metalens_b200.farfield import FarfieldPlan
+    M = 4096
+    d = WL / 2.2
+    plan = FarfieldPlan((M, 8), d, d, WL, NG, stride=(64, 1), method="dense")
+    x_rel = (np.arange(M) - M // 2) * d
+    ref = np.exp(-1j * (2 * np.pi * NG / WL) * np.outer(x_rel, plan.ux))
+    got = plan.AxT[:, :plan.Kx].cpu().numpy()
+    assert np.abs(got - ref).max() < 1.5e-7
+
+
+def test_grid_violations_raise_like_reference():
+    from metalens_b200.farfield import farfield_from_nearfield, farfield_from_fields
+    x = np.arange(16) * 1e-7
+    F = np.zeros((16, 16), complex)
+    with pytest.raises(AssertionError):
+        farfield_from_nearfield(F, F, F, F, x * 10, x, WL, NG)           # spacing >= lambda/2
+    with pytest.raises(AssertionError):
+        farfield_from_nearfield(F[:8], F, F, F, x, x, WL, NG)            # shape mismatch
+    bad = x.copy(); bad[5] += 2e-9
+    with pytest.raises(AssertionError):
+        farfield_from_fields(F, F, F, F, bad, x, WL, NG)                 # non-uniform
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 (2048^2 -> 512^2): fold and dense paths agree; a sample of bins equals the
+    float64 direct sum (oracle); linearity of the aperture sums."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import FarfieldPlan
+    M, s = 2048, 4
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 1, WL, NG)
+    d = x[1] - x[0]
+    dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+    fold = FarfieldPlan((M, M), d, d, WL, NG, stride=s, method="fold")
+    dense = FarfieldPlan((M, M), d, d, WL, NG, stride=s, method="dense")
+    Pf, tf = fold.run(dev)
+    Pd, td = dense.run(dev)
+    Pf, Pd = Pf.cpu().numpy(), Pd.cpu().numpy()
+    assert power_map_error(Pf, Pd) < FF_TOL
+    assert abs(tf.item() - td.item()) <= FF_TOL * abs(td.item())
+    # oracle at a sample of bins (float64 direct sum over the whole aperture)
+    ii = np.array([0, 17, 200, 255, 256, 257, 300, 511])
+    jj = np.array([3, 128, 256, 260, 400])
+    P_ref, _ = fo.farfield_dense(Ex, Ey, Hx, Hy, d, d, fold.ux[ii], fold.uy[jj], WL, NG)
+    scale = np.nanmax(Pd)
+    sub_f, sub_d = Pf[np.ix_(ii, jj)], Pd[np.ix_(ii, jj)]
+    assert np.array_equal(np.isnan(sub_f), np.isnan(P_ref))
+    fin = np.isfinite(P_ref)
+    assert np.abs(sub_f - P_ref)[fin].max() / scale < FF_TOL
+    assert np.abs(sub_d - P_ref)[fin].max() / scale < FF_TOL
+    # KAT: energy conservation of the lens aperture, total_P / P_in ~ 1
+    P_in = float((Ex * np.conj(Hy) - Ey * np.conj(Hx)).real.sum()) * d * d
+    assert abs(tf.item() / P_in - 1) < 5e-3
+    # linearity: F(2a + b) = 2F(a) + F(b) on the aperture sums
+    a1 = fold.amplitudes().clone()
+    rot = [torch.from_numpy(a).cuda() for a in apertures.focusing_lens(M, 1, WL, NG, rotate=True)[:4]]
+    fold.run(rot)
+    a2 = fold.amplitudes().clone()
+    mix = [2 * p + q for p, q in zip(dev, rot)]
+    fold.run(mix)
+    a3 = fold.amplitudes()
+    err = (a3 - (2 * a1 + a2)).abs().max().item() / a3.abs().max().item()
+    assert err < 1e-5
