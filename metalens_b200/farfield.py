@@ -253,7 +253,7 @@ class FarfieldPlan:
                 pin[i] = a                  # dtype conversion to complex64 happens here
             src = self._pin_in
         self._dev_in[:, :, :self.My].copy_(src, non_blocking=True)
-        P, total = self.run([self._dev_in[i] for i in range(4)])
+        P, total = self.run([self._dev_in[i][:, :self.My] for i in range(4)])
         self._p_host.copy_(P, non_blocking=True)
         self._t_host.copy_(total, non_blocking=True)
         torch.cuda.current_stream().synchronize()
