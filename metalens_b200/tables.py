@@ -1,0 +1,107 @@
+"""Amplitude tables: the input contract of the aperture-field assembly.
+
+The reference wraps every ``(wavelength_nm, (ox,oy), pol, amp)`` table in a scipy
+``RegularGridInterpolator`` (grating.py:1227-1229, lens_center.py:222-223) and
+``build_nearfield`` calls those objects on ``(n,3)`` point arrays (nearfield.py:310-311).
+Here the same tables are kept as plain arrays (:class:`AmplitudeTable`, same ``.grid`` /
+``.values`` attributes as the scipy object, so either kind can be handed to
+``build_nearfield``), and flattened into one device-resident pack per collection
+(:class:`TablePack`) that the CUDA kernels gather from.  Calling an
+:class:`AmplitudeTable` evaluates it on the GPU (``mlb_table_eval``).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class AmplitudeTable:
+    """One complex amplitude on a rectilinear (ux, uy, third-axis) grid.
+
+    ``table(points)`` with points of shape (n,3) returns the trilinear interpolant,
+    like the reference's RegularGridInterpolator objects with their default
+    ``method='linear', bounds_error=True``: out-of-range points raise ValueError.
+    """
+
+    def __init__(self, grid, values):
+        self.grid = tuple(np.ascontiguousarray(g, dtype=np.float64) for g in grid)
+        self.values = np.ascontiguousarray(values, dtype=np.complex128)
+        assert self.values.shape == tuple(g.size for g in self.grid)
+        for g in self.grid:
+            assert g.size >= 2 and np.all(np.diff(g) > 0), "grid axes must be strictly ascending"
+        self._dev = None
+
+    def _device_arrays(self):
+        if self._dev is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            axes = torch.from_numpy(np.concatenate(self.grid)).to(dev)
+            vals = torch.from_numpy(self.values.reshape(-1)).to(dev)
+            self._dev = (axes, vals)
+        return self._dev
+
+    def __call__(self, xi):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
+        pts = np.ascontiguousarray(xi, dtype=np.float64)
+        lead = pts.shape[:-1]
+        pts = pts.reshape(-1, 3)
+        for d in range(3):
+            lo, hi = self.grid[d][0], self.grid[d][-1]
+            if pts.size and (pts[:, d].min() < lo or pts[:, d].max() > hi):
+                raise ValueError("One of the requested xi is out of bounds in dimension %d" % d)
+        axes, vals = self._device_arrays()
+        dpts = torch.from_numpy(pts).to(axes.device)
+        out = torch.empty(pts.shape[0], dtype=torch.complex128, device=axes.device)
+        n = [g.size for g in self.grid]
+        rc = lib.mlb_table_eval(axes.data_ptr(), n[0], n[1], n[2], vals.data_ptr(), dpts.data_ptr(),
+                                pts.shape[0], out.data_ptr(), _stream_ptr())
+        _lib.check(rc, "mlb_table_eval")
+        return out.cpu().numpy().reshape(lead)
+
+
+def orders_of(grating_list):
+    """The (ox,oy) set of nearfield.py:264 / :390, built with the same expression so that
+    its iteration order matches the reference's within one process."""
+    return {(e['ox'], e['oy']) for g in grating_list for e in g.data}
+
+
+class TablePack:
+    """Flattened tables of ONE GratingCollection / HexGridSet for the assembly kernel.
+
+    Layout (all float64 / complex128, contiguous):
+      axes   : ux nodes | uy nodes | third-axis nodes
+      values : [order][iu][iv][ig][slot]  with slot = 2*pol + amp,
+               pol: 0='x', 1='y'; amp: 0='ampfy', 1='ampfx'
+               (the 4 complex values one interpolation corner needs are 64 contiguous bytes)
+      orders : int32 [n_orders][2] in the reference's iteration order
+    """
+    SLOTS = (('x', 'ampfy'), ('x', 'ampfx'), ('y', 'ampfy'), ('y', 'ampfx'))
+
+    def __init__(self, owner, wavelength_in_nm):
+        self.orders = list(orders_of(owner.grating_list))
+        grid = None
+        blocks = []
+        for (ox, oy) in self.orders:
+            slot_vals = []
+            for pol, amp in self.SLOTS:
+                f = owner.interpolators[(wavelength_in_nm, (ox, oy), pol, amp)]
+                g = tuple(np.asarray(a, dtype=np.float64) for a in f.grid)
+                if grid is None:
+                    grid = g
+                else:
+                    assert all(np.array_equal(a, b) for a, b in zip(grid, g)), "tables of one collection share axes"
+                slot_vals.append(np.asarray(f.values, dtype=np.complex128))
+            blocks.append(np.stack(slot_vals, axis=-1))            # [iu][iv][ig][slot]
+        self.grid = grid
+        self.n = tuple(a.size for a in grid)
+        self.values = np.ascontiguousarray(np.stack(blocks, axis=0))   # [order][iu][iv][ig][slot]
+        self.bounds = tuple(float(b) for b in owner.interpolator_bounds)
+        self.axes = np.concatenate(grid)
+        self.order_array = np.asarray(self.orders, dtype=np.int32).reshape(-1, 2)
