@@ -100,6 +100,75 @@ int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const double *ux, con
 /* out[0] = scale * sum_{i<n} in[i], summed in a fixed order by one block */
 int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream);
 
+/* ---- T1-T4 / B2-B7: amplitude tables and aperture-field assembly ---------------- */
+#define MLB_MAX_PACKS 12
+
+/* Flattened tables of one GratingCollection / HexGridSet (metalens_b200/tables.py):
+ *   axes   : float64  ux[n_ux] | uy[n_uy] | third[n_g]     (third = grating period or index)
+ *   values : complex128 [order][iu][iv][ig][slot], slot = 2*pol + amp
+ *            (pol 0='x',1='y'; amp 0='ampfy',1='ampfx'), i.e. grating.py:1186-1232 /
+ *            lens_center.py:188-226 tables with the four values one corner needs adjacent
+ *   orders : int32 [n_orders][2] = (ox,oy) in the reference's loop order (nearfield.py:264)
+ *   bounds : interpolator_bounds 6-tuple (grating.py:1230-1232)
+ *   stats_slot : first slot of this pack in the `stats` array of mlb_nearfield_assemble */
+typedef struct mlb_table_pack {
+    const double *axes;
+    const double *values;
+    const int *orders;
+    int n_ux, n_uy, n_g, n_orders;
+    double bounds[6];
+    int stats_slot;
+    int _pad;
+} mlb_table_pack;
+
+/* Everything build_nearfield (nearfield.py:66-480) reads, as device arrays + scalars. */
+typedef struct mlb_lens_desc {
+    const double *x_pts, *y_pts;          /* sample coordinates, nx and ny entries          */
+    int nx, ny;
+    /* periphery rings, inside -> out (lens_periphery_summary, design_collimator.py:221-227) */
+    const double *ring_boundary;          /* n_rings+1: r_min_list then lens_max_r (nearfield.py:125) */
+    const double *r_center, *grating_period, *num_around;   /* n_rings each                 */
+    const int *gc_index;                  /* n_rings: gratingcollection_index_here_list     */
+    int n_rings, n_packs;
+    mlb_table_pack packs[MLB_MAX_PACKS];  /* one per GratingCollection                      */
+    /* centre cells (lens_center_summary rows x,y,index), bucketed into a uniform bin grid   */
+    const double *cell_x, *cell_y;        /* n_cells, sorted by bin                         */
+    const int *cell_which, *cell_orig;    /* grating index; original row number (tie-break) */
+    const int *bin_start;                 /* nbx*nby+1 offsets into the sorted cells        */
+    int n_cells, nbx, nby, _pad;
+    double bin_x0, bin_y0, bin_size;
+    mlb_table_pack hex;                   /* HexGridSet tables                              */
+    double hex_x_period, hex_y_period;    /* nearfield.py:391-392                           */
+    /* source (nearfield.py:66-73): point dipole at (sx,sy,sz<0) or plane wave (plane_wave=1) */
+    double source_x, source_y, source_z;
+    int plane_wave, source_pol;           /* pol: 0='x' 1='y' 2='z'                         */
+    double wavelength, n_glass, dipole_moment, c0, Z0;
+} mlb_lens_desc;
+
+#define MLB_STATS_PER_ORDER 8   /* count, min/max ux, min/max uy, min/max third, pad (int64 each) */
+
+/*
+ * Fused build_nearfield: one thread per aperture sample computes ring lookup, incident dipole
+ * field, grating-frame rotation, the diffraction-order loop with trilinear table gathers
+ * (nearfield.py:263-327), propagation phase, rotation back, and the centre region with a
+ * nearest-cell search (:359-466); all in float64.  Output fields are written as complex64
+ * (out_is_double=0) or complex128 (1), row pitch `ld` elements.  power_block_sums receives
+ * mlb_nearfield_blocks() partial sums of Ex_inc*Hy_inc - Ey_inc*Hx_inc over lens points
+ * (:474-477).  violation[0] is set non-zero if any interpolation point lies outside a pack's
+ * bounds (the ValueErrors of :294-305, :412-419); with want_stats=1 the per-(pack,order)
+ * count / min / max needed for the reference's messages are accumulated in `stats`
+ * (int64, order-preserving encoding of doubles; see metalens_b200/nearfield.py).
+ */
+int mlb_nearfield_blocks(int nx, int ny);
+int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
+                           int out_is_double, double *power_block_sums, long long *stats, int want_stats,
+                           int *violation, void *stream);
+
+/* Trilinear gather of ONE table (scipy RegularGridInterpolator linear mode):
+ * axes = u0[n0]|u1[n1]|u2[n2], values complex128 [n0][n1][n2], pts float64 [n][3] -> out complex128 [n] */
+int mlb_table_eval(const double *axes, int n0, int n1, int n2, const double *values, const double *pts, int n,
+                   double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

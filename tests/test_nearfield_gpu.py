@@ -1,0 +1,137 @@
+"""GPU parity tests for hot path B (aperture-field assembly) through the C-ABI.
+
+Oracle = outputs of the unmodified reference's build_nearfield on the synthetic lens
+(tests/golden/nearfield_*.npz) and oracle/nearfield_oracle.py for sizes without a fixture.
+The kernel computes in float64 and the drop-in returns complex128, so the tolerance here is far
+below north_star's 1e-5; the complex64 device output is checked at 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import synth_lens
+from parity import field_error
+from test_oracle_nearfield import CASES, library, periphery_from
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+inf = float("inf")
+
+
+def call(fn, name, golden_dir, **extra):
+    spec, kw = CASES[name]
+    g = np.load(os.path.join(golden_dir, "nearfield_%s.npz" % name))
+    collections, hgs = library(spec)
+    sx, sy, sz = g["source"]
+    explicit = name.endswith("ragged")
+    kw = dict(kw, **extra)
+    res = fn(source_x=sx, source_y=sy, source_z=sz, source_pol=str(g["pol"]), wavelength=float(g["wavelength"]),
+             lens_periphery_summary=periphery_from(g, collections), lens_center_summary=g["center"],
+             hexgridset=hgs, x_pts=g["x_pts"] if explicit else None, y_pts=g["y_pts"] if explicit else None, **kw)
+    return res, g
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_build_nearfield_matches_reference(name, golden_dir):
+    from metalens_b200.nearfield import build_nearfield
+    res, g = call(build_nearfield, name, golden_dir)
+    escale = max(np.abs(g["Ex"]).max(), np.abs(g["Ey"]).max())
+    hscale = max(np.abs(g["Hx"]).max(), np.abs(g["Hy"]).max())
+    for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
+        assert res[k].dtype == np.complex128 and res[k].shape == g[key].shape
+        err = np.abs(res[k] - g[key]).max() / (escale if k < 2 else hscale)
+        assert err < 1e-9, (key, err)
+    np.testing.assert_array_equal(res[4], g["x_pts"])
+    np.testing.assert_array_equal(res[5], g["y_pts"])
+    assert abs(res[6] - g["power"]) <= 1e-11 * abs(g["power"])
+    assert res[7] == g["n_glass"]
+
+
+def test_complex64_device_output_and_big(golden_dir):
+    """The device-resident complex64 output (what feeds NF->FF) and build_nearfield_big."""
+    from metalens_b200.nearfield import NearfieldPlan, build_nearfield_big
+    g = np.load(os.path.join(golden_dir, "nearfield_small_x_ragged.npz"))
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    periph = periphery_from(g, collections)
+    plan = NearfieldPlan(580e-9, periph, g["center"], hgs)
+    out, power = plan.run(0.0, 0.0, float(g["source"][2]), "x", g["x_pts"], g["y_pts"])
+    assert out.dtype == torch.complex64
+    got = out[:, :, :g["y_pts"].size].cpu().numpy()
+    for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
+        assert field_error(got[k], g[key]) < 1e-6
+    assert abs(power.item() - g["power"]) <= 1e-11 * abs(g["power"])
+    res = build_nearfield_big(0.0, 0.0, float(g["source"][2]), "x", 580e-9, periph, g["center"], hgs,
+                              x_pts=g["x_pts"], y_pts=g["y_pts"])
+    for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
+        assert field_error(res[k], g[key]) < 1e-9
+
+
+def test_bounds_violation_raises_reference_valueerror(golden_dir):
+    from metalens_b200.nearfield import build_nearfield
+    e = np.load(os.path.join(golden_dir, "nearfield_error_small_plane.npz"))
+    g = np.load(os.path.join(golden_dir, "nearfield_small_x_onaxis.npz"))
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    with pytest.raises(ValueError) as ei:
+        build_nearfield(0.0, 0.0, -inf, "x", 580e-9, periphery_from(g, collections), g["center"], hgs)
+    assert ei.value.args[0] == str(e["message"])
+    assert ei.value.args[1] == float(e["value"]) and ei.value.args[2] == float(e["bound"])
+
+
+def test_argument_assertions(golden_dir):
+    from metalens_b200 import grating, lens_center
+    from metalens_b200.nearfield import build_nearfield
+    g = np.load(os.path.join(golden_dir, "nearfield_small_x_onaxis.npz"))
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    periph = periphery_from(g, collections)
+    with pytest.raises(AssertionError):
+        build_nearfield(0, 0, +1e-6, "x", 580e-9, periph, g["center"], hgs)          # source_z >= 0
+    with pytest.raises(AssertionError):
+        build_nearfield(0, 0, -1e-5, "q", 580e-9, periph, g["center"], hgs)          # bad polarisation
+    with pytest.raises(AssertionError):
+        build_nearfield(0, 0, -1e-5, "x", 580e-9, periph, g["center"], hgs,
+                        x_pts=np.linspace(-1e-5, 1e-5, 20), y_pts=np.linspace(-1e-5, 1e-5, 20))   # dx > lambda/2
+    # n_glass == 0 -> grating.n_glass(532) is not tabulated -> ValueError('bad wavelength...') (Q6)
+    c0, h0 = synth_lens.make_library(grating, lens_center, synth_lens.SMALL_LENS, n_glass=0)
+    with pytest.raises(ValueError):
+        build_nearfield(0, 0, -1.43e-5, "x", 532e-9, periphery_from(g, c0), g["center"], h0)
+
+
+def test_larger_lens_against_oracle():
+    """A lens without a fixture (wider aperture, off-axis z-polarised source): CUDA vs numpy oracle,
+    and the empty-grid early return."""
+    from oracle import nearfield_oracle as no
+    from metalens_b200 import grating, lens_center
+    from metalens_b200.design import make_design
+    from metalens_b200.nearfield import build_nearfield
+    spec = dict(bands=[(15.0, 25.0, 1000e-9, 0.3), (25.0, 45.0, 650e-9, 1.1)], source_distance=30e-6, radius=29e-6)
+    collections, hgs = synth_lens.make_library(grating, lens_center, spec)
+    periph, center, r_switch = make_design(collections, spec["source_distance"], spec["radius"], hgs)
+    args = (1.1e-6, -0.6e-6, -30e-6, "z", 580e-9, periph, center, hgs)
+    got = build_nearfield(*args)
+    ref = no.build_nearfield(*args)
+    assert got[0].shape == ref[0].shape and got[0].shape[0] >= 216
+    for k in range(4):
+        assert field_error(got[k], ref[k]) < 1e-9
+    assert abs(got[6] - ref[6]) <= 1e-11 * abs(ref[6])
+    far = np.linspace(40e-6, 44e-6, 20)
+    z = build_nearfield(*args, x_pts=far, y_pts=far)
+    assert all(np.all(z[k] == 0) for k in range(4)) and z[6] == 0
+
+
+def test_table_callable_matches_oracle():
+    """T4: an AmplitudeTable is callable like the reference's RegularGridInterpolator."""
+    from oracle import nearfield_oracle as no
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    gc = collections[1][1]
+    key = sorted(gc.interpolators, key=repr)[3]
+    f = gc.interpolators[key]
+    rng = np.random.default_rng(0)
+    lo = np.array([g[0] for g in f.grid]); hi = np.array([g[-1] for g in f.grid])
+    pts = lo + (hi - lo) * rng.random((500, 3))
+    pts[0] = lo; pts[1] = hi; pts[2] = [f.grid[0][2], f.grid[1][1], f.grid[2][3]]      # nodes and corners
+    got = f(pts)
+    ref = no.trilinear(f.grid, f.values, pts)
+    assert np.abs(got - ref).max() <= 1e-14 * np.abs(ref).max()
+    with pytest.raises(ValueError):
+        f(np.array([[hi[0] * 1.01 + 1, lo[1], lo[2]]]))
