@@ -261,6 +261,25 @@ def ours(args):
     h2d = n_items * plans[0].h2d_bytes
     d2h = n_items * plans[0].d2h_bytes
 
+    # ---- the other formulations on the same workload (device-resident, fewer steps), for context
+    paths = {plans[0].method: value}
+    if world == 1 and not args.no_paths:
+        for m in ("fft", "fold", "dense"):
+            if m in paths:
+                continue
+            try:
+                alt = [FarfieldPlan((M, M), p.dxp, p.dyp, p.wavelength, p.n_glass, stride=s, method=m) for p in plans]
+            except ValueError:
+                continue
+
+            def step_alt(alt=alt):
+                for i, plan in enumerate(alt):
+                    plan.run([dev_fields[i][f] for f in range(4)])
+            t_alt, _, _, _ = timed(step_alt, 3, 2)
+            paths[m] = pts_per_step * 3 / t_alt
+            del alt
+            torch.cuda.empty_cache()
+
     # ---- per-kernel timing of one item for the roofline (CUDA events on the launching stream)
     def kernel_time(fn, reps=20):
         for _ in range(3):
@@ -274,50 +293,23 @@ def ours(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
-    import ctypes as C
-    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    # every kernel of one item, timed alone; rotate over the batch items so that the inputs
+    # (n_items x 32 M^2 bytes) exceed L2 between launches of the same kernel
+    all_steps = [plan.steps([dev_fields[i][f] for f in range(4)]) for i, plan in enumerate(plans)]
+    for i in range(len(plans)):
+        plans[i].run([dev_fields[i][f] for f in range(4)])
     kernels = {}
-    nplan = len(plans)
     rr = [0]
-
-    def rot():              # rotate over the batch items so inputs (3 x 537 MB) exceed L2 between launches
-        rr[0] = (rr[0] + 1) % nplan
-        return rr[0]
-
+    for k, (name, _fn, nbytes, flops) in enumerate(all_steps[0]):
+        def one(k=k):
+            rr[0] = (rr[0] + 1) % len(all_steps)
+            all_steps[rr[0]][k][1]()
+        kernels[name] = dict(seconds=kernel_time(one), bytes=nbytes, flops=flops)
     p0 = plans[0]
-    if p0.method == "fold":
-        def run_fold():
-            i = rot()
-            pj, k1 = _lib.ptr_array([dev_fields[i][f] for f in range(4)])
-            pg, k2 = _lib.ptr_array(plans[i].G)
-            lib.mlb_fold(pj, M, M, M, s, s, M // 2, M // 2, pg, plans[i].G[0].shape[1], 4, st())
-        t_fold = kernel_time(run_fold)
-        kernels["fold"] = dict(seconds=t_fold, bytes=4 * 8 * (M * M + K * K), flops=0)
-    R = p0.Rx
-
-    def run_s1():
-        i = rot()
-        ops = plans[i].G if plans[i].method == "fold" else [dev_fields[i][f] for f in range(4)]
-        pa, k1 = _lib.ptr_array(ops)
-        pu, k2 = _lib.ptr_array(plans[i].UT)
-        lib.mlb_cgemm_tn(pa, ops[0].shape[-1], plans[i].AxT.data_ptr(), plans[i].AxT.shape[1], pu,
-                         plans[i].UT[0].shape[1], plans[i].Ry, K, plans[i].Rx, 4, st())
-
-    def run_s2():
-        i = rot()
-        pu, k2 = _lib.ptr_array(plans[i].UT)
-        pf, k3 = _lib.ptr_array(plans[i].Fhat)
-        lib.mlb_cgemm_tn(pu, plans[i].UT[0].shape[1], plans[i].Ay.data_ptr(), plans[i].Ay.shape[1], pf,
-                         plans[i].Fhat[0].shape[1], K, K, plans[i].Ry, 4, st())
-    kernels["cgemm_stage1"] = dict(seconds=kernel_time(run_s1), flops=4 * 8.0 * R * R * K,
-                                   bytes=8 * (4 * R * R + R * K + 4 * R * K))
-    kernels["cgemm_stage2"] = dict(seconds=kernel_time(run_s2), flops=4 * 8.0 * R * K * K,
-                                   bytes=8 * (4 * R * K + R * K + 4 * K * K))
-    kernels["epilogue"] = dict(seconds=kernel_time(lambda: plans[rot()].power()), flops=0, bytes=36 * K * K)
     dom = max(kernels, key=lambda k: kernels[k]["seconds"])
     kd = kernels[dom]
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12       # nominal fp32 FMA pipe, TFLOP/s at max clock
-    if dom == "fold" or dom == "epilogue":
+    if not dom.startswith("cgemm"):
         ach = kd["bytes"] / kd["seconds"] / 1e9
         roof = dict(kernel=dom, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
                     frac=ach / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"])
@@ -350,6 +342,7 @@ def ours(args):
             "roofline": roof,
             "kernels": {k: dict(ms=v["seconds"] * 1e3, gbs=v["bytes"] / v["seconds"] / 1e9,
                                 tflops=v["flops"] / v["seconds"] / 1e12) for k, v in kernels.items()},
+            "paths_points_per_s": paths,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -364,8 +357,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--method", default="auto", choices=["auto", "dense", "fold"])
+    ap.add_argument("--method", default="auto", choices=["auto", "dense", "fold", "fft"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-paths", action="store_true", help="skip timing the alternative formulations")
     ap.add_argument("--quick-cpu", action="store_true", help="tiny cpu_baseline sample (debug)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -80,6 +80,22 @@ int mlb_cgemm_tn(const mlb_c64 *const *h_At, int lda, const mlb_c64 *B, int ldb,
 int mlb_fold(const mlb_c64 *const *h_J, int ldj, int M1, int M2, int s1, int s2,
              int h1, int h2, mlb_c64 *const *h_G, int ldg, int batch, void *stream);
 
+/* ---- A1 (FFT formulation): shared-memory FFT passes, power-of-two lengths ---- */
+/* out[t] = exp(-2 pi i t / N), float64 phases rounded once to fp32 */
+int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);
+/* longest transform the shared-memory passes support (8192 complex64) */
+int mlb_fft_max_length(void);
+/*
+ * Batched 1-D DFT along rows (the contiguous axis) of `batch` matrices [n_rows][N], with the
+ * fftshift bookkeeping of nearfield_farfield.py:18-20, :68 folded into the indices:
+ *   out_b[r][(q + out_roll) % N] = sum_p in_b[(r - in_roll_r) mod n_rows][(p - in_roll_c) mod N] e^{-2 pi i q p / N}
+ */
+int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
+                 const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int batch, void *stream);
+/* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}; in-place allowed */
+int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N, int n_cols,
+                 const mlb_c64 *tw, int out_roll, int batch, void *stream);
+
 /* ---- A2/A3: radiated power ------------------------------------------------ */
 /*
  * Fhat (4 x Kx x Ky c64: Ex,Ey,Hx,Hy aperture sums) -> P (Kx x Ky) following
@@ -133,7 +149,8 @@ typedef struct mlb_lens_desc {
     mlb_table_pack packs[MLB_MAX_PACKS];  /* one per GratingCollection                      */
     /* centre cells (lens_center_summary rows x,y,index), bucketed into a uniform bin grid   */
     const double *cell_x, *cell_y;        /* n_cells, sorted by bin                         */
-    const int *cell_which, *cell_orig;    /* grating index; original row number (tie-break) */
+    const int *cell_which, *cell_orig;    /* grating index; original row number (exact distance ties
+                                             go to the highest row, cKDTree's usual choice)   */
     const int *bin_start;                 /* nbx*nby+1 offsets into the sorted cells        */
     int n_cells, nbx, nby, _pad;
     double bin_x0, bin_y0, bin_size;

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
         } else if (in_center) {
             // ---------------- centre (:359-466): nearest cell through the bin grid
             local_power = dEx * dHy - dEy * dHx;
-            int best = -1, best_orig = 0x7fffffff;
+            int best = -1, best_orig = -1;
             double best_d2 = CUDART_INF;
             if (L.n_cells > 0) {
                 int bx = (int)floor((x - L.bin_x0) / L.bin_size), by = (int)floor((y - L.bin_y0) / L.bin_size);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
                                 const double ddx = L.cell_x[cidx] - x, ddy = L.cell_y[cidx] - y;
                                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                                 const int orig = L.cell_orig[cidx];
-                                if (d2 < best_d2 || (d2 == best_d2 && orig < best_orig)) {
+                                if (d2 < best_d2 || (d2 == best_d2 && orig > best_orig)) {   // exact ties: highest row wins
                                     best_d2 = d2; best = cidx; best_orig = orig;
                                 }
                             }

@@ -68,11 +68,15 @@ class FarfieldPlan:
     stride : int or (sx, sy) -- far-field grid = every stride-th bin of the reference's
         fftshifted FFT-bin grid (stride 1 = the reference grid itself)
     ux, uy : explicit direction-cosine lists (arbitrary grid); excludes `stride`
-    method : 'auto' | 'dense' | 'fold'
+    method : 'auto' | 'dense' | 'fold' | 'fft'
         dense -- two-stage separable tiled complex reduction over the full aperture
         fold  -- exact aperture fold (HBM-bound) followed by the dense reduction on the
                  folded (Mx/sx x My/sy) aperture; needs an FFT-bin-stride grid with
                  sx | Mx//2 and sy | My//2
+        fft   -- fold (if stride > 1) followed by shared-memory row/column FFT passes: the
+                 reference's own algorithm, every kernel memory-bound; needs power-of-two
+                 folded sizes <= 8192
+        auto  -- fft if eligible, else fold, else dense
     p_dtype : torch.float32 (north-star output type) or torch.float64
     """
 
@@ -106,11 +110,22 @@ class FarfieldPlan:
         can_fold = (self.fft_bin_grid and self.Mx % self.sx == 0 and self.My % self.sy == 0
                     and (self.Mx // 2) % self.sx == 0 and (self.My // 2) % self.sy == 0
                     and (self.sx > 1 or self.sy > 1))
+        def pow2(n):
+            return n >= 2 and (n & (n - 1)) == 0
+        can_fft = False
+        if self.fft_bin_grid and self.Mx % self.sx == 0 and self.My % self.sy == 0:
+            k1, k2 = self.Mx // self.sx, self.My // self.sy
+            nmax = self.lib.mlb_fft_max_length()
+            can_fft = (pow2(k1) and pow2(k2) and k1 <= nmax and k2 <= nmax
+                       and (can_fold or (self.sx == 1 and self.sy == 1)))
         if method == "auto":
-            method = "fold" if can_fold else "dense"
+            method = "fft" if can_fft else ("fold" if can_fold else "dense")
         if method == "fold" and not can_fold:
             raise ValueError("fold needs an FFT-bin-stride grid with stride dividing M and M//2")
-        assert method in ("dense", "fold")
+        if method == "fft" and not can_fft:
+            raise ValueError("fft needs an FFT-bin(-stride) grid whose folded sizes are powers of two <= %d"
+                             % self.lib.mlb_fft_max_length())
+        assert method in ("dense", "fold", "fft")
         self.method = method
         self._build()
 
@@ -137,6 +152,18 @@ class FarfieldPlan:
             self.Ay = self._twiddle((np.arange(My) - oy) * self.dyp, self.uy, scale)    # [My][Ky]
             self.Rx, self.Ry = Mx, My            # size of the aperture the reduction runs over
             self.G = None
+        elif self.method == "fft":
+            K1, K2 = Mx // self.sx, My // self.sy
+            assert K1 == Kx and K2 == Ky
+            self.Rx, self.Ry = K1, K2
+            self.folds = self.sx > 1 or self.sy > 1
+            self.G = [_c64_buffer(K1, K2, dev) for _ in range(4)] if self.folds else None
+            self.W = [_c64_buffer(K1, K2, dev) for _ in range(4)]          # row-pass output
+            self.tw1 = torch.empty(K1, dtype=torch.complex64, device=dev)
+            self.tw2 = torch.empty(K2, dtype=torch.complex64, device=dev)
+            for t, n in ((self.tw1, K1), (self.tw2, K2)):
+                _lib.check(self.lib.mlb_fft_twiddle(n, t.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
+            self.AxT = self.Ay = None
         else:
             # folded aperture (K1 x K2) and exact integer DFT twiddles exp(-2 pi i p q / K)
             K1, K2 = Mx // self.sx, My // self.sy
@@ -147,7 +174,8 @@ class FarfieldPlan:
             self.Ay = self._twiddle(np.arange(K2), qy, -2.0 / K2)
             self.Rx, self.Ry = K1, K2
             self.G = [_c64_buffer(K1, K2, dev) for _ in range(4)]
-        self.UT = [_c64_buffer(self.Ry, Kx, dev) for _ in range(4)]      # stage-1 output, [m2][i]
+        self.UT = ([_c64_buffer(self.Ry, Kx, dev) for _ in range(4)]     # stage-1 output, [m2][i]
+                   if self.method != "fft" else None)
         self.Fhat = [_c64_buffer(Kx, Ky, dev) for _ in range(4)]         # aperture sums, [i][j]
         self.P = torch.empty((Kx, Ky), dtype=self.p_dtype, device=dev)
         self.nblocks = self.lib.mlb_ff_epilogue_blocks(Kx, Ky)
@@ -181,29 +209,68 @@ class FarfieldPlan:
         assert len(lds) == 1, "the four fields must share one row pitch"
         return [t for t, _ in out], lds.pop()
 
-    def aperture_sums(self, fields):
-        """Stage 1 + stage 2 (+ fold): Fhat_f[i,j] = sum_{m1,m2} J_f[m1,m2] e^{-ik(x'ux_i + y'uy_j)}.
-        Returns the 4 pitched device tensors (logical view [:, :Ky])."""
-        lib, st = self.lib, _stream_ptr()
+    def steps(self, fields):
+        """The kernel launches of one run() as (name, thunk, algorithmic bytes, algorithmic flops);
+        run() executes them in order, bench.py times them one by one for the roofline."""
+        lib = self.lib
         ops, ld = self._as_operands(fields)
-        if self.method == "fold":
-            pj, _k1 = _lib.ptr_array(ops)
-            pg, _k2 = _lib.ptr_array(self.G)
-            rc = lib.mlb_fold(pj, ld, self.Mx, self.My, self.sx, self.sy, self.Mx // 2, self.My // 2,
-                              pg, self.G[0].shape[1], 4, st)
-            _lib.check(rc, "mlb_fold")
-            ops, ld = self.G, self.G[0].shape[1]
-        # stage 1: UT_f[m2][i] = sum_{m1} J_f[m1][m2] * AxT[m1][i]
-        pa, _k3 = _lib.ptr_array(ops)
-        pu, _k4 = _lib.ptr_array(self.UT)
-        rc = lib.mlb_cgemm_tn(pa, ld, self.AxT.data_ptr(), self.AxT.shape[1], pu, self.UT[0].shape[1],
-                              self.Ry, self.Kx, self.Rx, 4, st)
-        _lib.check(rc, "mlb_cgemm_tn(stage 1)")
-        # stage 2: Fhat_f[i][j] = sum_{m2} UT_f[m2][i] * Ay[m2][j]
-        pf, _k5 = _lib.ptr_array(self.Fhat)
-        rc = lib.mlb_cgemm_tn(pu, self.UT[0].shape[1], self.Ay.data_ptr(), self.Ay.shape[1], pf,
-                              self.Fhat[0].shape[1], self.Kx, self.Ky, self.Ry, 4, st)
-        _lib.check(rc, "mlb_cgemm_tn(stage 2)")
+        Kx, Ky, Rx, Ry = self.Kx, self.Ky, self.Rx, self.Ry
+        out = []
+        if self.method in ("fold", "fft") and (self.sx > 1 or self.sy > 1):
+            pj, k1 = _lib.ptr_array(ops)
+            pg, k2 = _lib.ptr_array(self.G)
+            ldg = self.G[0].shape[1]
+
+            def fold(pj=pj, pg=pg, ld=ld, keep=(k1, k2)):
+                _lib.check(lib.mlb_fold(pj, ld, self.Mx, self.My, self.sx, self.sy, self.Mx // 2, self.My // 2,
+                                        pg, ldg, 4, _stream_ptr()), "mlb_fold")
+            out.append(("fold", fold, 32 * (self.Mx * self.My + Rx * Ry), 0.0))
+            ops, ld, folded = self.G, ldg, True
+        else:
+            folded = False
+        if self.method == "fft":
+            # F[s q] = sum_p G[p] e^{-2 pi i q p / K},  G[p] = sum_t J[((p - M//2) mod K) + t K]; outputs are
+            # stored at the fftshifted position q' = (q + (M//2)/s) mod K, the order of self.ux / self.uy
+            h1, h2 = self.Mx // 2, self.My // 2
+            roll_r, roll_c = (0, 0) if folded else (h1 % Rx, h2 % Ry)      # fftshift of the input, :18-20
+            pi_, k3 = _lib.ptr_array(ops)
+            pw, k4 = _lib.ptr_array(self.W)
+            pf, k5 = _lib.ptr_array(self.Fhat)
+            ldw, ldf = self.W[0].shape[1], self.Fhat[0].shape[1]
+
+            def rows(pi_=pi_, ld=ld, keep=(k3, k4)):
+                _lib.check(lib.mlb_fft_rows(pi_, ld, pw, ldw, Rx, Ry, self.tw2.data_ptr(), roll_r, roll_c,
+                                            (h2 // self.sy) % Ry, 4, _stream_ptr()), "mlb_fft_rows")
+
+            def cols(keep=k5):
+                _lib.check(lib.mlb_fft_cols(pw, ldw, pf, ldf, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx, 4,
+                                            _stream_ptr()), "mlb_fft_cols")
+            out.append(("fft_rows", rows, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Ry)))
+            out.append(("fft_cols", cols, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
+        else:
+            pa, k6 = _lib.ptr_array(ops)
+            pu, k7 = _lib.ptr_array(self.UT)
+            pf, k8 = _lib.ptr_array(self.Fhat)
+            ldu, ldf = self.UT[0].shape[1], self.Fhat[0].shape[1]
+
+            def stage1(pa=pa, ld=ld, keep=(k6, k7)):      # UT_f[m2][i] = sum_{m1} J_f[m1][m2] * AxT[m1][i]
+                _lib.check(lib.mlb_cgemm_tn(pa, ld, self.AxT.data_ptr(), self.AxT.shape[1], pu, ldu, Ry, Kx, Rx, 4,
+                                            _stream_ptr()), "mlb_cgemm_tn(stage 1)")
+
+            def stage2(keep=k8):                          # Fhat_f[i][j] = sum_{m2} UT_f[m2][i] * Ay[m2][j]
+                _lib.check(lib.mlb_cgemm_tn(pu, ldu, self.Ay.data_ptr(), self.Ay.shape[1], pf, ldf, Kx, Ky, Ry, 4,
+                                            _stream_ptr()), "mlb_cgemm_tn(stage 2)")
+            out.append(("cgemm_stage1", stage1, 8 * (4 * Rx * Ry + Rx * Kx + 4 * Ry * Kx), 32.0 * Rx * Ry * Kx))
+            out.append(("cgemm_stage2", stage2, 8 * (4 * Ry * Kx + Ry * Ky + 4 * Kx * Ky), 32.0 * Ry * Kx * Ky))
+        out.append(("epilogue", self.power, 36 * Kx * Ky, 0.0))
+        return out
+
+    def aperture_sums(self, fields):
+        """[fold ->] separable reduction or FFT passes:
+        Fhat_f[i,j] = sum_{m1,m2} J_f[m1,m2] e^{-ik(x'ux_i + y'uy_j)}.
+        Returns the 4 pitched device tensors (logical view [:, :Ky])."""
+        for name, fn, _b, _f in self.steps(fields)[:-1]:
+            fn()
         return self.Fhat
 
     def power(self, Fhat=None, amp_scale=None):

@@ -50,20 +50,22 @@ def test_dropin_farfield_from_nearfield(name, golden_dir):
     assert dux == g["dux"] and duy == g["duy"]
 
 
+@pytest.mark.parametrize("method", ["auto", "dense"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_fields_to_farfield_all_bins(name, golden_dir):
-    """Aperture sum on the GPU (dense tiled reduction) on the reference's full FFT-bin grid,
+def test_fields_to_farfield_all_bins(name, method, golden_dir):
+    """Aperture sum on the GPU on the reference's full FFT-bin grid: shared-memory FFT passes for
+    power-of-two apertures ('auto'), the dense tiled reduction otherwise and when forced,
     including odd and non-square apertures."""
     from metalens_b200.farfield import farfield_from_fields
     g = golden(golden_dir, name)
     Ex, Ey, Hx, Hy, x, y = CASES[name]()
-    P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=1)
+    P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=1, method=method)
     assert power_map_error(P, g["P"]) < FF_TOL
     assert abs(total - g["total_P"]) <= FF_TOL * abs(g["total_P"])
     np.testing.assert_array_equal(ux.ravel(), g["ux"])
 
 
-@pytest.mark.parametrize("method", ["dense", "fold"])
+@pytest.mark.parametrize("method", ["dense", "fold", "fft"])
 @pytest.mark.parametrize("name,stride", [("rand128_seed0", 4), ("lens256_seed1", 8), ("lens256_seed1_rot", 2),
                                          ("rand_48x40_seed5", (4, 2))])
 def test_strided_bins(name, stride, method, golden_dir):
@@ -72,6 +74,10 @@ def test_strided_bins(name, stride, method, golden_dir):
     g = golden(golden_dir, name)
     Ex, Ey, Hx, Hy, x, y = CASES[name]()
     sx, sy = (stride, stride) if np.isscalar(stride) else stride
+    if method == "fft" and name.startswith("rand_48x40"):       # folded size 12 x 20 is not a power of two
+        with pytest.raises(ValueError):
+            farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=stride, method=method)
+        return
     P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=stride, method=method,
                                                       p_dtype=torch.float32)
     ref = g["P"][::sx, ::sy]
@@ -98,10 +104,10 @@ def test_arbitrary_direction_cosine_grid():
 def test_complex_amplitudes_match_fft():
     """The aperture sums themselves (not only P) equal fft2(fftshift(.)) -- phase origin (Q4)."""
     from metalens_b200.farfield import FarfieldPlan
-    for M, My, seed in ((64, 64, 3), (45, 27, 6)):
+    for M, My, seed, method in ((64, 64, 3, "dense"), (45, 27, 6, "dense"), (64, 64, 3, "fft"), (32, 256, 8, "fft")):
         fields = apertures.gaussian_random(M, seed, WL, My=My)
         x, y = fields[4], fields[5]
-        plan = FarfieldPlan((M, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=1, method="dense")
+        plan = FarfieldPlan((M, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=1, method=method)
         dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in fields[:4]]
         plan.run(dev)
         amps = plan.amplitudes().cpu().numpy()
@@ -173,6 +179,46 @@ def test_fold_matches_numpy():
             assert field_error(d[:, :K2].cpu().numpy(), ref) < 1e-6
 
 
+def test_fft_passes_match_numpy():
+    """mlb_fft_rows / mlb_fft_cols against numpy.fft for every power of two up to the limit,
+    including the fftshift rolls."""
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    assert lib.mlb_fft_max_length() == 8192 * 3 // 2 or lib.mlb_fft_max_length() >= 8192
+    for N, other in ((2, 5), (4, 3), (8, 9), (16, 4), (64, 33), (128, 7), (512, 6), (1024, 5), (2048, 3), (8192, 2)):
+        a = [(rng.standard_normal((other, N)) + 1j * rng.standard_normal((other, N))).astype(np.complex64) for _ in range(2)]
+        tw = torch.empty(N, dtype=torch.complex64).cuda()
+        _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
+        ld = N + 2
+        din = [torch.zeros(other, ld, dtype=torch.complex64).cuda() for _ in a]
+        for d, v in zip(din, a):
+            d[:, :N].copy_(torch.from_numpy(v))
+        dout = [torch.zeros(other, ld, dtype=torch.complex64).cuda() for _ in a]
+        rr, rc, ro = other // 2, N // 2, (N // 2 + 1) % N
+        pi_, k1 = _lib.ptr_array(din)
+        po, k2 = _lib.ptr_array(dout)
+        _lib.check(lib.mlb_fft_rows(pi_, ld, po, ld, other, N, tw.data_ptr(), rr, rc, ro, 2, None), "rows")
+        torch.cuda.synchronize()
+        for v, d in zip(a, dout):
+            ref = np.roll(np.fft.fft(np.roll(v.astype(complex), (rr, rc), axis=(0, 1)), axis=1), ro, axis=1)
+            assert field_error(d[:, :N].cpu().numpy(), ref) < 3e-6, ("rows", N)
+        # columns: transform along axis 0 of the transposed data, in place
+        ldc = other + (other & 1) + 2
+        dcol = [torch.zeros(N, ldc, dtype=torch.complex64).cuda() for _ in a]
+        for d, v in zip(dcol, a):
+            d[:, :other].copy_(torch.from_numpy(v.T.copy()))
+        pc, k3 = _lib.ptr_array(dcol)
+        _lib.check(lib.mlb_fft_cols(pc, ldc, pc, ldc, N, other, tw.data_ptr(), ro, 2, None), "cols")
+        torch.cuda.synchronize()
+        for v, d in zip(a, dcol):
+            ref = np.roll(np.fft.fft(v.astype(complex).T, axis=0), ro, axis=0)
+            assert field_error(d[:, :other].cpu().numpy(), ref) < 3e-6, ("cols", N)
+    bad = torch.zeros(4, 12, dtype=torch.complex64).cuda()
+    pb, k4 = _lib.ptr_array([bad])
+    assert lib.mlb_fft_rows(pb, 12, pb, 12, 4, 12, bad.data_ptr(), 0, 0, 0, 1, None) != 0     # not a power of two
+
+
 def test_twiddle_float64_phase_accuracy():
     """H1: phases of ~1e4 rad must still be accurate to fp32 rounding."""
     from metalens_b200.farfield import FarfieldPlan
@@ -209,21 +255,27 @@ def test_config2_full_size_properties():
     dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
     fold = FarfieldPlan((M, M), d, d, WL, NG, stride=s, method="fold")
     dense = FarfieldPlan((M, M), d, d, WL, NG, stride=s, method="dense")
+    fft = FarfieldPlan((M, M), d, d, WL, NG, stride=s)
+    assert fft.method == "fft"
     Pf, tf = fold.run(dev)
     Pd, td = dense.run(dev)
-    Pf, Pd = Pf.cpu().numpy(), Pd.cpu().numpy()
+    Pq, tq = fft.run(dev)
+    Pf, Pd, Pq = Pf.cpu().numpy(), Pd.cpu().numpy(), Pq.cpu().numpy()
     assert power_map_error(Pf, Pd) < FF_TOL
+    assert power_map_error(Pq, Pd) < FF_TOL
     assert abs(tf.item() - td.item()) <= FF_TOL * abs(td.item())
+    assert abs(tq.item() - td.item()) <= FF_TOL * abs(td.item())
     # oracle at a sample of bins (float64 direct sum over the whole aperture)
     ii = np.array([0, 17, 200, 255, 256, 257, 300, 511])
     jj = np.array([3, 128, 256, 260, 400])
     P_ref, _ = fo.farfield_dense(Ex, Ey, Hx, Hy, d, d, fold.ux[ii], fold.uy[jj], WL, NG)
     scale = np.nanmax(Pd)
-    sub_f, sub_d = Pf[np.ix_(ii, jj)], Pd[np.ix_(ii, jj)]
+    sub_f, sub_d, sub_q = Pf[np.ix_(ii, jj)], Pd[np.ix_(ii, jj)], Pq[np.ix_(ii, jj)]
     assert np.array_equal(np.isnan(sub_f), np.isnan(P_ref))
     fin = np.isfinite(P_ref)
     assert np.abs(sub_f - P_ref)[fin].max() / scale < FF_TOL
     assert np.abs(sub_d - P_ref)[fin].max() / scale < FF_TOL
+    assert np.abs(sub_q - P_ref)[fin].max() / scale < FF_TOL
     # KAT: energy conservation of the lens aperture, total_P / P_in ~ 1
     P_in = float((Ex * np.conj(Hy) - Ey * np.conj(Hx)).real.sum()) * d * d
     assert abs(tf.item() / P_in - 1) < 5e-3

@@ -111,8 +111,17 @@ def test_larger_lens_against_oracle():
     got = build_nearfield(*args)
     ref = no.build_nearfield(*args)
     assert got[0].shape == ref[0].shape and got[0].shape[0] >= 216
+    # The default grid has an odd count here, so some samples sit exactly on y = 0, equidistant from the
+    # two hex cells at y = +-pitch/2.  Which of two exactly tied cells scipy's cKDTree returns depends on
+    # its internal split order; those measure-zero samples are excluded from the comparison.
+    X, Y = np.meshgrid(got[4], got[5], indexing="ij")
+    d2 = (X.ravel()[:, None] - center[None, :, 0]) ** 2 + (Y.ravel()[:, None] - center[None, :, 1]) ** 2
+    in_center = np.hypot(X, Y).ravel() <= periph["r_min_list"][0]
+    tied = ((d2 <= d2.min(axis=1, keepdims=True)).sum(axis=1) > 1) & in_center
+    assert 0 < tied.sum() < 1e-3 * tied.size
+    keep = ~tied.reshape(X.shape)
     for k in range(4):
-        assert field_error(got[k], ref[k]) < 1e-9
+        assert field_error(got[k] * keep, ref[k] * keep) < 1e-9
     assert abs(got[6] - ref[6]) <= 1e-11 * abs(ref[6])
     far = np.linspace(40e-6, 44e-6, 20)
     z = build_nearfield(*args, x_pts=far, y_pts=far)
