@@ -86,12 +86,17 @@ int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);
 /* longest transform the shared-memory passes support (8192 complex64) */
 int mlb_fft_max_length(void);
 /*
- * Batched 1-D DFT along rows (the contiguous axis) of `batch` matrices [n_rows][N], with the
- * fftshift bookkeeping of nearfield_farfield.py:18-20, :68 folded into the indices:
- *   out_b[r][(q + out_roll) % N] = sum_p in_b[(r - in_roll_r) mod n_rows][(p - in_roll_c) mod N] e^{-2 pi i q p / N}
+ * Batched 1-D DFT along rows (the contiguous axis) with the aperture fold and the fftshift
+ * bookkeeping of nearfield_farfield.py:18-20, :68 folded into the indices.  Input matrices are
+ * [n_rows*s1][N*s2]; the loader sums the s1*s2 aliased samples (see mlb_fold; s1 = s2 = 1 = no fold):
+ *   G_b[r][p]  = sum_{t1<s1,t2<s2} in_b[((r - in_roll_r) mod n_rows) + t1*n_rows][((p - in_roll_c) mod N) + t2*N]
+ *   out_b[r][(q + out_roll) % N] = sum_p G_b[r][p] e^{-2 pi i q p / N}
+ * For a strided far-field grid this is the only kernel that touches the full aperture: it reads
+ * 8*n_rows*s1*N*s2 bytes per field exactly once (HBM-bound).
  */
 int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
-                 const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int batch, void *stream);
+                 int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int batch,
+                 void *stream);
 /* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}; in-place allowed */
 int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N, int n_cols,
                  const mlb_c64 *tw, int out_roll, int batch, void *stream);

@@ -73,9 +73,9 @@ class FarfieldPlan:
         fold  -- exact aperture fold (HBM-bound) followed by the dense reduction on the
                  folded (Mx/sx x My/sy) aperture; needs an FFT-bin-stride grid with
                  sx | Mx//2 and sy | My//2
-        fft   -- fold (if stride > 1) followed by shared-memory row/column FFT passes: the
-                 reference's own algorithm, every kernel memory-bound; needs power-of-two
-                 folded sizes <= 8192
+        fft   -- shared-memory row/column FFT passes, the row pass folding the aperture while it
+                 loads (stride > 1): the reference's own algorithm, every kernel memory-bound,
+                 the aperture read from HBM exactly once; needs power-of-two folded sizes <= 8192
         auto  -- fft if eligible, else fold, else dense
     p_dtype : torch.float32 (north-star output type) or torch.float64
     """
@@ -156,8 +156,7 @@ class FarfieldPlan:
             K1, K2 = Mx // self.sx, My // self.sy
             assert K1 == Kx and K2 == Ky
             self.Rx, self.Ry = K1, K2
-            self.folds = self.sx > 1 or self.sy > 1
-            self.G = [_c64_buffer(K1, K2, dev) for _ in range(4)] if self.folds else None
+            self.G = None          # the row pass folds while loading: the folded aperture never exists in memory
             self.W = [_c64_buffer(K1, K2, dev) for _ in range(4)]          # row-pass output
             self.tw1 = torch.empty(K1, dtype=torch.complex64, device=dev)
             self.tw2 = torch.empty(K2, dtype=torch.complex64, device=dev)
@@ -216,7 +215,7 @@ class FarfieldPlan:
         ops, ld = self._as_operands(fields)
         Kx, Ky, Rx, Ry = self.Kx, self.Ky, self.Rx, self.Ry
         out = []
-        if self.method in ("fold", "fft") and (self.sx > 1 or self.sy > 1):
+        if self.method == "fold":
             pj, k1 = _lib.ptr_array(ops)
             pg, k2 = _lib.ptr_array(self.G)
             ldg = self.G[0].shape[1]
@@ -232,20 +231,22 @@ class FarfieldPlan:
             # F[s q] = sum_p G[p] e^{-2 pi i q p / K},  G[p] = sum_t J[((p - M//2) mod K) + t K]; outputs are
             # stored at the fftshifted position q' = (q + (M//2)/s) mod K, the order of self.ux / self.uy
             h1, h2 = self.Mx // 2, self.My // 2
-            roll_r, roll_c = (0, 0) if folded else (h1 % Rx, h2 % Ry)      # fftshift of the input, :18-20
+            roll_r, roll_c = h1 % Rx, h2 % Ry          # fftshift of the input (:18-20), modulo the fold
+            assert not folded
             pi_, k3 = _lib.ptr_array(ops)
             pw, k4 = _lib.ptr_array(self.W)
             pf, k5 = _lib.ptr_array(self.Fhat)
             ldw, ldf = self.W[0].shape[1], self.Fhat[0].shape[1]
 
             def rows(pi_=pi_, ld=ld, keep=(k3, k4)):
-                _lib.check(lib.mlb_fft_rows(pi_, ld, pw, ldw, Rx, Ry, self.tw2.data_ptr(), roll_r, roll_c,
-                                            (h2 // self.sy) % Ry, 4, _stream_ptr()), "mlb_fft_rows")
+                _lib.check(lib.mlb_fft_rows(pi_, ld, pw, ldw, Rx, Ry, self.sx, self.sy, self.tw2.data_ptr(),
+                                            roll_r, roll_c, (h2 // self.sy) % Ry, 4, _stream_ptr()), "mlb_fft_rows")
 
             def cols(keep=k5):
                 _lib.check(lib.mlb_fft_cols(pw, ldw, pf, ldf, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx, 4,
                                             _stream_ptr()), "mlb_fft_cols")
-            out.append(("fft_rows", rows, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Ry)))
+            out.append(("fold_fft_rows" if (self.sx > 1 or self.sy > 1) else "fft_rows", rows,
+                        32 * (self.Mx * self.My + Rx * Ry), 4 * 5.0 * Rx * Ry * math.log2(Ry)))
             out.append(("fft_cols", cols, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
         else:
             pa, k6 = _lib.ptr_array(ops)

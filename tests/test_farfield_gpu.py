@@ -185,7 +185,7 @@ def test_fft_passes_match_numpy():
     from metalens_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(9)
-    assert lib.mlb_fft_max_length() == 8192 * 3 // 2 or lib.mlb_fft_max_length() >= 8192
+    assert lib.mlb_fft_max_length() == 8192
     for N, other in ((2, 5), (4, 3), (8, 9), (16, 4), (64, 33), (128, 7), (512, 6), (1024, 5), (2048, 3), (8192, 2)):
         a = [(rng.standard_normal((other, N)) + 1j * rng.standard_normal((other, N))).astype(np.complex64) for _ in range(2)]
         tw = torch.empty(N, dtype=torch.complex64).cuda()
@@ -198,7 +198,7 @@ def test_fft_passes_match_numpy():
         rr, rc, ro = other // 2, N // 2, (N // 2 + 1) % N
         pi_, k1 = _lib.ptr_array(din)
         po, k2 = _lib.ptr_array(dout)
-        _lib.check(lib.mlb_fft_rows(pi_, ld, po, ld, other, N, tw.data_ptr(), rr, rc, ro, 2, None), "rows")
+        _lib.check(lib.mlb_fft_rows(pi_, ld, po, ld, other, N, 1, 1, tw.data_ptr(), rr, rc, ro, 2, None), "rows")
         torch.cuda.synchronize()
         for v, d in zip(a, dout):
             ref = np.roll(np.fft.fft(np.roll(v.astype(complex), (rr, rc), axis=(0, 1)), axis=1), ro, axis=1)
@@ -216,7 +216,21 @@ def test_fft_passes_match_numpy():
             assert field_error(d[:, :other].cpu().numpy(), ref) < 3e-6, ("cols", N)
     bad = torch.zeros(4, 12, dtype=torch.complex64).cuda()
     pb, k4 = _lib.ptr_array([bad])
-    assert lib.mlb_fft_rows(pb, 12, pb, 12, 4, 12, bad.data_ptr(), 0, 0, 0, 1, None) != 0     # not a power of two
+    assert lib.mlb_fft_rows(pb, 12, pb, 12, 4, 12, 1, 1, bad.data_ptr(), 0, 0, 0, 1, None) != 0   # not a power of two
+    # fused fold: [n_rows*s1][N*s2] input, summed over the aliased copies while loading
+    n_rows, N, s1, s2 = 6, 64, 3, 4
+    big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
+    dbig = [torch.from_numpy(big).cuda()]
+    dres = [torch.zeros(n_rows, N, dtype=torch.complex64).cuda()]
+    tw = torch.empty(N, dtype=torch.complex64).cuda()
+    _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
+    pi_, k1 = _lib.ptr_array(dbig)
+    po, k2 = _lib.ptr_array(dres)
+    _lib.check(lib.mlb_fft_rows(pi_, N * s2, po, N, n_rows, N, s1, s2, tw.data_ptr(), 2, 10, 5, 1, None), "fold rows")
+    torch.cuda.synchronize()
+    folded = big.astype(complex).reshape(s1, n_rows, s2, N).sum(axis=(0, 2))
+    ref = np.roll(np.fft.fft(np.roll(folded, (2, 10), axis=(0, 1)), axis=1), 5, axis=1)
+    assert field_error(dres[0].cpu().numpy(), ref) < 3e-6
 
 
 def test_twiddle_float64_phase_accuracy():
