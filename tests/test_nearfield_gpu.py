@@ -111,15 +111,24 @@ def test_larger_lens_against_oracle():
     got = build_nearfield(*args)
     ref = no.build_nearfield(*args)
     assert got[0].shape == ref[0].shape and got[0].shape[0] >= 216
-    # The default grid has an odd count here, so some samples sit exactly on y = 0, equidistant from the
-    # two hex cells at y = +-pitch/2.  Which of two exactly tied cells scipy's cKDTree returns depends on
-    # its internal split order; those measure-zero samples are excluded from the comparison.
+    # The default grid has an odd count here, so some samples sit exactly on symmetry lines where the
+    # reference's own result hinges on the last bit of a libm call; both are measure-zero sets and are
+    # excluded from the comparison:
+    #  (1) centre samples exactly equidistant from two hex cells (y = 0 between cells at +-pitch/2):
+    #      which of two tied cells scipy's cKDTree returns depends on its internal split order;
+    #  (2) periphery samples exactly on the boundary between two grating copies, phi/angle_per_grating
+    #      = k + 1/2 (e.g. x = -y with num_around = 4 mod 8): round() flips with one ulp of arctan2.
     X, Y = np.meshgrid(got[4], got[5], indexing="ij")
+    r = np.hypot(X, Y)
     d2 = (X.ravel()[:, None] - center[None, :, 0]) ** 2 + (Y.ravel()[:, None] - center[None, :, 1]) ** 2
-    in_center = np.hypot(X, Y).ravel() <= periph["r_min_list"][0]
-    tied = ((d2 <= d2.min(axis=1, keepdims=True)).sum(axis=1) > 1) & in_center
-    assert 0 < tied.sum() < 1e-3 * tied.size
-    keep = ~tied.reshape(X.shape)
+    in_center = r.ravel() <= periph["r_min_list"][0]
+    tied = (((d2 <= d2.min(axis=1, keepdims=True)).sum(axis=1) > 1) & in_center).reshape(X.shape)
+    ring = np.searchsorted(np.hstack((periph["r_min_list"], periph["r_max_list"][-1])), r) - 1
+    ring[ring == len(periph["r_min_list"])] = -1
+    turns = np.arctan2(Y, X) / (2 * np.pi / periph["num_around_circle_list"][np.maximum(ring, 0)])
+    on_wedge_edge = (np.abs(np.abs(turns - np.round(turns)) - 0.5) < 1e-9) & (ring >= 0)
+    assert 0 < tied.sum() + on_wedge_edge.sum() < 1e-2 * tied.size
+    keep = ~(tied | on_wedge_edge)
     for k in range(4):
         assert field_error(got[k] * keep, ref[k] * keep) < 1e-9
     assert abs(got[6] - ref[6]) <= 1e-11 * abs(ref[6])
