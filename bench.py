@@ -19,6 +19,7 @@ N > 1  : one process per GPU (torchrun), weak scaling -- every rank owns a full 
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -159,6 +160,54 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------- hot path B
+def bench_nearfield(M, torch, cpu_cols=384):
+    """Aperture-field assembly (build_nearfield) on a synthetic round lens filling an M x M grid
+    (SURVEY 8d cfg4 shape): samples/s and achieved write bandwidth of the fused kernel, next to the
+    numpy oracle timed on a strip of the same grid."""
+    import synth_lens
+    from metalens_b200 import grating, lens_center
+    from metalens_b200.design import make_design
+    from metalens_b200.nearfield import NearfieldPlan
+    wl = 580e-9
+    R = M * (wl / 2.2) / 2
+    f = R / math.tan(math.radians(44.0))
+    spec = dict(bands=[(15.0, 25.0, 1000e-9, 0.3), (25.0, 45.0, 650e-9, 1.1)], source_distance=f, radius=R * 0.999)
+    t0 = time.perf_counter()
+    collections, hgs = synth_lens.make_library(grating, lens_center, spec)
+    periph, center, _ = make_design(collections, f, spec["radius"], hgs)
+    t_design = time.perf_counter() - t0
+    plan = NearfieldPlan(wl, periph, center, hgs)
+    x = np.linspace(-R, R, M)
+    out = torch.zeros((4, M, M), dtype=torch.complex64, device="cuda")
+    for _ in range(2):
+        plan.run(0.0, 0.0, -f, "x", x, x, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        plan.run(0.0, 0.0, -f, "x", x, x, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / reps * 1e-3
+    res = dict(aperture=[M, M], rings=int(len(periph["r_min_list"])), hex_cells=int(len(center)),
+               ms=t * 1e3, samples_per_s=M * M / t, write_gbs=32.0 * M * M / t / 1e9,
+               note="one fused kernel launch incl. host packing of x/y and the violation read-back; "
+                    "algorithmic bytes = 32*M^2 written (4 complex64 fields)", design_seconds=t_design)
+    # CPU oracle on a strip of the same grid (off-centre so centre and rings are both represented)
+    from oracle import nearfield_oracle as no
+    j0 = M // 2 + M // 8
+    ys = x[j0:j0 + cpu_cols]
+    t0 = time.perf_counter()
+    no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center, hgs, x_pts=x, y_pts=ys)
+    tc = time.perf_counter() - t0
+    res["cpu_baseline"] = dict(value=M * cpu_cols / tc, unit="aperture samples/s", cores=1, kind="port",
+                               sample="%d x %d strip of the same grid, oracle/nearfield_oracle.py (numpy + scipy "
+                                      "cKDTree), 1 thread, %.1f s" % (M, cpu_cols, tc))
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def ours(args):
     import torch
@@ -184,37 +233,44 @@ def ours(args):
     n_items = len(w["items"])
     peaks = measured_peaks()
 
-    # synthetic apertures (seeded per rank: every rank owns different sources), pinned on the host
-    pinned, dev_fields, plans = [], [], []
-    for i, (wl, ng, rot) in enumerate(w["items"]):
-        Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 1000 * rank + i + 1, wl, ng, rotate=rot)
+    # far-field tiles over the ranks (metalens_b200/sharding.py): weak scaling -> world x n_items batch
+    # items, whole items per rank, so each rank synthesises and owns only its own apertures
+    from metalens_b200.sharding import ShardedFarfield
+    n_global = n_items * world
+    geom = {}
+
+    def make_plan(item, r0, r1):
+        wl, ng, rot = w["items"][item % n_items]
+        d = apertures.grid(M, wl)[0]
+        d = float(d[1] - d[0])
+        rows = None if (r0, r1) == (0, K) else (r0, r1)
+        return FarfieldPlan((M, M), d, d, wl, ng, stride=s, method=args.method if rows is None else "fold", rows=rows)
+
+    sharded = ShardedFarfield(n_global, K, make_plan, rank=rank, world=world)
+    plans = sharded.plans
+    pinned, dev_fields = {}, {}
+    for item in sharded.items_needed:
+        wl, ng, rot = w["items"][item % n_items]
+        Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 1000 + item, wl, ng, rotate=rot)
         pin = torch.empty((4, M, M), dtype=torch.complex64).pin_memory()
         for f, a in enumerate((Ex, Ey, Hx, Hy)):
             pin[f].copy_(torch.from_numpy(a))
-        pinned.append(pin)
-        dev_fields.append(pin.cuda())
-        d = x[1] - x[0]
-        plans.append(FarfieldPlan((M, M), d, d, wl, ng, stride=s, method=args.method))
+        pinned[item] = pin
+        dev_fields[item] = pin.cuda()
         del Ex, Ey, Hx, Hy
-    gathered = torch.empty((world * n_items, K, K), dtype=torch.float32, device="cuda") if world > 1 else None
-    local_P = torch.empty((n_items, K, K), dtype=torch.float32, device="cuda")
+
+    def fields_of(item):
+        return [dev_fields[item][f] for f in range(4)]
 
     def step_device():
-        for i, plan in enumerate(plans):
-            P, _ = plan.run([dev_fields[i][f] for f in range(4)])
-            local_P[i].copy_(P)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, local_P)
+        return sharded.run(fields_of)            # local tiles + the one all-gather
+
+    def host_runner(plan, pin):
+        plan.run_host(pin)                       # pinned host -> H2D -> kernels -> D2H of P and total_P
+        return plan.P, plan.total
 
     def step_host():
-        out = None
-        for i, plan in enumerate(plans):
-            out = plan.run_host(pinned[i])
-            local_P[i].copy_(plan.P)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, local_P)
-            torch.cuda.synchronize()
-        return out
+        return sharded.run(lambda item: pinned[item], runner=host_runner)
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,8 +314,8 @@ def ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     _, e2e_wall, _, _ = timed(step_host, e2e_steps, 2)
     e2e_value = pts_per_step * e2e_steps / e2e_wall
-    h2d = n_items * plans[0].h2d_bytes
-    d2h = n_items * plans[0].d2h_bytes
+    h2d = world * n_items * plans[0].h2d_bytes          # whole job, all ranks
+    d2h = world * n_items * plans[0].d2h_bytes
 
     # ---- the other formulations on the same workload (device-resident, fewer steps), for context
     paths = {plans[0].method: value}
@@ -269,12 +325,13 @@ def ours(args):
                 continue
             try:
                 alt = [FarfieldPlan((M, M), p.dxp, p.dyp, p.wavelength, p.n_glass, stride=s, method=m) for p in plans]
+                items_alt = [t.item for t in sharded.tiles]
             except ValueError:
                 continue
 
             def step_alt(alt=alt):
-                for i, plan in enumerate(alt):
-                    plan.run([dev_fields[i][f] for f in range(4)])
+                for it, plan in zip(items_alt, alt):
+                    plan.run(fields_of(it))
             t_alt, _, _, _ = timed(step_alt, 3, 2)
             paths[m] = pts_per_step * 3 / t_alt
             del alt
@@ -295,9 +352,9 @@ def ours(args):
 
     # every kernel of one item, timed alone; rotate over the batch items so that the inputs
     # (n_items x 32 M^2 bytes) exceed L2 between launches of the same kernel
-    all_steps = [plan.steps([dev_fields[i][f] for f in range(4)]) for i, plan in enumerate(plans)]
-    for i in range(len(plans)):
-        plans[i].run([dev_fields[i][f] for f in range(4)])
+    all_steps = [plan.steps(fields_of(t.item)) for t, plan in zip(sharded.tiles, plans)]
+    for t, plan in zip(sharded.tiles, plans):
+        plan.run(fields_of(t.item))
     kernels = {}
     rr = [0]
     for k, (name, _fn, nbytes, flops) in enumerate(all_steps[0]):
@@ -325,6 +382,12 @@ def ours(args):
         a = kernels["fold"]["bytes"] / kernels["fold"]["seconds"] / 1e9
         roof["fold_hbm"] = dict(achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
 
+    nf = None
+    if rank == 0 and world == 1 and not args.no_nearfield:
+        del dev_fields, pinned
+        torch.cuda.empty_cache()
+        nf = bench_nearfield(args.nearfield_m, torch)
+
     if rank == 0:
         line = {
             "metric": "far-field points/sec (NF->FF)", "value": value, "unit": "far-field points/s",
@@ -343,6 +406,7 @@ def ours(args):
             "kernels": {k: dict(ms=v["seconds"] * 1e3, gbs=v["bytes"] / v["seconds"] / 1e9,
                                 tflops=v["flops"] / v["seconds"] / 1e12) for k, v in kernels.items()},
             "paths_points_per_s": paths,
+            "nearfield_assembly": nf,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -360,6 +424,8 @@ def main():
     ap.add_argument("--method", default="auto", choices=["auto", "dense", "fold", "fft"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-paths", action="store_true", help="skip timing the alternative formulations")
+    ap.add_argument("--no-nearfield", action="store_true", help="skip the aperture-assembly (hot path B) section")
+    ap.add_argument("--nearfield-m", type=int, default=4096, help="aperture size of the hot path B section")
     ap.add_argument("--quick-cpu", action="store_true", help="tiny cpu_baseline sample (debug)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

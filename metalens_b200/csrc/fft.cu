@@ -223,13 +223,14 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     bool vec = (N >= 2) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
-    if (vec) {
+    static bool attr_set = false;            // once per process: keeps launches capturable in CUDA graphs
+    if (!attr_set) {
         MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
-        mlb::fft_rows_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
-    } else {
         MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
-        mlb::fft_rows_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+        attr_set = true;
     }
+    if (vec) mlb::fft_rows_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    else mlb::fft_rows_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_fft_rows");
 }
 
@@ -249,7 +250,11 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     while (lanes < 16 && 2 * (size_t)(lanes * 2) * N * sizeof(float2) <= 64 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
     a.lgL = mlb::ilog2(lanes);
     const size_t smem = 2 * (size_t)lanes * N * sizeof(float2);
-    MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
+    static bool attr_set = false;
+    if (!attr_set) {
+        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
+        attr_set = true;
+    }
     dim3 grid((n_cols + lanes - 1) / lanes, batch);
     mlb::fft_cols_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_fft_cols");

@@ -78,10 +78,13 @@ class FarfieldPlan:
                  the aperture read from HBM exactly once; needs power-of-two folded sizes <= 8192
         auto  -- fft if eligible, else fold, else dense
     p_dtype : torch.float32 (north-star output type) or torch.float64
+    rows : optional (row0, row1): compute only that slab of far-field rows (ux indices) -- the
+        multi-GPU tile of metalens_b200/sharding.py.  Supported by 'dense' and 'fold', whose work
+        scales with the slab; the FFT passes produce all rows at once.
     """
 
     def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride=None, ux=None, uy=None,
-                 method="auto", p_dtype=torch.float32, device=None):
+                 method="auto", p_dtype=torch.float32, device=None, rows=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
@@ -105,6 +108,11 @@ class FarfieldPlan:
             self.fft_bin_grid = False
         self.ux = np.ascontiguousarray(ux, dtype=np.float64)
         self.uy = np.ascontiguousarray(uy, dtype=np.float64)
+        self.Kx_full = self.ux.size
+        self.rows = None if rows is None else (int(rows[0]), int(rows[1]))
+        if self.rows is not None:
+            assert 0 <= self.rows[0] < self.rows[1] <= self.Kx_full
+            self.ux = np.ascontiguousarray(self.ux[self.rows[0]:self.rows[1]])
         self.Kx, self.Ky = self.ux.size, self.uy.size
 
         can_fold = (self.fft_bin_grid and self.Mx % self.sx == 0 and self.My % self.sy == 0
@@ -118,6 +126,10 @@ class FarfieldPlan:
             nmax = self.lib.mlb_fft_max_length()
             can_fft = (pow2(k1) and pow2(k2) and k1 <= nmax and k2 <= nmax
                        and (can_fold or (self.sx == 1 and self.sy == 1)))
+        if self.rows is not None and self.rows != (0, self.Kx_full):
+            if method == "fft":
+                raise ValueError("row slabs need method 'dense' or 'fold' (the FFT passes yield all rows)")
+            can_fft = False
         if method == "auto":
             method = "fft" if can_fft else ("fold" if can_fold else "dense")
         if method == "fold" and not can_fold:
@@ -166,9 +178,11 @@ class FarfieldPlan:
         else:
             # folded aperture (K1 x K2) and exact integer DFT twiddles exp(-2 pi i p q / K)
             K1, K2 = Mx // self.sx, My // self.sy
-            assert K1 == Kx and K2 == Ky
+            assert K1 == self.Kx_full and K2 == Ky
             qx = (np.arange(K1) - (Mx // 2) // self.sx) % K1     # un-shifted bin number of output q'
             qy = (np.arange(K2) - (My // 2) // self.sy) % K2
+            if self.rows is not None:
+                qx = qx[self.rows[0]:self.rows[1]]
             self.AxT = self._twiddle(np.arange(K1), qx, -2.0 / K1)
             self.Ay = self._twiddle(np.arange(K2), qy, -2.0 / K2)
             self.Rx, self.Ry = K1, K2

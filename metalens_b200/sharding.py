@@ -1,0 +1,91 @@
+"""Multi-GPU sharding of the far field: one process per GPU, far-field tiles
+distributed over the ranks, ONE all-gather of the finished power tiles at the end.
+
+A *tile* is a slab of far-field rows (a contiguous range of ux) of one batch item
+(wavelength / polarisation / source).  Tiles are independent -- the reference's own RAM chunk
+loop (nearfield_farfield.py:45-66) already computes disjoint slabs of the far field
+separately -- so the only exchange step on the path is assembling the result.  With B items
+and G ranks every item is cut into S = G / gcd(B, G) slabs, giving B*S tiles, B*S/G per rank:
+whole items per rank when G divides B (no aperture replication), finer slabs otherwise.
+
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing; the per-tile compute
+is a FarfieldPlan restricted to its rows.
+"""
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class Tile:
+    item: int       # batch item
+    slab: int       # slab number within the item
+    row0: int       # first far-field row (ux index) of the tile
+    row1: int       # one past the last row
+
+
+def tile_schedule(n_items, n_rows, world):
+    """Tiles of every rank: list (len world) of lists of Tile.  Requires n_rows % S == 0."""
+    assert n_items >= 1 and world >= 1
+    slabs = world // math.gcd(n_items, world)
+    if n_rows % slabs:
+        raise ValueError("far-field rows (%d) must divide into %d equal slabs" % (n_rows, slabs))
+    per = n_rows // slabs
+    tiles = [Tile(i, s, s * per, (s + 1) * per) for i in range(n_items) for s in range(slabs)]
+    per_rank = len(tiles) // world
+    assert per_rank * world == len(tiles)
+    return [tiles[r * per_rank:(r + 1) * per_rank] for r in range(world)]
+
+
+def gather_tiles(local, n_items, n_rows, world, group=None):
+    """All-gather the per-rank tile stacks into the full far field on every rank.
+
+    local : (tiles_per_rank, rows_per_tile, n_cols) tensor of this rank's tiles in schedule order.
+    Returns (n_items, n_rows, n_cols).  Tiles are ordered item-major, slab-minor and ranks own
+    consecutive tiles, so the gathered buffer IS the result: no reshuffle after the collective.
+    """
+    t, rows, cols = local.shape
+    out = torch.empty((world * t, rows, cols), dtype=local.dtype, device=local.device)
+    if world == 1:
+        out.copy_(local)
+    else:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out.view(n_items, n_rows, cols)
+
+
+class ShardedFarfield:
+    """Far field of a batch of apertures computed across `world` ranks.
+
+    make_plan(item, row0, row1) must return a FarfieldPlan-like object whose ``run(fields)``
+    yields (P tile (row1-row0, Ky) device tensor, total_P scalar tensor); ``fields_of(item)``
+    the four device fields of an item this rank owns.
+    """
+
+    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None):
+        self.world = dist.get_world_size(group) if world is None else world
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.group = group
+        self.n_items, self.n_rows = n_items, n_rows
+        self.schedule = tile_schedule(n_items, n_rows, self.world)
+        self.tiles = self.schedule[self.rank]
+        self.plans = [make_plan(t.item, t.row0, t.row1) for t in self.tiles]
+        self._local = None
+
+    @property
+    def items_needed(self):
+        return sorted({t.item for t in self.tiles})
+
+    def run(self, fields_of, runner=None):
+        """Compute this rank's tiles, then the single all-gather.  Returns
+        (P (n_items, n_rows, Ky) on every rank, partial total_P per local tile).
+        `runner(plan, fields)` defaults to ``plan.run(fields)``."""
+        totals = []
+        for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
+            P, total = plan.run(fields_of(tile.item)) if runner is None else runner(plan, fields_of(tile.item))
+            if self._local is None:
+                self._local = torch.empty((len(self.tiles),) + tuple(P.shape), dtype=P.dtype, device=P.device)
+            self._local[k].copy_(P)
+            totals.append(total)
+        return gather_tiles(self._local, self.n_items, self.n_rows, self.world, self.group), totals

@@ -116,6 +116,27 @@ def test_complex_amplitudes_match_fft():
             assert field_error(amps[k], ref) < 2e-6
 
 
+def test_row_slabs_equal_full_far_field(golden_dir):
+    """Multi-GPU tile = a slab of far-field rows: slabs computed separately (as different ranks
+    would) reassemble to the single-plan result bit for bit (dense and fold)."""
+    from metalens_b200.farfield import FarfieldPlan
+    Ex, Ey, Hx, Hy, x, y = CASES["lens256_seed1"]()
+    dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+    d = x[1] - x[0]
+    for method in ("dense", "fold"):
+        full = FarfieldPlan((256, 256), d, d, WL, NG, stride=4, method=method)
+        P_full = full.run(dev)[0].clone()
+        parts = []
+        for r0, r1 in ((0, 16), (16, 32), (32, 64)):
+            slab = FarfieldPlan((256, 256), d, d, WL, NG, stride=4, method=method, rows=(r0, r1))
+            assert slab.Kx == r1 - r0
+            parts.append(slab.run(dev)[0].clone())
+        assert torch.equal(torch.cat(parts, dim=0), P_full) or \
+            bool(((torch.cat(parts, dim=0) == P_full) | (torch.isnan(P_full))).all())
+    with pytest.raises(ValueError):
+        FarfieldPlan((256, 256), d, d, WL, NG, stride=4, method="fft", rows=(0, 16))
+
+
 def test_cgemm_tn_ragged_shapes():
     """C[r][c] = sum_k At[k][r] B[k][c] against torch for ragged sizes, both tile configs."""
     import ctypes as C
