@@ -118,6 +118,15 @@ int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const double *ux, con
                     int Kx, int Ky, double amp_scale, double wavelength, double n_glass,
                     double Z0, void *P, int ldp, int p_is_double, double *block_sums,
                     void *stream);
+/*
+ * A5 (figure of merit of a far field, new composition -- the reference's FOM lives in S4/Lua,
+ * grating.lua:188-253): per-block sums (mlb_ff_epilogue_blocks() entries each) of P over the finite
+ * bins inside the cone (ux-ux0)^2+(uy-uy0)^2 <= radius^2 and over all finite bins; reduce both
+ * with mlb_sum_f64.  FOM = cone / total.
+ */
+int mlb_cone_power(const void *P, int ldp, int p_is_double, const double *ux, const double *uy, int Kx, int Ky,
+                   double ux0, double uy0, double radius, double *cone_block_sums, double *total_block_sums,
+                   void *stream);
 /* out[0] = scale * sum_{i<n} in[i], summed in a fixed order by one block */
 int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream);
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "mlb_ff_epilogue": (C.c_int, [_PP, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_cone_power": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                 C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlb_sum_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "mlb_nearfield_blocks": (C.c_int, [C.c_int, C.c_int]),
     "mlb_nearfield_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

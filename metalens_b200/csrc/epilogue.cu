@@ -81,6 +81,43 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
     }
 }
 
+// Figure-of-merit reduction: per-block sums of P over (a) all finite bins and
+// (b) the finite bins inside a cone (ux-ux0)^2 + (uy-uy0)^2 <= radius^2 around a target direction.
+template <typename T>
+__global__ void __launch_bounds__(EPI_THREADS) cone_power_kernel(const T *__restrict__ P, int ldp,
+                                                                 const double *__restrict__ ux,
+                                                                 const double *__restrict__ uy, int Kx, int Ky,
+                                                                 double ux0, double uy0, double r2,
+                                                                 double *__restrict__ cone_sums,
+                                                                 double *__restrict__ total_sums) {
+    const long long n = (long long)blockIdx.x * EPI_THREADS + threadIdx.x;
+    double c = 0.0, t = 0.0;
+    if (n < (long long)Kx * Ky) {
+        const int i = (int)(n / Ky), j = (int)(n % Ky);
+        const double p = (double)P[(size_t)i * ldp + j];
+        if (isfinite(p)) {
+            t = p;
+            const double dx = ux[i] - ux0, dy = uy[j] - uy0;
+            if (dx * dx + dy * dy <= r2) c = p;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __shared__ double wc[EPI_THREADS / 32], wt[EPI_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { wc[threadIdx.x >> 5] = c; wt[threadIdx.x >> 5] = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sc = 0.0, st = 0.0;
+#pragma unroll
+        for (int w = 0; w < EPI_THREADS / 32; ++w) { sc += wc[w]; st += wt[w]; }
+        cone_sums[blockIdx.x] = sc;
+        total_sums[blockIdx.x] = st;
+    }
+}
+
 __global__ void __launch_bounds__(1024) sum_f64_kernel(const double *__restrict__ in, int n, double scale,
                                                        double *__restrict__ out) {
     __shared__ double ws[32];
@@ -125,6 +162,23 @@ extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const doub
     a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double;
     mlb::ff_epilogue_kernel<<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_ff_epilogue");
+}
+
+extern "C" int mlb_cone_power(const void *P, int ldp, int p_is_double, const double *ux, const double *uy, int Kx,
+                              int Ky, double ux0, double uy0, double radius, double *cone_block_sums,
+                              double *total_block_sums, void *stream) {
+    MLB_REQUIRE(P && ux && uy && cone_block_sums && total_block_sums, "mlb_cone_power: NULL pointer");
+    MLB_REQUIRE(Kx > 0 && Ky > 0 && ldp >= Ky && radius >= 0, "mlb_cone_power: bad sizes");
+    const int nb = mlb_ff_epilogue_blocks(Kx, Ky);
+    if (p_is_double)
+        mlb::cone_power_kernel<double><<<nb, mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const double *>(P), ldp, ux, uy, Kx, Ky, ux0, uy0, radius * radius, cone_block_sums,
+            total_block_sums);
+    else
+        mlb::cone_power_kernel<float><<<nb, mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float *>(P), ldp, ux, uy, Kx, Ky, ux0, uy0, radius * radius, cone_block_sums,
+            total_block_sums);
+    return mlb::check_launch("mlb_cone_power");
 }
 
 extern "C" int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream) {

@@ -324,3 +324,31 @@ def test_config2_full_size_properties():
     a3 = fold.amplitudes()
     err = (a3 - (2 * a1 + a2)).abs().max().item() / a3.abs().max().item()
     assert err < 1e-5
+
+
+def test_fom_and_graph_replay():
+    """A5: cone-power figure of merit, eager vs CUDA-graph replay, over a small angle sweep of tilted
+    plane-wave patches (256 x 256, all bins): the peak follows sin(theta) and FOM ~ 1 inside the cone."""
+    from metalens_b200.farfield import FarfieldPlan
+    from metalens_b200.fom import FarfieldFOM
+    from oracle import farfield_oracle as fo
+    M = 256
+    plan = FarfieldPlan((M, M), WL / 2.2, WL / 2.2, WL, NG, stride=1)
+    fom = FarfieldFOM(plan, 0.0, 0.0, 0.05)
+    for deg in (5.0, 20.0, 35.0):
+        Ex, Ey, Hx, Hy, x, y = apertures.tilted_te(M, WL, NG, angle_deg=deg)
+        fields = [torch.from_numpy(a.astype(np.complex64)).cuda() for a in (Ex, Ey, Hx, Hy)]
+        fom.set_target(np.sin(np.radians(deg)), 0.0)
+        eager = fom.evaluate(fields).clone()
+        replay = fom.replay().clone()                       # captures, then replays on the same inputs
+        assert torch.equal(eager, replay)
+        P_ref, total_ref, ux, uy, dux, duy = fo.farfield_reference_path(Ex, Ey, Hx, Hy, x, y, WL, NG)
+        cone = ((ux - np.sin(np.radians(deg))) ** 2 + uy ** 2 <= 0.05 ** 2) & np.isfinite(P_ref)
+        ref = np.array([P_ref[cone].sum() * dux * duy, total_ref])
+        np.testing.assert_allclose(eager.cpu().numpy(), ref, rtol=2e-5)
+        assert FarfieldFOM.fom(eager) > 0.95
+    # replay picks up NEW inputs written into the static buffers without re-capture
+    Ex, Ey, Hx, Hy, x, y = apertures.tilted_te(M, WL, NG, angle_deg=10.0)
+    for i, a in enumerate((Ex, Ey, Hx, Hy)):
+        fom.static_fields[i][:, :M].copy_(torch.from_numpy(a.astype(np.complex64)))
+    assert FarfieldFOM.fom(fom.replay()) < 0.05             # cone still at 35 degrees -> little power there
