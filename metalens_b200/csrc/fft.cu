@@ -21,28 +21,27 @@ __device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2
 __device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
-// One Stockham stage of radix R over 2^lgL independent transforms of length 2^lgN in shared memory.
-// Element n of transform `lane` lives at  COLS ? (n << lgL) + lane : (lane << lgN) + n.
-template <int R, bool COLS>
+// One Stockham stage of radix R over `lanes` independent transforms of length 2^lgN held in shared
+// memory; element n of transform `lane` lives at lane*pitch + n (pitch >= N, even).
+template <int R>
 __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ x, float2 *__restrict__ y, int lgN, int lgNs,
-                                               int lgL, const float2 *__restrict__ tw) {
+                                               int lanes, int pitch, const float2 *__restrict__ tw) {
     constexpr int lgR = (R == 4) ? 2 : 1;
     const int lgPer = lgN - lgR;
     const int per = 1 << lgPer;
-    const int total = per << lgL;
+    const int total = lanes << lgPer;
     const int Ns = 1 << lgNs;
     const int lgTstep = lgN - lgNs - lgR;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int j, lane;
-        if (COLS) { j = idx >> lgL; lane = idx & ((1 << lgL) - 1); }
-        else { lane = idx >> lgPer; j = idx & (per - 1); }
+        const int lane = idx >> lgPer, j = idx & (per - 1);
         const int k = j & (Ns - 1);
         const int base_out = ((j - k) << lgR) + k;             // expand(j, Ns, R)
+        const float2 *xl = x + lane * pitch;
+        float2 *yl = y + lane * pitch;
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int n = j + r * per;
-            v[r] = x[COLS ? (n << lgL) + lane : (lane << lgN) + n];
+            v[r] = xl[j + r * per];
             if (r > 0 && lgNs > 0) v[r] = cmulf(v[r], __ldg(tw + ((r * k) << lgTstep)));
         }
         if (R == 4) {
@@ -54,80 +53,124 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ x, flo
             v[0] = a0; v[1] = a1;
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int n = base_out + (r << lgNs);
-            y[COLS ? (n << lgL) + lane : (lane << lgN) + n] = v[r];
-        }
+        for (int r = 0; r < R; ++r) yl[base_out + (r << lgNs)] = v[r];
     }
 }
 
-// runs all stages; returns the buffer (0 or 1) that holds the result
-template <bool COLS>
-__device__ __forceinline__ int fft_in_smem(float2 *buf0, float2 *buf1, int lgN, int lgL, const float2 *tw) {
-    int cur = 0, lgNs = 0;
+// Runs the stages from sub-transform length 2^lgNs0 on (data in buf0); returns the buffer (0/1) with
+// the result.  The first stage (lgNs = 0, all twiddles 1) is done by the loaders in registers.
+__device__ __forceinline__ int fft_in_smem(float2 *buf0, float2 *buf1, int lgN, int lgNs0, int lanes, int pitch,
+                                           const float2 *tw) {
+    int cur = 0, lgNs = lgNs0;
     while (lgNs + 2 <= lgN) {
         __syncthreads();
-        if (cur == 0) stockham_stage<4, COLS>(buf0, buf1, lgN, lgNs, lgL, tw);
-        else stockham_stage<4, COLS>(buf1, buf0, lgN, lgNs, lgL, tw);
+        if (cur == 0) stockham_stage<4>(buf0, buf1, lgN, lgNs, lanes, pitch, tw);
+        else stockham_stage<4>(buf1, buf0, lgN, lgNs, lanes, pitch, tw);
         cur ^= 1;
         lgNs += 2;
     }
     if (lgNs < lgN) {
         __syncthreads();
-        if (cur == 0) stockham_stage<2, COLS>(buf0, buf1, lgN, lgNs, lgL, tw);
-        else stockham_stage<2, COLS>(buf1, buf0, lgN, lgNs, lgL, tw);
+        if (cur == 0) stockham_stage<2>(buf0, buf1, lgN, lgNs, lanes, pitch, tw);
+        else stockham_stage<2>(buf1, buf0, lgN, lgNs, lanes, pitch, tw);
         cur ^= 1;
     }
     __syncthreads();
     return cur;
 }
 
+// first-stage butterfly on 4 (or 2) loaded values, twiddle-free
+__device__ __forceinline__ void bfly4(float2 &v0, float2 &v1, float2 &v2, float2 &v3) {
+    const float2 a0 = caddf(v0, v2), a1 = csubf(v0, v2);
+    const float2 a2 = caddf(v1, v3), a3 = mul_mi(csubf(v1, v3));
+    v0 = caddf(a0, a2); v1 = caddf(a1, a3); v2 = csubf(a0, a2); v3 = csubf(a1, a3);
+}
+
 struct FftArgs {
     const float2 *in[4];
     float2 *out[4];
     const float2 *tw;
-    int ld_in, ld_out, lgN, other, lgL, in_roll_r, in_roll_c, out_roll, s1, s2;
+    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2;
 };
 
-// rows: 2^lgL consecutive rows per CTA, transform along the contiguous axis; the loader sums the
-// s1 x s2 aliased copies (aperture fold) and applies the input fftshift.
+// folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions)
+template <int VEC>
+__device__ __forceinline__ void load_folded(const FftArgs &a, const float2 *__restrict__ in, int rs, int n, int N,
+                                            float (&acc)[2 * VEC]) {
+#pragma unroll
+    for (int v = 0; v < 2 * VEC; ++v) acc[v] = 0.f;
+    int cs = n - a.in_roll_c; if (cs < 0) cs += N;
+    for (int t1 = 0; t1 < a.s1; ++t1) {
+        const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in + cs;
+#pragma unroll 4
+        for (int t2 = 0; t2 < a.s2; ++t2) {
+            if (VEC == 2) {
+                const float4 v = __ldcs(reinterpret_cast<const float4 *>(row + ((size_t)t2 << a.lgN)));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            } else {
+                const float2 v = __ldcs(row + ((size_t)t2 << a.lgN));
+                acc[0] += v.x; acc[1] += v.y;
+            }
+        }
+    }
+}
+
+// rows: `lanes` consecutive rows per CTA, transform along the contiguous axis.  The loader sums the
+// s1 x s2 aliased copies (aperture fold), applies the input fftshift and performs the first radix-4
+// stage in registers, so its shared-memory writes are contiguous 64-byte runs.
 template <int VEC>
 __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
-    const int N = 1 << a.lgN, L = 1 << a.lgL;
-    float2 *buf0 = fsm, *buf1 = fsm + ((size_t)L << a.lgN);
+    const int N = 1 << a.lgN, L = a.lanes;
+    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N;
     const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
-    const int row0 = blockIdx.x << a.lgL;
-    const int total = (L << a.lgN) / VEC;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int e = idx * VEC;
-        const int lane = e >> a.lgN, n = e & (N - 1);
-        const int r = row0 + lane;
-        float acc[2 * VEC];
+    const int row0 = blockIdx.x * L;
+    int lgNs0;
+    if (a.lgN >= 2) {
+        lgNs0 = 2;
+        const int lgPer = a.lgN - 2, per = 1 << lgPer;
+        const int total = (L << lgPer) / VEC;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int e = idx * VEC;
+            const int lane = e >> lgPer, j = e & (per - 1);
+            const int r = row0 + lane;
+            float acc[4][2 * VEC];
+            if (r < a.other) {
+                int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
 #pragma unroll
-        for (int v = 0; v < 2 * VEC; ++v) acc[v] = 0.f;
-        if (r < a.other) {
-            int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
-            int cs = n - a.in_roll_c; if (cs < 0) cs += N;
-            for (int t1 = 0; t1 < a.s1; ++t1) {
-                const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in + cs;
-#pragma unroll 4
-                for (int t2 = 0; t2 < a.s2; ++t2) {
-                    if (VEC == 2) {
-                        const float4 v = __ldcs(reinterpret_cast<const float4 *>(row + ((size_t)t2 << a.lgN)));
-                        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-                    } else {
-                        const float2 v = __ldcs(row + ((size_t)t2 << a.lgN));
-                        acc[0] += v.x; acc[1] += v.y;
-                    }
-                }
+                for (int q = 0; q < 4; ++q) load_folded<VEC>(a, in, rs, j + q * per, N, acc[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int v = 0; v < 2 * VEC; ++v) acc[q][v] = 0.f;
+            }
+            float2 *y = buf0 + lane * N + 4 * j;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float2 v0 = make_float2(acc[0][2 * v], acc[0][2 * v + 1]), v1 = make_float2(acc[1][2 * v], acc[1][2 * v + 1]);
+                float2 v2 = make_float2(acc[2][2 * v], acc[2][2 * v + 1]), v3 = make_float2(acc[3][2 * v], acc[3][2 * v + 1]);
+                bfly4(v0, v1, v2, v3);
+                *reinterpret_cast<float4 *>(y + 4 * v) = make_float4(v0.x, v0.y, v1.x, v1.y);
+                *reinterpret_cast<float4 *>(y + 4 * v + 2) = make_float4(v2.x, v2.y, v3.x, v3.y);
             }
         }
-        if (VEC == 2) *reinterpret_cast<float4 *>(buf0 + e) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        else buf0[e] = make_float2(acc[0], acc[1]);
+    } else {                                                   // N == 2: the whole transform is one butterfly
+        lgNs0 = 1;
+        for (int lane = threadIdx.x; lane < L; lane += blockDim.x) {
+            const int r = row0 + lane;
+            float x0[2] = {0.f, 0.f}, x1[2] = {0.f, 0.f};
+            if (r < a.other) {
+                int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
+                load_folded<1>(a, in, rs, 0, N, x0);
+                load_folded<1>(a, in, rs, 1, N, x1);
+            }
+            buf0[lane * N] = make_float2(x0[0] + x1[0], x0[1] + x1[1]);
+            buf0[lane * N + 1] = make_float2(x0[0] - x1[0], x0[1] - x1[1]);
+        }
     }
-    const int cur = fft_in_smem<false>(buf0, buf1, a.lgN, a.lgL, a.tw);
+    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, N, a.tw);
     const float2 *res = cur ? buf1 : buf0;
     const int tot = L << a.lgN;
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
@@ -135,33 +178,60 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
         const int r = row0 + lane;
         if (r < a.other) {
             const int q = (n - a.out_roll) & (N - 1);           // out[(q + roll) % N] = X[q]
-            out[(size_t)r * a.ld_out + n] = res[(lane << a.lgN) + q];
+            out[(size_t)r * a.ld_out + n] = res[lane * N + q];
         }
     }
 }
 
-// columns: 2^lgL adjacent columns per CTA, transform along the strided axis
+// columns: `lanes` adjacent columns per CTA, transform along the strided axis.  Columns are
+// transposed into [lane][n] shared-memory rows (pitch N+4) while the loader does the first stage.
 __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
-    const int N = 1 << a.lgN, L = 1 << a.lgL;
-    float2 *buf0 = fsm, *buf1 = fsm + ((size_t)L << a.lgN);
+    const int N = 1 << a.lgN, L = a.lanes, P = N + 4;
+    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * P;
     const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
-    const int c0 = blockIdx.x << a.lgL;
+    const int c0 = blockIdx.x * L;
+    int lgNs0;
+    if (a.lgN >= 2) {
+        lgNs0 = 2;
+        const int per = N >> 2;
+        const int total = per * L;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int j = idx / L, lane = idx - j * L;
+            const int c = c0 + lane;
+            float2 v0, v1, v2, v3;
+            if (c < a.other) {
+                const float2 *src = in + (size_t)j * a.ld_in + c;
+                const size_t step = (size_t)per * a.ld_in;
+                v0 = src[0]; v1 = src[step]; v2 = src[2 * step]; v3 = src[3 * step];
+            } else {
+                v0 = v1 = v2 = v3 = make_float2(0.f, 0.f);
+            }
+            bfly4(v0, v1, v2, v3);
+            float2 *y = buf0 + lane * P + 4 * j;
+            *reinterpret_cast<float4 *>(y) = make_float4(v0.x, v0.y, v1.x, v1.y);
+            *reinterpret_cast<float4 *>(y + 2) = make_float4(v2.x, v2.y, v3.x, v3.y);
+        }
+    } else {
+        lgNs0 = 1;
+        for (int lane = threadIdx.x; lane < L; lane += blockDim.x) {
+            const int c = c0 + lane;
+            float2 x0 = make_float2(0.f, 0.f), x1 = x0;
+            if (c < a.other) { x0 = in[c]; x1 = in[(size_t)a.ld_in + c]; }
+            buf0[lane * P] = caddf(x0, x1);
+            buf0[lane * P + 1] = csubf(x0, x1);
+        }
+    }
+    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, P, a.tw);
+    const float2 *res = cur ? buf1 : buf0;
     const int total = L << a.lgN;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int n = idx >> a.lgL, lane = idx & (L - 1);
-        const int c = c0 + lane;
-        buf0[idx] = (c < a.other) ? in[(size_t)n * a.ld_in + c] : make_float2(0.f, 0.f);
-    }
-    const int cur = fft_in_smem<true>(buf0, buf1, a.lgN, a.lgL, a.tw);
-    const float2 *res = cur ? buf1 : buf0;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int n = idx >> a.lgL, lane = idx & (L - 1);       // n = OUTPUT row
+        const int n = idx / L, lane = idx - n * L;              // n = OUTPUT row
         const int c = c0 + lane;
         if (c < a.other) {
             const int q = (n - a.out_roll) & (N - 1);
-            out[(size_t)n * a.ld_out + c] = res[(q << a.lgL) + lane];
+            out[(size_t)n * a.ld_out + c] = res[lane * P + q];
         }
     }
 }
@@ -217,10 +287,10 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_rows;
     a.in_roll_r = in_roll_r; a.in_roll_c = in_roll_c; a.out_roll = out_roll; a.s1 = s1; a.s2 = s2;
     int lanes = 1;
-    while (lanes * 2 * N <= 1024 && lanes * 2 <= n_rows) lanes *= 2;      // small transforms: several rows per CTA
-    a.lgL = mlb::ilog2(lanes);
+    while (lanes * 2 * N <= 2048 && lanes * 2 <= n_rows) lanes *= 2;      // >= 2048 points per CTA when possible
+    a.lanes = lanes;
     const size_t smem = 2 * (size_t)lanes * N * sizeof(float2);
-    bool vec = (N >= 2) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
+    bool vec = (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
     static bool attr_set = false;            // once per process: keeps launches capturable in CUDA graphs
@@ -247,12 +317,12 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1;
     // as many adjacent columns as fit 64 KB (so 3 CTAs share an SM), at most 16 (128-byte row segments)
     int lanes = 1;
-    while (lanes < 16 && 2 * (size_t)(lanes * 2) * N * sizeof(float2) <= 64 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
-    a.lgL = mlb::ilog2(lanes);
-    const size_t smem = 2 * (size_t)lanes * N * sizeof(float2);
+    while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 4) * sizeof(float2) <= 72 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
+    a.lanes = lanes;
+    const size_t smem = 2 * (size_t)lanes * (N + 4) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
+        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (mlb::FFT_MAX_N + 4) * 8));
         attr_set = true;
     }
     dim3 grid((n_cols + lanes - 1) / lanes, batch);
