@@ -320,7 +320,7 @@ def ours(args):
     # ---- the other formulations on the same workload (device-resident, fewer steps), for context
     paths = {plans[0].method: value}
     if world == 1 and not args.no_paths:
-        for m in ("fft", "fold", "dense"):
+        for m in ("fft", "fold", "tc", "dense"):
             if m in paths:
                 continue
             try:
@@ -421,7 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--method", default="auto", choices=["auto", "dense", "fold", "fft"])
+    ap.add_argument("--method", default="auto", choices=["auto", "dense", "fold", "fft", "tc"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-paths", action="store_true", help="skip timing the alternative formulations")
     ap.add_argument("--no-nearfield", action="store_true", help="skip the aperture-assembly (hot path B) section")

@@ -80,6 +80,28 @@ int mlb_cgemm_tn(const mlb_c64 *const *h_At, int lda, const mlb_c64 *B, int ldb,
 int mlb_fold(const mlb_c64 *const *h_J, int ldj, int M1, int M2, int s1, int s2,
              int h1, int h2, mlb_c64 *const *h_G, int ldg, int batch, void *stream);
 
+/* ---- A4 on the tensor cores: 3xTF32 complex GEMM (tcgen05 + TMEM + TMA), BASELINE cfg3 ---------- */
+/*
+ * Complex C = A.B embedded in a real K-major GEMM (see csrc/cgemm_tc.cu):
+ *   A operand : complex64 row-major [rows][depth_c] viewed as fp32 [rows][2*depth_c]
+ *   B operand : "embedding" fp32 [2*cols_c][2*depth_c]: row 2n = (Re,-Im) pairs of column n, row 2n+1 = (Im,Re)
+ * Every operand comes as a tf32 hi/lo pair; D += Ah.Bh + Al.Bh + Ah.Bl in fp32 TMEM accumulators.
+ * mlb_tf32_split   : fp32 matrix -> hi = tf32(x), lo = tf32(x - hi)   (aperture fields -> A operand)
+ * mlb_twiddle_tf32 : exp(i*pi*scale*coord[m]*u[i]) from float64 phases, written as A operand
+ *                    (layout 0: [n_u][2*n_coord]) or B embedding (layout 1: [2*n_u][2*n_coord])
+ * mlb_cgemm_tc     : mode 1: result written as the B embedding (hi and lo) of the NEXT stage,
+ *                            out[2j+q][2*row..2*row+1], pitch ldo floats;
+ *                    mode 2: result written as complex64 out[row*ldo + j].
+ *   NF->FF stage 1:  T[m1][j] = sum_m2 J[m1][m2] Ay[m2][j]  (A = split fields,  B = twiddle embedding, mode 1)
+ *   NF->FF stage 2:  F[i][j]  = sum_m1 Ax[i][m1] T[m1][j]   (A = twiddle rows,  B = stage-1 output,    mode 2)
+ * Pitches (floats) must be multiples of 4 (TMA needs 16-byte row pitches).
+ */
+int mlb_tf32_split(const float *in, int ld_in, float *hi, float *lo, int ld_out, int rows, int cols, void *stream);
+int mlb_twiddle_tf32(const double *coord, int n_coord, const double *u, int n_u, double scale, int layout,
+                     float *hi, float *lo, int ld, void *stream);
+int mlb_cgemm_tc(const float *Ah, const float *Al, int lda, const float *Bh, const float *Bl, int ldb,
+                 int rows, int cols_c, int depth_c, int mode, float *out_hi, float *out_lo, int ldo, void *stream);
+
 /* ---- A1 (FFT formulation): shared-memory FFT passes, power-of-two lengths ---- */
 /* out[t] = exp(-2 pi i t / N), float64 phases rounded once to fp32 */
 int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);

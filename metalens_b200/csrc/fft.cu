@@ -42,7 +42,7 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ x, flo
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             v[r] = xl[j + r * per];
-            if (r > 0 && lgNs > 0) v[r] = cmulf(v[r], __ldg(tw + ((r * k) << lgTstep)));
+            if (r > 0 && lgNs > 0) v[r] = cmulf(v[r], tw[(r * k) << lgTstep]);
         }
         if (R == 4) {
             const float2 a0 = caddf(v[0], v[2]), a1 = csubf(v[0], v[2]);
@@ -122,10 +122,11 @@ template <int VEC>
 __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int N = 1 << a.lgN, L = a.lanes;
-    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N;
+    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N, *stw = buf1 + (size_t)L * N;
     const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
     const int row0 = blockIdx.x * L;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[t];     // twiddle table -> shared memory
     int lgNs0;
     if (a.lgN >= 2) {
         lgNs0 = 2;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
             buf0[lane * N + 1] = make_float2(x0[0] - x1[0], x0[1] - x1[1]);
         }
     }
-    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, N, a.tw);
+    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, N, stw);
     const float2 *res = cur ? buf1 : buf0;
     const int tot = L << a.lgN;
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
@@ -188,10 +189,11 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
 __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int N = 1 << a.lgN, L = a.lanes, P = N + 4;
-    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * P;
+    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * P, *stw = buf1 + (size_t)L * P;
     const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
     const int c0 = blockIdx.x * L;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[t];
     int lgNs0;
     if (a.lgN >= 2) {
         lgNs0 = 2;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
             buf0[lane * P + 1] = csubf(x0, x1);
         }
     }
-    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, P, a.tw);
+    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, P, stw);
     const float2 *res = cur ? buf1 : buf0;
     const int total = L << a.lgN;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -287,20 +289,24 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_rows;
     a.in_roll_r = in_roll_r; a.in_roll_c = in_roll_c; a.out_roll = out_roll; a.s1 = s1; a.s2 = s2;
     int lanes = 1;
-    while (lanes * 2 * N <= 2048 && lanes * 2 <= n_rows) lanes *= 2;      // >= 2048 points per CTA when possible
+    while (lanes * 2 * N <= 1024 && lanes * 2 <= n_rows) lanes *= 2;      // small transforms: several rows per CTA
     a.lanes = lanes;
-    const size_t smem = 2 * (size_t)lanes * N * sizeof(float2);
+    const size_t smem = (2 * (size_t)lanes + 1) * N * sizeof(float2);     // ping-pong buffers + twiddle table
     bool vec = (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
     static bool attr_set = false;            // once per process: keeps launches capturable in CUDA graphs
     if (!attr_set) {
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
+        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * mlb::FFT_MAX_N * 8));
+        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * mlb::FFT_MAX_N * 8));
         attr_set = true;
     }
-    if (vec) mlb::fft_rows_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
-    else mlb::fft_rows_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    // one loader task per thread where possible: small CTAs, many of them per SM, so that some are always
+    // in their (HBM-bound) load phase while others run their FFT stages
+    const int tasks = lanes * (N >= 4 ? N / 4 : 1) / (vec ? 2 : 1);
+    const int threads = tasks >= 256 ? 256 : (tasks <= 64 ? 64 : 128);
+    if (vec) mlb::fft_rows_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+    else mlb::fft_rows_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_fft_rows");
 }
 
@@ -317,12 +323,12 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1;
     // as many adjacent columns as fit 64 KB (so 3 CTAs share an SM), at most 16 (128-byte row segments)
     int lanes = 1;
-    while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 4) * sizeof(float2) <= 72 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
+    while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 4) * sizeof(float2) <= 66 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
     a.lanes = lanes;
-    const size_t smem = 2 * (size_t)lanes * (N + 4) * sizeof(float2);
+    const size_t smem = (2 * (size_t)lanes * (N + 4) + N) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (mlb::FFT_MAX_N + 4) * 8));
+        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * mlb::FFT_MAX_N + 8) * 8));
         attr_set = true;
     }
     dim3 grid((n_cols + lanes - 1) / lanes, batch);

@@ -130,7 +130,24 @@ __device__ __forceinline__ void store_c(void *base, size_t off, cplx v, int is_d
     else reinterpret_cast<float2 *>(base)[off] = make_float2((float)v.re, (float)v.im);
 }
 
-template <bool STATS>
+// e^{i x}: float64 sincos for the complex128 output; for the complex64 output the argument is reduced
+// to [-pi, pi] in float64 (exact to ~1e-16 turns) and the sine/cosine taken in fp32 (abs. error
+// ~1e-7, below the output's own rounding).
+template <bool FAST>
+__device__ __forceinline__ cplx expi(double x) {
+    if (FAST) {
+        const double t = x * 0.15915494309189535;                 // x / 2 pi
+        const float f = (float)((t - rint(t)) * 6.283185307179586);
+        float s, c;
+        sincosf(f, &s, &c);
+        return {(double)c, (double)s};
+    }
+    double s, c;
+    sincos(x, &s, &c);
+    return {c, s};
+}
+
+template <bool STATS, bool FAST>
 __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_constant__ mlb_lens_desc L, const NfOut out) {
     const int j = blockIdx.x * NF_THREADS + threadIdx.x;   // y index (fast)
     const int i = blockIdx.y;                              // x index
@@ -192,18 +209,23 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
                 const mlb_table_pack &p = L.packs[gc];
                 Interp3 q;
                 bool located = false;
+                const double qx = 2.0 * PI / gp, qy = 2.0 * PI / lat;
+                const float fux = (float)uxp, fuy = (float)uyp, fqx = (float)(qx / kvac), fqy = (float)(qy / kvac);
                 for (int o = 0; o < p.n_orders; ++o) {
-                    const double kxp = kvac * uxp + p.orders[2 * o] * 2.0 * PI / gp;        // :268
-                    const double kyp = kvac * uyp + p.orders[2 * o + 1] * 2.0 * PI / lat;   // :269
+                    const int ox = p.orders[2 * o], oy = p.orders[2 * o + 1];
+                    // cheap fp32 screen: clearly evanescent-in-air orders are skipped before any float64 work
+                    const float sx = fmaf((float)ox, fqx, fux), sy = fmaf((float)oy, fqy, fuy);
+                    if (fmaf(sx, sx, sy * sy) > 1.001f) continue;
+                    const double kxp = kvac * uxp + ox * qx;                               // :268
+                    const double kyp = kvac * uyp + oy * qy;                               // :269
                     if (kxp * kxp + kyp * kyp <= kvac * kvac) {                            // :279
                         record<STATS>(p, o, uxp, uyp, gp, true, out.stats, out.violation);
                         if (!located) { q = locate(p, uxp, uyp, gp); located = true; }
                         const double kzp = sqrt(kg * kg - kxp * kxp - kyp * kyp);           // :287
-                        double ps, pc;
-                        sincos(kxp * xp + kyp * yp, &ps, &pc);                              // :291
+                        const cplx ph = expi<FAST>(kxp * xp + kyp * yp);                    // :291
                         cplx amp[4];
                         gather4(p, o, q, amp);
-                        add_order(amp, Hw_x, Hw_y, kxp, kyp, kzp, inv_kg_n, L.Z0, {pc, ps}, Exp, Eyp, Hxp, Hyp);
+                        add_order(amp, Hw_x, Hw_y, kxp, kyp, kzp, inv_kg_n, L.Z0, ph, Exp, Eyp, Hxp, Hyp);
                     }
                 }
             }
@@ -211,9 +233,7 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
                 const double gx = rc * c, gy = rc * s;                              // :170-171
                 const double path = sqrt((gx - L.source_x) * (gx - L.source_x) + (gy - L.source_y) * (gy - L.source_y) +
                                          L.source_z * L.source_z);
-                double es, ec;
-                sincos(kvac * path, &es, &ec);
-                const cplx e = {ec, es};
+                const cplx e = expi<FAST>(kvac * path);
                 Exp = Exp * e; Eyp = Eyp * e; Hxp = Hxp * e; Hyp = Hyp * e;
             }
             Ex = {Exp.re * c - Eyp.re * s, Exp.im * c - Eyp.im * s};               // :351-354
@@ -260,26 +280,28 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
                 const mlb_table_pack &p = L.hex;
                 Interp3 q;
                 bool located = false;
+                const double qx = 2.0 * PI / L.hex_x_period, qy = 2.0 * PI / L.hex_y_period;
+                const float fux = (float)ux, fuy = (float)uy, fqx = (float)(qx / kvac), fqy = (float)(qy / kvac);
                 for (int o = 0; o < p.n_orders; ++o) {
-                    const double kx = kvac * ux + p.orders[2 * o] * 2.0 * PI / L.hex_x_period;      // :395
-                    const double ky = kvac * uy + p.orders[2 * o + 1] * 2.0 * PI / L.hex_y_period;  // :396
+                    const int ox = p.orders[2 * o], oy = p.orders[2 * o + 1];
+                    const float sx = fmaf((float)ox, fqx, fux), sy = fmaf((float)oy, fqy, fuy);
+                    if (fmaf(sx, sx, sy * sy) > 1.001f) continue;
+                    const double kx = kvac * ux + ox * qx;                                         // :395
+                    const double ky = kvac * uy + oy * qy;                                         // :396
                     if (kx * kx + ky * ky <= kvac * kvac) {                                        // :398
                         record<STATS>(p, o, ux, uy, which, false, out.stats, out.violation);
                         if (!located) { q = locate(p, ux, uy, which); located = true; }
                         const double kz = sqrt(kg * kg - kx * kx - ky * ky);                        // :404
-                        double ps, pc;
-                        sincos(kx * (x - cx) + ky * (y - cy), &ps, &pc);                            // :408-409
+                        const cplx ph = expi<FAST>(kx * (x - cx) + ky * (y - cy));                  // :408-409
                         cplx amp[4];
                         gather4(p, o, q, amp);
-                        add_order(amp, Hw_x, Hw_y, kx, ky, kz, inv_kg_n, L.Z0, {pc, ps}, Ex, Ey, Hx, Hy);
+                        add_order(amp, Hw_x, Hw_y, kx, ky, kz, inv_kg_n, L.Z0, ph, Ex, Ey, Hx, Hy);
                     }
                 }
                 if (!L.plane_wave) {                                                // :453-461
                     const double path = sqrt((cx - L.source_x) * (cx - L.source_x) + (cy - L.source_y) * (cy - L.source_y) +
                                              L.source_z * L.source_z);
-                    double es, ec;
-                    sincos(kvac * path, &es, &ec);
-                    const cplx e = {ec, es};
+                    const cplx e = expi<FAST>(kvac * path);
                     Ex = Ex * e; Ey = Ey * e; Hx = Hx * e; Hy = Hy * e;
                 }
             }
@@ -372,8 +394,14 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     out.power_block_sums = power_block_sums; out.stats = stats; out.violation = violation;
     out.ld = ld; out.out_is_double = out_is_double;
     dim3 grid((L.ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS, L.nx);
-    if (want_stats) mlb::nearfield_kernel<true><<<grid, mlb::NF_THREADS, 0, (cudaStream_t)stream>>>(L, out);
-    else mlb::nearfield_kernel<false><<<grid, mlb::NF_THREADS, 0, (cudaStream_t)stream>>>(L, out);
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (want_stats) {
+        if (out_is_double) mlb::nearfield_kernel<true, false><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        else mlb::nearfield_kernel<true, true><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+    } else {
+        if (out_is_double) mlb::nearfield_kernel<false, false><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        else mlb::nearfield_kernel<false, true><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+    }
     return mlb::check_launch("mlb_nearfield_assemble");
 }
 

@@ -76,6 +76,8 @@ class FarfieldPlan:
         fft   -- shared-memory row/column FFT passes, the row pass folding the aperture while it
                  loads (stride > 1): the reference's own algorithm, every kernel memory-bound,
                  the aperture read from HBM exactly once; needs power-of-two folded sizes <= 8192
+        tc    -- the dense separable reduction on the tensor cores: tcgen05 UMMA (TF32 operands split
+                 hi/lo, three products per term -> fp32-class accuracy), TMEM accumulators, TMA-fed
         auto  -- fft if eligible, else fold, else dense
     p_dtype : torch.float32 (north-star output type) or torch.float64
     rows : optional (row0, row1): compute only that slab of far-field rows (ux indices) -- the
@@ -137,7 +139,7 @@ class FarfieldPlan:
         if method == "fft" and not can_fft:
             raise ValueError("fft needs an FFT-bin(-stride) grid whose folded sizes are powers of two <= %d"
                              % self.lib.mlb_fft_max_length())
-        assert method in ("dense", "fold", "fft")
+        assert method in ("dense", "fold", "fft", "tc")
         self.method = method
         self._build()
 
@@ -164,6 +166,8 @@ class FarfieldPlan:
             self.Ay = self._twiddle((np.arange(My) - oy) * self.dyp, self.uy, scale)    # [My][Ky]
             self.Rx, self.Ry = Mx, My            # size of the aperture the reduction runs over
             self.G = None
+        elif self.method == "tc":
+            self._build_tc()
         elif self.method == "fft":
             K1, K2 = Mx // self.sx, My // self.sy
             assert K1 == Kx and K2 == Ky
@@ -188,7 +192,7 @@ class FarfieldPlan:
             self.Rx, self.Ry = K1, K2
             self.G = [_c64_buffer(K1, K2, dev) for _ in range(4)]
         self.UT = ([_c64_buffer(self.Ry, Kx, dev) for _ in range(4)]     # stage-1 output, [m2][i]
-                   if self.method != "fft" else None)
+                   if self.method in ("dense", "fold") else None)
         self.Fhat = [_c64_buffer(Kx, Ky, dev) for _ in range(4)]         # aperture sums, [i][j]
         self.P = torch.empty((Kx, Ky), dtype=self.p_dtype, device=dev)
         self.nblocks = self.lib.mlb_ff_epilogue_blocks(Kx, Ky)
@@ -200,6 +204,66 @@ class FarfieldPlan:
         self.duy = float(self.uy[1] - self.uy[0]) if Ky > 1 else float("nan")
         self._staging = None
         self._pinned = None
+
+    def _build_tc(self):
+        """Operands of the tensor-core path (csrc/cgemm_tc.cu): y-first contraction
+        T[m1][j] = sum_m2 J[m1][m2] Ay[m2][j];  F[i][j] = sum_m1 Ax[i][m1] T[m1][j]."""
+        dev, lib = self.device, self.lib
+        Mx, My, Kx, Ky = self.Mx, self.My, self.Kx, self.Ky
+        self.Rx, self.Ry = Mx, My
+        self.G = None
+        ox, oy = Mx - Mx // 2, My - My // 2
+        scale = -2.0 * self.n_glass / self.wavelength
+
+        def pad4(n):
+            return (n + 3) // 4 * 4
+
+        def f32(rows, cols):
+            return torch.zeros((rows, pad4(cols)), dtype=torch.float32, device=dev)
+
+        def tw(coord, u, layout, rows):
+            c = torch.from_numpy(np.ascontiguousarray(coord, dtype=np.float64)).to(dev)
+            v = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).to(dev)
+            hi, lo = f32(rows, 2 * c.numel()), f32(rows, 2 * c.numel())
+            _lib.check(lib.mlb_twiddle_tf32(c.data_ptr(), c.numel(), v.data_ptr(), v.numel(), scale, layout,
+                                            hi.data_ptr(), lo.data_ptr(), hi.shape[1], _stream_ptr()), "mlb_twiddle_tf32")
+            return hi, lo
+        # stage-1 B operand: embedding of Ay[m2][j] = e^{-ik y'_m2 uy_j}, rows 2j+q, columns 2m2+p
+        self.AyB = tw((np.arange(My) - oy) * self.dyp, self.uy, 1, 2 * Ky)
+        # stage-2 A operand: Ax[i][m1] = e^{-ik x'_m1 ux_i}, row i, columns (2m1, 2m1+1)
+        self.AxA = tw((np.arange(Mx) - ox) * self.dxp, self.ux, 0, Kx)
+        self.Jh = [f32(Mx, 2 * My) for _ in range(4)]
+        self.Jl = [f32(Mx, 2 * My) for _ in range(4)]
+        self.TBh = [f32(2 * Ky, 2 * Mx) for _ in range(4)]
+        self.TBl = [f32(2 * Ky, 2 * Mx) for _ in range(4)]
+        self.AxT = self.Ay = None
+
+    def _steps_tc(self, ops, ld):
+        lib = self.lib
+        Mx, My, Kx, Ky = self.Mx, self.My, self.Kx, self.Ky
+        ldj = self.Jh[0].shape[1]
+
+        def split():
+            for f in range(4):
+                _lib.check(lib.mlb_tf32_split(ops[f].data_ptr(), 2 * ld, self.Jh[f].data_ptr(), self.Jl[f].data_ptr(),
+                                              ldj, Mx, 2 * My, _stream_ptr()), "mlb_tf32_split")
+
+        def stage1():
+            for f in range(4):
+                _lib.check(lib.mlb_cgemm_tc(self.Jh[f].data_ptr(), self.Jl[f].data_ptr(), ldj,
+                                            self.AyB[0].data_ptr(), self.AyB[1].data_ptr(), self.AyB[0].shape[1],
+                                            Mx, Ky, My, 1, self.TBh[f].data_ptr(), self.TBl[f].data_ptr(),
+                                            self.TBh[f].shape[1], _stream_ptr()), "mlb_cgemm_tc(stage 1)")
+
+        def stage2():
+            for f in range(4):
+                _lib.check(lib.mlb_cgemm_tc(self.AxA[0].data_ptr(), self.AxA[1].data_ptr(), self.AxA[0].shape[1],
+                                            self.TBh[f].data_ptr(), self.TBl[f].data_ptr(), self.TBh[f].shape[1],
+                                            Kx, Ky, Mx, 2, self.Fhat[f].data_ptr(), None, self.Fhat[f].shape[1],
+                                            _stream_ptr()), "mlb_cgemm_tc(stage 2)")
+        return [("tf32_split", split, 4 * 24 * Mx * My, 0.0),
+                ("tc_stage1", stage1, 4 * (16 * Mx * My + 32 * Ky * Mx) + 16 * Ky * My, 32.0 * Mx * My * Ky),
+                ("tc_stage2", stage2, 4 * (32 * Ky * Mx + 8 * Kx * Ky) + 16 * Kx * Mx, 32.0 * Kx * Mx * Ky)]
 
     # ------------------------------------------------------------------ run
     def _as_operands(self, fields):
@@ -229,6 +293,8 @@ class FarfieldPlan:
         ops, ld = self._as_operands(fields)
         Kx, Ky, Rx, Ry = self.Kx, self.Ky, self.Rx, self.Ry
         out = []
+        if self.method == "tc":
+            return self._steps_tc(ops, ld) + [("epilogue", self.power, 36 * Kx * Ky, 0.0)]
         if self.method == "fold":
             pj, k1 = _lib.ptr_array(ops)
             pg, k2 = _lib.ptr_array(self.G)

@@ -352,3 +352,32 @@ def test_fom_and_graph_replay():
     for i, a in enumerate((Ex, Ey, Hx, Hy)):
         fom.static_fields[i][:, :M].copy_(torch.from_numpy(a.astype(np.complex64)))
     assert FarfieldFOM.fom(fom.replay()) < 0.05             # cone still at 35 degrees -> little power there
+
+
+def test_tensor_core_path_matches_reference(golden_dir):
+    """tcgen05 3xTF32 complex GEMM (method 'tc'): same answer as the reference within the 1e-5
+    budget, on power-of-two, ragged and arbitrary-grid cases; its complex amplitudes agree with
+    the fp32 SIMT reduction to ~1e-6."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import FarfieldPlan, farfield_from_fields
+    for name, stride in (("rand128_seed0", 1), ("lens256_seed1", 2), ("rand_45x27_seed6", 1), ("rand_48x40_seed5", (4, 2))):
+        g = golden(golden_dir, name)
+        Ex, Ey, Hx, Hy, x, y = CASES[name]()
+        sx, sy = (stride, stride) if np.isscalar(stride) else stride
+        P, total, *_ = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=stride, method="tc", p_dtype=torch.float32)
+        ref = g["P"][::sx, ::sy]
+        assert power_map_error(P, ref) < FF_TOL, name
+    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(300, 21, WL, My=260)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
+    ux = np.linspace(-0.7, 0.8, 150)
+    uy = np.linspace(-0.6, 0.65, 131)
+    tc = FarfieldPlan((300, 260), x[1] - x[0], y[1] - y[0], WL, NG, ux=ux, uy=uy, method="tc")
+    simt = FarfieldPlan((300, 260), x[1] - x[0], y[1] - y[0], WL, NG, ux=ux, uy=uy, method="dense")
+    P1 = tc.run(dev)[0].cpu().numpy()
+    a1 = tc.amplitudes().cpu().numpy()
+    P2 = simt.run(dev)[0].cpu().numpy()
+    a2 = simt.amplitudes().cpu().numpy()
+    assert field_error(a1, a2) < 3e-6
+    P_ref, F_ref = fo.farfield_dense(Ex, Ey, Hx, Hy, x[1] - x[0], y[1] - y[0], ux, uy, WL, NG)
+    assert power_map_error(P1, P_ref) < FF_TOL and power_map_error(P2, P_ref) < FF_TOL
+    assert field_error(a1[0], F_ref[0]) < 3e-6
