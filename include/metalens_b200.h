@@ -105,6 +105,10 @@ int mlb_cgemm_tc(const float *Ah, const float *Al, int lda, const float *Bh, con
 /* ---- A1 (FFT formulation): shared-memory FFT passes, power-of-two lengths ---- */
 /* out[t] = exp(-2 pi i t / N), float64 phases rounded once to fp32 */
 int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);
+/* Tuning knobs of the row pass (defaults are the B200-tuned values): loader variant (1 = consecutive
+ * samples per thread, all stages in shared memory; 0 = first radix-4 stage done by the loader),
+ * points per CTA, threads per CTA (64/128/256), vector width of the loads (1 or 2 complex). */
+int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_threads, int rows_vec);
 /* longest transform the shared-memory passes support (8192 complex64) */
 int mlb_fft_max_length(void);
 /*

@@ -36,6 +36,7 @@ SIGNATURES = {
                                C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "mlb_fft_twiddle": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_fft_max_length": (C.c_int, []),
+    "mlb_fft_tune": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "mlb_fft_rows": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mlb_fft_cols": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,

@@ -90,26 +90,39 @@ struct FftArgs {
     const float2 *in[4];
     float2 *out[4];
     const float2 *tw;
-    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2;
+    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader;
 };
 
-// folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions)
+// folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
+// The s1*s2 aliased copies are fetched in batches of up to 16 independent loads (all issued before
+// the first add) so that every thread keeps 128-256 bytes in flight: the kernel's HBM phase has to
+// cover for the CTAs that are busy in their FFT stages.
 template <int VEC>
 __device__ __forceinline__ void load_folded(const FftArgs &a, const float2 *__restrict__ in, int rs, int n, int N,
                                             float (&acc)[2 * VEC]) {
 #pragma unroll
     for (int v = 0; v < 2 * VEC; ++v) acc[v] = 0.f;
     int cs = n - a.in_roll_c; if (cs < 0) cs += N;
-    for (int t1 = 0; t1 < a.s1; ++t1) {
-        const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in + cs;
-#pragma unroll 4
-        for (int t2 = 0; t2 < a.s2; ++t2) {
-            if (VEC == 2) {
-                const float4 v = __ldcs(reinterpret_cast<const float4 *>(row + ((size_t)t2 << a.lgN)));
-                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-            } else {
-                const float2 v = __ldcs(row + ((size_t)t2 << a.lgN));
-                acc[0] += v.x; acc[1] += v.y;
+    const int S = a.s1 * a.s2;
+    const float2 *base = in + (size_t)rs * a.ld_in + cs;
+    for (int t0 = 0; t0 < S; t0 += 16) {
+        float4 v4[16];
+        float2 v2[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int t = t0 + u;
+            if (t < S) {
+                const int t1 = t / a.s2, t2 = t - t1 * a.s2;
+                const float2 *ptr = base + (size_t)t1 * a.other * a.ld_in + ((size_t)t2 << a.lgN);
+                if (VEC == 2) v4[u] = __ldcs(reinterpret_cast<const float4 *>(ptr));
+                else v2[u] = __ldcs(ptr);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (t0 + u < S) {
+                if (VEC == 2) { acc[0] += v4[u].x; acc[1] += v4[u].y; acc[2] += v4[u].z; acc[3] += v4[u].w; }
+                else { acc[0] += v2[u].x; acc[1] += v2[u].y; }
             }
         }
     }
@@ -128,7 +141,26 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
     const int row0 = blockIdx.x * L;
     for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[t];     // twiddle table -> shared memory
     int lgNs0;
-    if (a.lgN >= 2) {
+    if (a.plain_loader) {
+        // plain loader: consecutive samples per thread, every FFT stage in shared memory
+        lgNs0 = 0;
+        const int total = (L << a.lgN) / VEC;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int e = idx * VEC;
+            const int lane = e >> a.lgN, n = e & (N - 1);
+            const int r = row0 + lane;
+            float acc[2 * VEC];
+            if (r < a.other) {
+                int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
+                load_folded<VEC>(a, in, rs, n, N, acc);
+            } else {
+#pragma unroll
+                for (int v = 0; v < 2 * VEC; ++v) acc[v] = 0.f;
+            }
+            if (VEC == 2) *reinterpret_cast<float4 *>(buf0 + e) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            else buf0[e] = make_float2(acc[0], acc[1]);
+        }
+    } else if (a.lgN >= 2) {
         lgNs0 = 2;
         const int lgPer = a.lgN - 2, per = 1 << lgPer;
         const int total = (L << lgPer) / VEC;
@@ -246,6 +278,9 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
     out[t] = make_float2((float)c, (float)s);
 }
 
+// tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
+static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2;
+
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 constexpr int FFT_MAX_N = 8192;                     // 2 x 8192 x 8 B = 128 KB of shared memory
@@ -269,6 +304,17 @@ extern "C" int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream) {
     return mlb::check_launch("mlb_fft_twiddle");
 }
 
+extern "C" int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_threads, int rows_vec) {
+    MLB_REQUIRE((rows_threads == 64 || rows_threads == 128 || rows_threads == 256) && rows_points_per_cta >= 1 &&
+                    (rows_vec == 1 || rows_vec == 2),
+                "mlb_fft_tune: bad arguments");
+    mlb::g_rows_plain = rows_plain_loader ? 1 : 0;
+    mlb::g_rows_points = rows_points_per_cta;
+    mlb::g_rows_threads = rows_threads;
+    mlb::g_rows_vec = rows_vec;
+    return MLB_OK;
+}
+
 extern "C" int mlb_fft_max_length(void) { return mlb::FFT_MAX_N; }
 
 extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
@@ -289,10 +335,11 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_rows;
     a.in_roll_r = in_roll_r; a.in_roll_c = in_roll_c; a.out_roll = out_roll; a.s1 = s1; a.s2 = s2;
     int lanes = 1;
-    while (lanes * 2 * N <= 1024 && lanes * 2 <= n_rows) lanes *= 2;      // small transforms: several rows per CTA
+    while (lanes * 2 * N <= mlb::g_rows_points && lanes * 2 <= n_rows) lanes *= 2;   // small transforms: several rows per CTA
     a.lanes = lanes;
+    a.plain_loader = mlb::g_rows_plain;
     const size_t smem = (2 * (size_t)lanes + 1) * N * sizeof(float2);     // ping-pong buffers + twiddle table
-    bool vec = (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
+    bool vec = (mlb::g_rows_vec == 2) && (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
     static bool attr_set = false;            // once per process: keeps launches capturable in CUDA graphs
@@ -303,8 +350,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     }
     // one loader task per thread where possible: small CTAs, many of them per SM, so that some are always
     // in their (HBM-bound) load phase while others run their FFT stages
-    const int tasks = lanes * (N >= 4 ? N / 4 : 1) / (vec ? 2 : 1);
-    const int threads = tasks >= 256 ? 256 : (tasks <= 64 ? 64 : 128);
+    const int threads = mlb::g_rows_threads;
     if (vec) mlb::fft_rows_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     else mlb::fft_rows_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_fft_rows");
