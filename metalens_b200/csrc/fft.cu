@@ -94,45 +94,82 @@ struct FftArgs {
 };
 
 // folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
-// The s1*s2 aliased copies are fetched in batches of up to 16 independent loads (all issued before
-// the first add) so that every thread keeps 128-256 bytes in flight: the kernel's HBM phase has to
-// cover for the CTAs that are busy in their FFT stages.
+// Kept deliberately light (4 loads in flight, ~32 registers/thread): measured on B200, a deeper
+// per-thread load queue costs more in occupancy than it gains (scripts/tune_fft_rows.py).
 template <int VEC>
 __device__ __forceinline__ void load_folded(const FftArgs &a, const float2 *__restrict__ in, int rs, int n, int N,
                                             float (&acc)[2 * VEC]) {
 #pragma unroll
     for (int v = 0; v < 2 * VEC; ++v) acc[v] = 0.f;
     int cs = n - a.in_roll_c; if (cs < 0) cs += N;
-    const int S = a.s1 * a.s2;
-    const float2 *base = in + (size_t)rs * a.ld_in + cs;
-    for (int t0 = 0; t0 < S; t0 += 16) {
-        float4 v4[16];
-        float2 v2[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int t = t0 + u;
-            if (t < S) {
-                const int t1 = t / a.s2, t2 = t - t1 * a.s2;
-                const float2 *ptr = base + (size_t)t1 * a.other * a.ld_in + ((size_t)t2 << a.lgN);
-                if (VEC == 2) v4[u] = __ldcs(reinterpret_cast<const float4 *>(ptr));
-                else v2[u] = __ldcs(ptr);
+    for (int t1 = 0; t1 < a.s1; ++t1) {
+        const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in + cs;
+#pragma unroll 4
+        for (int t2 = 0; t2 < a.s2; ++t2) {
+            if (VEC == 2) {
+                const float4 v = __ldcs(reinterpret_cast<const float4 *>(row + ((size_t)t2 << a.lgN)));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            } else {
+                const float2 v = __ldcs(row + ((size_t)t2 << a.lgN));
+                acc[0] += v.x; acc[1] += v.y;
             }
         }
+    }
+}
+
+// ---- compile-time-sized stages: all index math folds into constants, loops fully unrolled ----------
+template <int R, int LGN, int LGNS, int LANES, int PITCH>
+__device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *__restrict__ y,
+                                         const float2 *__restrict__ tw) {
+    constexpr int lgR = (R == 4) ? 2 : 1;
+    constexpr int lgPer = LGN - lgR, per = 1 << lgPer, total = per * LANES, Ns = 1 << LGNS;
+    constexpr int lgTstep = LGN - LGNS - lgR;
+    constexpr int iters = (total + 255) / 256;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            if (t0 + u < S) {
-                if (VEC == 2) { acc[0] += v4[u].x; acc[1] += v4[u].y; acc[2] += v4[u].z; acc[3] += v4[u].w; }
-                else { acc[0] += v2[u].x; acc[1] += v2[u].y; }
-            }
+    for (int it = 0; it < iters; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        if (total % 256 != 0 && idx >= total) break;
+        const int lane = idx >> lgPer, j = idx & (per - 1);
+        const int k = j & (Ns - 1);
+        const int base_out = ((j - k) << lgR) + k;
+        const float2 *xl = x + lane * PITCH;
+        float2 *yl = y + lane * PITCH;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = xl[j + r * per];
+            if (r > 0 && LGNS > 0) v[r] = cmulf(v[r], tw[(r * k) << lgTstep]);
         }
+        if (R == 4) {
+            bfly4(v[0], v[1], v[2], v[3]);
+        } else {
+            const float2 a0 = caddf(v[0], v[1]), a1 = csubf(v[0], v[1]);
+            v[0] = a0; v[1] = a1;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) yl[base_out + (r << LGNS)] = v[r];
+    }
+}
+
+template <int LGN, int LGNS, int LANES, int PITCH, int CUR>
+__device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *tw) {
+    __syncthreads();
+    if constexpr (LGNS + 2 <= LGN) {
+        stage_ct<4, LGN, LGNS, LANES, PITCH>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
+        return fft_ct<LGN, LGNS + 2, LANES, PITCH, CUR ^ 1>(buf0, buf1, tw);
+    } else if constexpr (LGNS < LGN) {
+        stage_ct<2, LGN, LGNS, LANES, PITCH>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
+        return fft_ct<LGN, LGNS + 1, LANES, PITCH, CUR ^ 1>(buf0, buf1, tw);
+    } else {
+        return CUR;
     }
 }
 
 // rows: `lanes` consecutive rows per CTA, transform along the contiguous axis.  The loader sums the
 // s1 x s2 aliased copies (aperture fold), applies the input fftshift and performs the first radix-4
 // stage in registers, so its shared-memory writes are contiguous 64-byte runs.
-template <int VEC>
-__global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
+template <int VEC, int LGN>
+__global__ void __launch_bounds__(256, (LGN >= 8 && LGN <= 11) ? 8 : 1) fft_rows_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int N = 1 << a.lgN, L = a.lanes;
     float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N, *stw = buf1 + (size_t)L * N;
@@ -203,7 +240,13 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
             buf0[lane * N + 1] = make_float2(x0[0] - x1[0], x0[1] - x1[1]);
         }
     }
-    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, N, stw);
+    int cur;
+    if constexpr (LGN > 0) {
+        constexpr int CL = (1024 >> LGN) > 0 ? (1024 >> LGN) : 1;          // rows per CTA (host uses the same rule)
+        cur = (lgNs0 == 0) ? fft_ct<LGN, 0, CL, (1 << LGN), 0>(buf0, buf1, stw) : fft_ct<LGN, 2, CL, (1 << LGN), 0>(buf0, buf1, stw);
+    } else {
+        cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, N, stw);
+    }
     const float2 *res = cur ? buf1 : buf0;
     const int tot = L << a.lgN;
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
@@ -218,6 +261,7 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const FftArgs a) {
 
 // columns: `lanes` adjacent columns per CTA, transform along the strided axis.  Columns are
 // transposed into [lane][n] shared-memory rows (pitch N+4) while the loader does the first stage.
+template <int LGN, int CL>
 __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int N = 1 << a.lgN, L = a.lanes, P = N + 4;
@@ -257,7 +301,9 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
             buf0[lane * P + 1] = csubf(x0, x1);
         }
     }
-    const int cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, P, stw);
+    int cur;
+    if constexpr (LGN > 0) cur = fft_ct<LGN, 2, CL, (1 << LGN) + 4, 0>(buf0, buf1, stw);
+    else cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, P, stw);
     const float2 *res = cur ? buf1 : buf0;
     const int total = L << a.lgN;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -342,17 +388,38 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     bool vec = (mlb::g_rows_vec == 2) && (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
-    static bool attr_set = false;            // once per process: keeps launches capturable in CUDA graphs
-    if (!attr_set) {
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * mlb::FFT_MAX_N * 8));
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * mlb::FFT_MAX_N * 8));
-        attr_set = true;
+    // Compile-time-sized kernels for 256..8192 points (always 256 threads and max(1, 1024/N) rows per CTA);
+    // the runtime-sized kernel covers the small transforms and the tuning knobs.
+    const int lgN = a.lgN;
+    const bool ct = lgN >= 8 && lgN <= 13 && mlb::g_rows_threads == 256 && mlb::g_rows_points == 1024 &&
+                    lanes == ((1024 >> lgN) > 0 ? (1024 >> lgN) : 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem_max = 3 * mlb::FFT_MAX_N * 8;
+#define MLB_ROWS_LAUNCH(V, LG)                                                                                      \
+    do {                                                                                                            \
+        static bool set_ = false;                                                                                   \
+        if (!set_) {                                                                                                \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<V, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem_max));                                                               \
+            set_ = true;                                                                                            \
+        }                                                                                                           \
+        mlb::fft_rows_kernel<V, LG><<<grid, mlb::g_rows_threads, smem, st>>>(a);                                    \
+    } while (0)
+#define MLB_ROWS_CASE(LG)                                  \
+    case LG:                                               \
+        if (vec) MLB_ROWS_LAUNCH(2, LG);                   \
+        else MLB_ROWS_LAUNCH(1, LG);                       \
+        break;
+    if (ct) {
+        switch (lgN) {
+            MLB_ROWS_CASE(8) MLB_ROWS_CASE(9) MLB_ROWS_CASE(10) MLB_ROWS_CASE(11) MLB_ROWS_CASE(12) MLB_ROWS_CASE(13)
+        }
+    } else {
+        if (vec) MLB_ROWS_LAUNCH(2, 0);
+        else MLB_ROWS_LAUNCH(1, 0);
     }
-    // one loader task per thread where possible: small CTAs, many of them per SM, so that some are always
-    // in their (HBM-bound) load phase while others run their FFT stages
-    const int threads = mlb::g_rows_threads;
-    if (vec) mlb::fft_rows_kernel<2><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
-    else mlb::fft_rows_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(a);
+#undef MLB_ROWS_CASE
+#undef MLB_ROWS_LAUNCH
     return mlb::check_launch("mlb_fft_rows");
 }
 
@@ -372,12 +439,27 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 4) * sizeof(float2) <= 66 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
     a.lanes = lanes;
     const size_t smem = (2 * (size_t)lanes * (N + 4) + N) * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * mlb::FFT_MAX_N + 8) * 8));
-        attr_set = true;
-    }
-    dim3 grid((n_cols + lanes - 1) / lanes, batch);
-    mlb::fft_cols_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem_max = (3 * mlb::FFT_MAX_N + 8) * 8;
+#define MLB_COLS_LAUNCH(LG, CL)                                                                                      \
+    do {                                                                                                             \
+        static bool set_ = false;                                                                                    \
+        if (!set_) {                                                                                                 \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem_max));                                                                \
+            set_ = true;                                                                                             \
+        }                                                                                                            \
+        dim3 grid((n_cols + lanes - 1) / lanes, batch);                                                              \
+        mlb::fft_cols_kernel<LG, CL><<<grid, 256, smem, st>>>(a);                                                    \
+    } while (0)
+    // compile-time-sized kernels when the lane count is the canonical one for that length
+    if (a.lgN == 8 && lanes == 16) MLB_COLS_LAUNCH(8, 16);
+    else if (a.lgN == 9 && lanes == 8) MLB_COLS_LAUNCH(9, 8);
+    else if (a.lgN == 10 && lanes == 4) MLB_COLS_LAUNCH(10, 4);
+    else if (a.lgN == 11 && lanes == 2) MLB_COLS_LAUNCH(11, 2);
+    else if (a.lgN == 12 && lanes == 1) MLB_COLS_LAUNCH(12, 1);
+    else if (a.lgN == 13 && lanes == 1) MLB_COLS_LAUNCH(13, 1);
+    else MLB_COLS_LAUNCH(0, 0);
+#undef MLB_COLS_LAUNCH
     return mlb::check_launch("mlb_fft_cols");
 }
