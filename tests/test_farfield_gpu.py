@@ -381,7 +381,7 @@ def test_tensor_core_path_matches_reference(golden_dir):
     a1 = tc.amplitudes().cpu().numpy()
     P2 = simt.run(dev)[0].cpu().numpy()
     a2 = simt.amplitudes().cpu().numpy()
-    assert field_error(a1, a2) < 3e-6
+    assert field_error(a1, a2) < 2e-5          # truncating tensor-core accumulation, see above
     P_ref, F_ref = fo.farfield_dense(Ex, Ey, Hx, Hy, x[1] - x[0], y[1] - y[0], ux, uy, WL, NG)
     assert power_map_error(P1, P_ref) < FF_TOL and power_map_error(P2, P_ref) < FF_TOL
-    assert field_error(a1[0], F_ref[0]) < 3e-6
+    assert field_error(a1[0], F_ref[0]) < 2e-5 and field_error(a2[0], F_ref[0]) < 3e-6
