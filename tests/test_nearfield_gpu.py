@@ -153,3 +153,32 @@ def test_table_callable_matches_oracle():
     assert np.abs(got - ref).max() <= 1e-14 * np.abs(ref).max()
     with pytest.raises(ValueError):
         f(np.array([[hi[0] * 1.01 + 1, lo[1], lo[2]]]))
+
+
+def test_lens_to_far_field_pipeline_on_device(golden_dir):
+    """SURVEY KAT-5 / BASELINE cfg4 shape: GratingCollection + HexGridSet lens -> aperture fields
+    (complex64, stays on the GPU) -> far-field power map, against the reference chain restated by the
+    oracles (build_nearfield -> fft2(fftshift) -> farfield_from_nearfield)."""
+    from oracle import farfield_oracle as fo
+    from oracle import nearfield_oracle as no
+    from metalens_b200.farfield import FarfieldPlan
+    from metalens_b200.nearfield import NearfieldPlan
+    g = np.load(os.path.join(golden_dir, "nearfield_small_x_onaxis.npz"))
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    periph = periphery_from(g, collections)
+    f = float(-g["source"][2])
+    # power-of-two grid over the lens so the FFT path is exercised; spacing < lambda/2
+    x = np.linspace(-12e-6, 12e-6, 128)
+    nf = NearfieldPlan(580e-9, periph, g["center"], hgs)
+    fields, p_in = nf.run(0.0, 0.0, -f, "x", x, x)
+    ff = FarfieldPlan((128, 128), x[1] - x[0], x[1] - x[0], 580e-9, nf.n_glass, stride=1)
+    assert ff.method == "fft"
+    P, total = ff.run([fields[i][:, :128] for i in range(4)])
+    ref_fields = no.build_nearfield(0.0, 0.0, -f, "x", 580e-9, periph, g["center"], hgs, x_pts=x, y_pts=x)
+    P_ref, total_ref, *_ = fo.farfield_reference_path(*ref_fields[:4], x, x, 580e-9, ref_fields[7])
+    from parity import power_map_error
+    assert power_map_error(P.cpu().numpy(), P_ref) < 1e-5
+    assert abs(total.item() - total_ref) <= 1e-5 * abs(total_ref)
+    assert abs(p_in.item() - ref_fields[6]) <= 1e-11 * abs(ref_fields[6])
+    # the lens transmits most of the incident power into propagating far-field bins
+    assert 0.05 < total.item() / p_in.item() < 1.5
