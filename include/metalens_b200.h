@@ -164,12 +164,14 @@ int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream
  *   values : complex128 [order][iu][iv][ig][slot], slot = 2*pol + amp
  *            (pol 0='x',1='y'; amp 0='ampfy',1='ampfx'), i.e. grating.py:1186-1232 /
  *            lens_center.py:188-226 tables with the four values one corner needs adjacent
+ *   values_f32 : the same table as complex64 (float pairs), read by the complex64-output path
  *   orders : int32 [n_orders][2] = (ox,oy) in the reference's loop order (nearfield.py:264)
  *   bounds : interpolator_bounds 6-tuple (grating.py:1230-1232)
  *   stats_slot : first slot of this pack in the `stats` array of mlb_nearfield_assemble */
 typedef struct mlb_table_pack {
     const double *axes;
     const double *values;
+    const float *values_f32;
     const int *orders;
     int n_ux, n_uy, n_g, n_orders;
     double bounds[6];

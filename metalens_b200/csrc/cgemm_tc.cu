@@ -9,8 +9,11 @@
 //   Both operands are K-major, i.e. exactly the layout TMA + UMMA descriptors (SWIZZLE_128B) want.
 //
 //   TF32 keeps 10 mantissa bits; the 1e-5 parity target needs more, so every operand is split into
-//   hi = tf32(x), lo = tf32(x - hi) and   D += Ah.Bh + Al.Bh + Ah.Bl   (the dropped Al.Bl term is
-//   2^-22 relative).  All three products accumulate into the same fp32 TMEM accumulator.
+//   hi = tf32(x), lo = tf32(x - hi) and   D = sum Ah.Bh  +  sum (Al.Bh + Ah.Bl)   (the dropped Al.Bl
+//   term is 2^-22 relative).  The tensor core adds into its fp32 accumulator with truncation, so the
+//   large main term and the 2^-11-times-smaller correction term get SEPARATE TMEM accumulators
+//   (2 x 256 columns = all of TMEM) and are summed in fp32 by the epilogue: the correction products no
+//   longer cost a truncation of the big accumulator each (3x fewer biased roundings).
 //
 // Kernel anatomy (one 128 x 256 real output tile per CTA, 192 threads):
 //   warp 0 : TMA producer  (cp.async.bulk.tensor 2-D, 4 operand tiles per k-block, mbarrier tx)
@@ -126,7 +129,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         mbar_init(tmem_full, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TC_BN);          // 256 fp32 columns x 128 lanes
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * TC_BN);      // main + correction accumulators: 512 columns x 128 lanes
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -160,9 +163,9 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {          // UMMA K = 8 tf32 = 32 bytes -> +2 in the >>4 address field
                     const uint64_t adv = (uint64_t)(kk * 2);
-                    umma_tf32(tmem_d, dAh + adv, dBh + adv, TC_IDESC, (kb | kk) != 0);
-                    umma_tf32(tmem_d, dAl + adv, dBh + adv, TC_IDESC, 1);
-                    umma_tf32(tmem_d, dAh + adv, dBl + adv, TC_IDESC, 1);
+                    umma_tf32(tmem_d, dAh + adv, dBh + adv, TC_IDESC, (kb | kk) != 0);           // main term
+                    umma_tf32(tmem_d + TC_BN, dAl + adv, dBh + adv, TC_IDESC, (kb | kk) != 0);   // corrections
+                    umma_tf32(tmem_d + TC_BN, dAh + adv, dBl + adv, TC_IDESC, 1);
                 }
                 umma_commit(&empty[s]);                           // smem slot free once these MMAs have read it
             }
@@ -175,8 +178,11 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         const int lane_base = (warp & 3) * 32;                    // TMEM lanes this warp may touch
         const int row = m0 + lane_base + lane;                    // real output row held by this thread
         for (int c = 0; c < TC_BN; c += 16) {
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+            tmem_ld16(tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)(TC_BN + c), w);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
             if (row < a.rows) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -202,7 +208,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_d, TC_BN);
+    if (warp == 1) tmem_dealloc(tmem_d, 2 * TC_BN);
 }
 
 // ---- operand preparation kernels ----------------------------------------------------------------------

@@ -81,6 +81,97 @@ __device__ __forceinline__ void gather4(const mlb_table_pack &p, int order, cons
     }
 }
 
+// e^{i x}: float64 sincos for the complex128 output; for the complex64 output the argument is reduced
+// to [-pi, pi] in float64 (exact to ~1e-16 turns) and the sine/cosine taken in fp32 (abs. error
+// ~1e-7, below the output's own rounding).
+template <bool FAST>
+__device__ __forceinline__ cplx expi(double x) {
+    if (FAST) {
+        const double t = x * 0.15915494309189535;                 // x / 2 pi
+        const float f = (float)((t - rint(t)) * 6.283185307179586);
+        float s, c;
+        sincosf(f, &s, &c);
+        return {(double)c, (double)s};
+    }
+    double s, c;
+    sincos(x, &s, &c);
+    return {c, s};
+}
+
+// fp32 versions for the complex64 output path: tables read from the float2 copy of the pack, the
+// order's contribution formed in fp32 (relative error ~1e-7, below the output rounding) and added
+// to the float64 per-sample accumulators.
+struct cf { float re, im; };
+__device__ __forceinline__ cf operator+(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cf operator*(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cf operator*(cf a, float s) { return {a.re * s, a.im * s}; }
+__device__ __forceinline__ cf operator*(float s, cf a) { return {a.re * s, a.im * s}; }
+
+__device__ __forceinline__ void gather4f(const mlb_table_pack &p, int order, const Interp3 &q, cf (&amp)[4]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) amp[s] = {0.f, 0.f};
+    const size_t per_order = (size_t)p.n_ux * p.n_uy * p.n_g;
+    const float4 *__restrict__ base = reinterpret_cast<const float4 *>(p.values_f32) + (size_t)order * per_order * 2;
+    const float t0 = (float)q.t0, t1 = (float)q.t1, t2 = (float)q.t2;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const float wa = a ? t0 : 1.f - t0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const float wb = b ? t1 : 1.f - t1;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float w = wa * wb * (c ? t2 : 1.f - t2);
+                const float4 *v = base + (((size_t)(q.i0 + a) * p.n_uy + (q.i1 + b)) * p.n_g + (q.i2 + c)) * 2;
+                const float4 x0 = __ldg(v), x1 = __ldg(v + 1);          // slots (0,1) and (2,3)
+                amp[0].re = fmaf(x0.x, w, amp[0].re); amp[0].im = fmaf(x0.y, w, amp[0].im);
+                amp[1].re = fmaf(x0.z, w, amp[1].re); amp[1].im = fmaf(x0.w, w, amp[1].im);
+                amp[2].re = fmaf(x1.x, w, amp[2].re); amp[2].im = fmaf(x1.y, w, amp[2].im);
+                amp[3].re = fmaf(x1.z, w, amp[3].re); amp[3].im = fmaf(x1.w, w, amp[3].im);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void add_order_f(const cf (&amp)[4], float Hw_x, float Hw_y, float kx, float ky, float kz,
+                                            float f, cf phase, cplx &Ea, cplx &Eb, cplx &Ha, cplx &Hb) {
+    const cf Sfy = Hw_x * amp[0] + Hw_y * amp[2];
+    const cf Sfx = Hw_x * amp[1] + Hw_y * amp[3];
+    const cf ea = ((Sfy * (kx * ky) + Sfx * (ky * ky + kz * kz)) * f) * phase;
+    const cf eb = ((Sfy * (-kx * kx - kz * kz) + Sfx * (-kx * ky)) * f) * phase;
+    const cf ha = Sfy * phase, hb = Sfx * phase;
+    Ea.re += ea.re; Ea.im += ea.im; Eb.re += eb.re; Eb.im += eb.im;
+    Ha.re += ha.re; Ha.im += ha.im; Hb.re += hb.re; Hb.im += hb.im;
+}
+
+__device__ __forceinline__ void add_order(const cplx (&amp)[4], double Hw_x, double Hw_y, double kx, double ky,
+                                          double kz, double inv_kg_n, double Z0, cplx phase, cplx &Ea, cplx &Eb,
+                                          cplx &Ha, cplx &Hb);
+
+// one diffraction order, either precision.  kx, ky are in units of kvac in the fp32 path so that the
+// products stay well inside the fp32 range; the common factor Z0 kvac / (k_g n) is applied via `f`.
+template <bool FAST>
+__device__ __forceinline__ void order_term(const mlb_table_pack &p, int o, const Interp3 &q, double Hw_x, double Hw_y,
+                                           double kx, double ky, double kg, double kvac, double inv_kg_n, double Z0,
+                                           double phase_arg, cplx &Ea, cplx &Eb, cplx &Ha, cplx &Hb) {
+    if (FAST) {
+        const float nx = (float)(kx / kvac), ny = (float)(ky / kvac);
+        const float ng2 = (float)((kg / kvac) * (kg / kvac));
+        const float nz = sqrtf(ng2 - nx * nx - ny * ny);
+        const cplx ph = expi<true>(phase_arg);
+        cf amp[4];
+        gather4f(p, o, q, amp);
+        const float f = (float)(Z0 * inv_kg_n * kvac) / nz;
+        add_order_f(amp, (float)Hw_x, (float)Hw_y, nx, ny, nz, f, {(float)ph.re, (float)ph.im}, Ea, Eb, Ha, Hb);
+    } else {
+        const double kz = sqrt(kg * kg - kx * kx - ky * ky);
+        const cplx ph = expi<false>(phase_arg);
+        cplx amp[4];
+        gather4(p, o, q, amp);
+        add_order(amp, Hw_x, Hw_y, kx, ky, kz, inv_kg_n, Z0, ph, Ea, Eb, Ha, Hb);
+    }
+}
+
 // one diffraction order's contribution (nearfield.py:306-327 / :420-441), both incident
 // polarisations and both amplitudes at once:
 //   E_a += Z0 [ S_fy kx ky + S_fx (ky^2+kz^2) ] / (k_g kz n) * phase
@@ -128,23 +219,6 @@ struct NfOut {
 __device__ __forceinline__ void store_c(void *base, size_t off, cplx v, int is_double) {
     if (is_double) reinterpret_cast<double2 *>(base)[off] = make_double2(v.re, v.im);
     else reinterpret_cast<float2 *>(base)[off] = make_float2((float)v.re, (float)v.im);
-}
-
-// e^{i x}: float64 sincos for the complex128 output; for the complex64 output the argument is reduced
-// to [-pi, pi] in float64 (exact to ~1e-16 turns) and the sine/cosine taken in fp32 (abs. error
-// ~1e-7, below the output's own rounding).
-template <bool FAST>
-__device__ __forceinline__ cplx expi(double x) {
-    if (FAST) {
-        const double t = x * 0.15915494309189535;                 // x / 2 pi
-        const float f = (float)((t - rint(t)) * 6.283185307179586);
-        float s, c;
-        sincosf(f, &s, &c);
-        return {(double)c, (double)s};
-    }
-    double s, c;
-    sincos(x, &s, &c);
-    return {c, s};
 }
 
 template <bool STATS, bool FAST>
@@ -221,11 +295,9 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
                     if (kxp * kxp + kyp * kyp <= kvac * kvac) {                            // :279
                         record<STATS>(p, o, uxp, uyp, gp, true, out.stats, out.violation);
                         if (!located) { q = locate(p, uxp, uyp, gp); located = true; }
-                        const double kzp = sqrt(kg * kg - kxp * kxp - kyp * kyp);           // :287
-                        const cplx ph = expi<FAST>(kxp * xp + kyp * yp);                    // :291
-                        cplx amp[4];
-                        gather4(p, o, q, amp);
-                        add_order(amp, Hw_x, Hw_y, kxp, kyp, kzp, inv_kg_n, L.Z0, ph, Exp, Eyp, Hxp, Hyp);
+                        // kzp (:287), phase about the grating centre (:291), table gathers, accumulation
+                        order_term<FAST>(p, o, q, Hw_x, Hw_y, kxp, kyp, kg, kvac, inv_kg_n, L.Z0, kxp * xp + kyp * yp,
+                                         Exp, Eyp, Hxp, Hyp);
                     }
                 }
             }
@@ -291,11 +363,9 @@ __global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_cons
                     if (kx * kx + ky * ky <= kvac * kvac) {                                        // :398
                         record<STATS>(p, o, ux, uy, which, false, out.stats, out.violation);
                         if (!located) { q = locate(p, ux, uy, which); located = true; }
-                        const double kz = sqrt(kg * kg - kx * kx - ky * ky);                        // :404
-                        const cplx ph = expi<FAST>(kx * (x - cx) + ky * (y - cy));                  // :408-409
-                        cplx amp[4];
-                        gather4(p, o, q, amp);
-                        add_order(amp, Hw_x, Hw_y, kx, ky, kz, inv_kg_n, L.Z0, ph, Ex, Ey, Hx, Hy);
+                        // kz (:404), phase about the cell centre (:408-409), gathers, accumulation
+                        order_term<FAST>(p, o, q, Hw_x, Hw_y, kx, ky, kg, kvac, inv_kg_n, L.Z0,
+                                         kx * (x - cx) + ky * (y - cy), Ex, Ey, Hx, Hy);
                     }
                 }
                 if (!L.plane_wave) {                                                // :453-461
@@ -358,7 +428,8 @@ __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n
 extern "C" int mlb_nearfield_blocks(int nx, int ny) { return nx * ((ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS); }
 
 static int check_pack(const mlb_table_pack &p, const char *what) {
-    MLB_REQUIRE(p.axes && p.values && p.orders, "mlb_nearfield_assemble: %s pack has NULL arrays", what);
+    MLB_REQUIRE(p.axes && p.values && p.values_f32 && p.orders, "mlb_nearfield_assemble: %s pack has NULL arrays", what);
+    MLB_REQUIRE(mlb::aligned16(p.values_f32), "mlb_nearfield_assemble: %s pack values_f32 not 16-byte aligned", what);
     MLB_REQUIRE(p.n_ux >= 2 && p.n_uy >= 2 && p.n_g >= 2 && p.n_orders >= 0,
                 "mlb_nearfield_assemble: %s pack needs >= 2 nodes per axis (%d,%d,%d)", what, p.n_ux, p.n_uy, p.n_g);
     MLB_REQUIRE(mlb::aligned16(p.values), "mlb_nearfield_assemble: %s pack values not 16-byte aligned", what);

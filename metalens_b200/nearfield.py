@@ -26,7 +26,7 @@ STATS_PER_ORDER = 8
 
 
 class _PackC(C.Structure):
-    _fields_ = [("axes", C.c_void_p), ("values", C.c_void_p), ("orders", C.c_void_p),
+    _fields_ = [("axes", C.c_void_p), ("values", C.c_void_p), ("values_f32", C.c_void_p), ("orders", C.c_void_p),
                 ("n_ux", C.c_int), ("n_uy", C.c_int), ("n_g", C.c_int), ("n_orders", C.c_int),
                 ("bounds", C.c_double * 6), ("stats_slot", C.c_int), ("_pad", C.c_int)]
 
@@ -132,7 +132,9 @@ class NearfieldPlan:
         for p in self.packs + [self.hex_pack]:
             p.stats_slot = slot
             slot += len(p.orders)
-            self._pack_dev.append((up(p.axes, np.float64), up(p.values.reshape(-1).view(np.float64), np.float64),
+            flat = p.values.reshape(-1)
+            self._pack_dev.append((up(p.axes, np.float64), up(flat.view(np.float64), np.float64),
+                                   up(flat.astype(np.complex64).view(np.float32), np.float32),
                                    up(p.order_array, np.int32)))
         self.n_stats = slot
 
@@ -166,7 +168,7 @@ class NearfieldPlan:
     # ------------------------------------------------------------------
     def _pack_struct(self, pack, dev_arrays):
         s = _PackC()
-        s.axes, s.values, s.orders = (t.data_ptr() for t in dev_arrays)
+        s.axes, s.values, s.values_f32, s.orders = (t.data_ptr() for t in dev_arrays)
         s.n_ux, s.n_uy, s.n_g = pack.n
         s.n_orders = len(pack.orders)
         for k in range(6):

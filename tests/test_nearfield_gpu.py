@@ -59,7 +59,7 @@ def test_complex64_device_output_and_big(golden_dir):
     assert out.dtype == torch.complex64
     got = out[:, :, :g["y_pts"].size].cpu().numpy()
     for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
-        assert field_error(got[k], g[key]) < 1e-6
+        assert field_error(got[k], g[key]) < 3e-6      # fp32 order terms, complex64 output
     assert abs(power.item() - g["power"]) <= 1e-11 * abs(g["power"])
     res = build_nearfield_big(0.0, 0.0, float(g["source"][2]), "x", 580e-9, periph, g["center"], hgs,
                               x_pts=g["x_pts"], y_pts=g["y_pts"])
