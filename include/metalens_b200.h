@@ -219,6 +219,8 @@ typedef struct mlb_lens_desc {
  * (int64, order-preserving encoding of doubles; see metalens_b200/nearfield.py).
  */
 int mlb_nearfield_blocks(int nx, int ny);
+/* tuning knob: register budget variant of the complex64 kernel (min resident blocks/SM: 1, 5 or 6) */
+int mlb_nearfield_tune(int min_blocks);
 int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
                            int out_is_double, double *power_block_sums, long long *stats, int want_stats,
                            int *violation, void *stream);

@@ -221,8 +221,8 @@ __device__ __forceinline__ void store_c(void *base, size_t off, cplx v, int is_d
     else reinterpret_cast<float2 *>(base)[off] = make_float2((float)v.re, (float)v.im);
 }
 
-template <bool STATS, bool FAST>
-__global__ void __launch_bounds__(NF_THREADS) nearfield_kernel(const __grid_constant__ mlb_lens_desc L, const NfOut out) {
+template <bool STATS, bool FAST, int MINB>
+__global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __grid_constant__ mlb_lens_desc L, const NfOut out) {
     const int j = blockIdx.x * NF_THREADS + threadIdx.x;   // y index (fast)
     const int i = blockIdx.y;                              // x index
     const double PI = 3.14159265358979323846;
@@ -425,6 +425,14 @@ __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n
 
 }  // namespace mlb
 
+static int g_nf_minblocks = 1;
+/* tuning knob: minimum resident blocks per SM the complex64 kernel is compiled for (1, 5 or 6) */
+extern "C" int mlb_nearfield_tune(int min_blocks) {
+    MLB_REQUIRE(min_blocks == 1 || min_blocks == 5 || min_blocks == 6, "mlb_nearfield_tune: min_blocks must be 1, 5 or 6");
+    g_nf_minblocks = min_blocks;
+    return MLB_OK;
+}
+
 extern "C" int mlb_nearfield_blocks(int nx, int ny) { return nx * ((ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS); }
 
 static int check_pack(const mlb_table_pack &p, const char *what) {
@@ -467,11 +475,13 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     dim3 grid((L.ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS, L.nx);
     const cudaStream_t st = (cudaStream_t)stream;
     if (want_stats) {
-        if (out_is_double) mlb::nearfield_kernel<true, false><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
-        else mlb::nearfield_kernel<true, true><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        if (out_is_double) mlb::nearfield_kernel<true, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        else mlb::nearfield_kernel<true, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
     } else {
-        if (out_is_double) mlb::nearfield_kernel<false, false><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
-        else mlb::nearfield_kernel<false, true><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        if (out_is_double) mlb::nearfield_kernel<false, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        else if (g_nf_minblocks == 5) mlb::nearfield_kernel<false, true, 5><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        else if (g_nf_minblocks == 6) mlb::nearfield_kernel<false, true, 6><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        else mlb::nearfield_kernel<false, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
     }
     return mlb::check_launch("mlb_nearfield_assemble");
 }
