@@ -425,7 +425,7 @@ __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n
 
 }  // namespace mlb
 
-static int g_nf_minblocks = 1;
+static int g_nf_minblocks = 5;   // 96 registers, 5 blocks/SM: fastest on B200 (scripts/tune_nearfield.py)
 /* tuning knob: minimum resident blocks per SM the complex64 kernel is compiled for (1, 5 or 6) */
 extern "C" int mlb_nearfield_tune(int min_blocks) {
     MLB_REQUIRE(min_blocks == 1 || min_blocks == 5 || min_blocks == 6, "mlb_nearfield_tune: min_blocks must be 1, 5 or 6");
