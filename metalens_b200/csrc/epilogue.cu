@@ -24,6 +24,16 @@ __device__ __forceinline__ double cabs2(cd a) { return a.re * a.re + a.im * a.im
 
 constexpr int EPI_THREADS = 256;
 
+struct cfl { float re, im; };
+__device__ __forceinline__ cfl fmul(cfl a, float s) { return {a.re * s, a.im * s}; }
+__device__ __forceinline__ cfl fadd(cfl a, cfl b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cfl fsub(cfl a, cfl b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ float fabs2(cfl a) { return a.re * a.re + a.im * a.im; }
+
+// F32: the float32-output flavour.  The evanescent mask and the DC test stay in float64 (bit-identical
+// to the reference); the polar projections and |.|^2 run in fp32 (relative error ~1e-7, the inputs are
+// complex64 anyway), which makes the kernel memory- instead of FP64-pipe-bound.
+template <bool F32>
 __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
     const long long n = (long long)blockIdx.x * EPI_THREADS + threadIdx.x;
     const long long total = (long long)a.Kx * a.Ky;
@@ -44,6 +54,36 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
         // evanescent (NaN) mask is bit-identical to the reference's (:153-155).
         const double ux2 = __dmul_rn(ux, ux), uy2 = __dmul_rn(uy, uy);
         const double uz2 = __dsub_rn(__dsub_rn(1.0, ux2), uy2);
+        if (F32) {
+            // raw aperture sums here; the common factor amp_scale^2 is applied in float64 at the end, so the
+            // fp32 part never sees the (unit-system dependent) dx*dy scale
+            const cfl nx = {-fhy.x, -fhy.y}, ny = {fhx.x, fhx.y};
+            const cfl lx = {fey.x, fey.y}, ly = {-fex.x, -fex.y};
+            cfl nth, nph, lth, lph;
+            float uzf;
+            if (uz2 < 0.0) {
+                uzf = CUDART_NAN_F;
+                nth = nph = lth = lph = {CUDART_NAN_F, CUDART_NAN_F};
+            } else {
+                uzf = sqrtf((float)uz2);
+                if (ux == 0.0 && uy == 0.0) {
+                    nth = nx; nph = ny; lth = lx; lph = ly;
+                } else {
+                    const float inv = 1.0f / ((float)sqrt(__dadd_rn(ux2, uy2)) + 1e-9f);
+                    const float px = (float)ux * inv, py = (float)uy * inv, cx = px * uzf, cy = py * uzf;
+                    nth = fadd(fmul(nx, cx), fmul(ny, cy));
+                    nph = fsub(fmul(ny, px), fmul(nx, py));
+                    lth = fadd(fmul(lx, cx), fmul(ly, cy));
+                    lph = fsub(fmul(ly, px), fmul(lx, py));
+                }
+            }
+            const float Zf = (float)a.Z;
+            const float mag = fabs2(fadd(lph, fmul(nth, Zf))) + fabs2(fsub(lth, fmul(nph, Zf)));
+            p = a.pref * s_ * s_ * (double)mag / ((double)uzf + 1e-5) * 2.0;
+            const float pf = (float)p;
+            reinterpret_cast<float *>(a.P)[(size_t)i * a.ldp + j] = pf;
+            finite = isfinite(pf);
+        } else {
         const double uz = (uz2 < 0.0) ? CUDART_NAN : sqrt(uz2);
         const double sinth = sqrt(__dadd_rn(ux2, uy2));
         const double d = sinth + 1e-9;                                    // :158 regulariser
@@ -64,6 +104,7 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
         if (a.p_is_double) reinterpret_cast<double *>(a.P)[po] = p;
         else reinterpret_cast<float *>(a.P)[po] = (float)p;
         finite = isfinite(p);
+        }
     }
     if (a.block_sums) {                                                   // :74 total_P over finite bins
         double v = finite ? p : 0.0;
@@ -160,7 +201,8 @@ extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const doub
     const double k = 2 * pi * n_glass / wavelength;
     a.pref = k * k / (32 * pi * pi * a.Z);                                  // :184
     a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double;
-    mlb::ff_epilogue_kernel<<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
+    if (p_is_double) mlb::ff_epilogue_kernel<false><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
+    else mlb::ff_epilogue_kernel<true><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_ff_epilogue");
 }
 
