@@ -376,11 +376,38 @@ def ours(args):
                     unit="TFLOP/s", frac=ach / fp32_peak, traffic=None,
                     peak_source="nominal 148 SM x 128 FMA/clk x 2 x 1.965 GHz; bf16 tensor peak %s TF/s for context"
                                 % peaks["bf16_tflops"])
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        t = json.load(open(tr)).get(args.workload, {}).get(dom)
+        if t:
+            roof["traffic"] = t["dram_bytes_per_launch"]
+            roof["traffic_source"] = t["source"]
     step_kernel_s = sum(k["seconds"] for k in kernels.values())
     roof["share_of_step"] = kd["seconds"] / step_kernel_s
     if "fold" in kernels:
         a = kernels["fold"]["bytes"] / kernels["fold"]["seconds"] / 1e9
         roof["fold_hbm"] = dict(achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
+
+    # ---- BASELINE configs[1] (2048^2 -> 512^2, TE+TM) on the same code path, for the record
+    other = None
+    if world == 1 and not args.no_paths and args.workload == "cfg3":
+        w2 = WORKLOADS["cfg2"]
+        M2, K2 = w2["M"], w2["M"] // w2["stride"]
+        f2, p2 = [], []
+        for i, (wl, ng, rot) in enumerate(w2["items"]):
+            Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M2, 2000 + i, wl, ng, rotate=rot)
+            f2.append([torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)])
+            p2.append(FarfieldPlan((M2, M2), float(x[1] - x[0]), float(x[1] - x[0]), wl, ng, stride=w2["stride"],
+                                   method=args.method))
+
+        def step_cfg2():
+            for pl, fl in zip(p2, f2):
+                pl.run(fl)
+        t2, _, _, _ = timed(step_cfg2, args.steps, args.warmup)
+        other = {"cfg2": {"workload": w2["name"], "method": p2[0].method,
+                          "value": len(p2) * K2 * K2 * args.steps / t2, "ms_per_step": t2 / args.steps * 1e3,
+                          "note": "268 MB of inputs per step: larger than L2"}}
+        del f2, p2
 
     nf = None
     if rank == 0 and world == 1 and not args.no_nearfield:
@@ -406,6 +433,7 @@ def ours(args):
             "kernels": {k: dict(ms=v["seconds"] * 1e3, gbs=v["bytes"] / v["seconds"] / 1e9,
                                 tflops=v["flops"] / v["seconds"] / 1e12) for k, v in kernels.items()},
             "paths_points_per_s": paths,
+            "other_workloads": other,
             "nearfield_assembly": nf,
             "cpu_baseline": cpu,
         }
