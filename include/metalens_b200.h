@@ -99,8 +99,11 @@ int mlb_fold(const mlb_c64 *const *h_J, int ldj, int M1, int M2, int s1, int s2,
 int mlb_tf32_split(const float *in, int ld_in, float *hi, float *lo, int ld_out, int rows, int cols, void *stream);
 int mlb_twiddle_tf32(const double *coord, int n_coord, const double *u, int n_u, double scale, int layout,
                      float *hi, float *lo, int ld, void *stream);
-int mlb_cgemm_tc(const float *Ah, const float *Al, int lda, const float *Bh, const float *Bl, int ldb,
-                 int rows, int cols_c, int depth_c, int mode, float *out_hi, float *out_lo, int ldo, void *stream);
+/* batch <= 4 problems of identical shape in one launch (host arrays of device pointers; repeat a
+ * pointer to share an operand between items, e.g. the twiddles across the four fields) */
+int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,
+                 const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
+                 float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream);
 
 /* ---- A1 (FFT formulation): shared-memory FFT passes, power-of-two lengths ---- */
 /* out[t] = exp(-2 pi i t / N), float64 phases rounded once to fp32 */

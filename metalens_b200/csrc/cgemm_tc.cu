@@ -102,8 +102,12 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=256, M=128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
+struct alignas(64) TcMaps {   // per batch item: A hi, A lo, B hi, B lo
+    CUtensorMap m[4][4];
+};
+
 struct TcArgs {
-    float *out_hi, *out_lo;   // mode 1: embedded operand hi / lo;  mode 2: out_hi = complex64 result
+    float *out_hi[4], *out_lo[4];   // mode 1: embedded operand hi / lo;  mode 2: out_hi = complex64 result
     int ldo;                  // floats (mode 1) or complex elements (mode 2)
     int rows, cols_c;         // valid output rows (real M) and complex columns (N/2)
     int k_blocks;
@@ -111,8 +115,9 @@ struct TcArgs {
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcArgs a) {
+cgemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
+    const CUtensorMap *mapAh = &maps.m[blockIdx.z][0], *mapAl = &maps.m[blockIdx.z][1];
+    const CUtensorMap *mapBh = &maps.m[blockIdx.z][2], *mapBl = &maps.m[blockIdx.z][3];
     extern __shared__ unsigned char tc_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(base + TC_STAGES * TC_STAGE_BYTES);
@@ -144,10 +149,10 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                 unsigned char *st = base + s * TC_STAGE_BYTES;
                 mbar_expect_tx(&full[s], TC_STAGE_BYTES);
                 const int k0 = kb * TC_BK;
-                tma_load_2d(st, &mapAh, k0, m0, &full[s]);
-                tma_load_2d(st + TC_A_BYTES, &mapAl, k0, m0, &full[s]);
-                tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, k0, n0, &full[s]);
-                tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, k0, n0, &full[s]);
+                tma_load_2d(st, mapAh, k0, m0, &full[s]);
+                tma_load_2d(st + TC_A_BYTES, mapAl, k0, m0, &full[s]);
+                tma_load_2d(st + 2 * TC_A_BYTES, mapBh, k0, n0, &full[s]);
+                tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, mapBl, k0, n0, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -176,6 +181,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int lane_base = (warp & 3) * 32;                    // TMEM lanes this warp may touch
+        float *const out_hi = pick4(a.out_hi, blockIdx.z), *const out_lo = pick4(a.out_lo, blockIdx.z);
         const int row = m0 + lane_base + lane;                    // real output row held by this thread
         for (int c = 0; c < TC_BN; c += 16) {
             uint32_t v[16], w[16];
@@ -195,12 +201,12 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                         split_tf32(re, rh, rl);
                         split_tf32(im, ih, il);
                         const size_t o0 = (size_t)(2 * jc) * a.ldo + 2 * row, o1 = o0 + a.ldo;
-                        *reinterpret_cast<float2 *>(a.out_hi + o0) = make_float2(rh, -ih);
-                        *reinterpret_cast<float2 *>(a.out_hi + o1) = make_float2(ih, rh);
-                        *reinterpret_cast<float2 *>(a.out_lo + o0) = make_float2(rl, -il);
-                        *reinterpret_cast<float2 *>(a.out_lo + o1) = make_float2(il, rl);
+                        *reinterpret_cast<float2 *>(out_hi + o0) = make_float2(rh, -ih);
+                        *reinterpret_cast<float2 *>(out_hi + o1) = make_float2(ih, rh);
+                        *reinterpret_cast<float2 *>(out_lo + o0) = make_float2(rl, -il);
+                        *reinterpret_cast<float2 *>(out_lo + o1) = make_float2(il, rl);
                     } else {
-                        reinterpret_cast<float2 *>(a.out_hi)[(size_t)row * a.ldo + jc] = make_float2(re, im);
+                        reinterpret_cast<float2 *>(out_hi)[(size_t)row * a.ldo + jc] = make_float2(re, im);
                     }
                 }
             }
@@ -301,31 +307,40 @@ extern "C" int mlb_twiddle_tf32(const double *coord, int n_coord, const double *
     return mlb::check_launch("mlb_twiddle_tf32");
 }
 
-extern "C" int mlb_cgemm_tc(const float *Ah, const float *Al, int lda, const float *Bh, const float *Bl, int ldb,
-                            int rows, int cols_c, int depth_c, int mode, float *out_hi, float *out_lo, int ldo,
-                            void *stream) {
-    MLB_REQUIRE(Ah && Al && Bh && Bl && out_hi, "mlb_cgemm_tc: NULL pointer");
+extern "C" int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,
+                            const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
+                            float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream) {
+    MLB_REQUIRE(h_Ah && h_Al && h_Bh && h_Bl && h_out_hi, "mlb_cgemm_tc: NULL pointer");
+    MLB_REQUIRE(batch >= 1 && batch <= 4, "mlb_cgemm_tc: batch %d not in 1..4", batch);
     MLB_REQUIRE(mode == 1 || mode == 2, "mlb_cgemm_tc: mode must be 1 (embedded hi/lo output) or 2 (complex64 output)");
-    MLB_REQUIRE(mode == 2 || out_lo, "mlb_cgemm_tc: mode 1 needs out_lo");
+    MLB_REQUIRE(mode == 2 || h_out_lo, "mlb_cgemm_tc: mode 1 needs out_lo");
     MLB_REQUIRE(rows > 0 && cols_c > 0 && depth_c > 0, "mlb_cgemm_tc: empty problem");
     const int K = 2 * depth_c;                       // real depth
     MLB_REQUIRE(lda >= K && ldb >= K && lda % 4 == 0 && ldb % 4 == 0, "mlb_cgemm_tc: operand pitch must be >= 2*depth and a multiple of 4 floats");
-    MLB_REQUIRE(mlb::aligned16(Ah) && mlb::aligned16(Al) && mlb::aligned16(Bh) && mlb::aligned16(Bl), "mlb_cgemm_tc: operands not 16-byte aligned");
     MLB_REQUIRE(mode == 2 ? ldo >= cols_c : (ldo >= 2 * rows && ldo % 2 == 0), "mlb_cgemm_tc: output pitch too small");
-    CUtensorMap mAh, mAl, mBh, mBl;
-    if (int rc = mlb::make_map(&mAh, Ah, rows, K, lda, mlb::TC_BM)) return rc;
-    if (int rc = mlb::make_map(&mAl, Al, rows, K, lda, mlb::TC_BM)) return rc;
-    if (int rc = mlb::make_map(&mBh, Bh, 2 * cols_c, K, ldb, mlb::TC_BN)) return rc;
-    if (int rc = mlb::make_map(&mBl, Bl, 2 * cols_c, K, ldb, mlb::TC_BN)) return rc;
+    mlb::TcMaps maps;
+    mlb::TcArgs a;
+    for (int b = 0; b < 4; ++b) {
+        const int s = b < batch ? b : 0;
+        MLB_REQUIRE(h_Ah[s] && h_Al[s] && h_Bh[s] && h_Bl[s] && h_out_hi[s] && (mode == 2 || h_out_lo[s]),
+                    "mlb_cgemm_tc: NULL operand in batch slot %d", s);
+        MLB_REQUIRE(mlb::aligned16(h_Ah[s]) && mlb::aligned16(h_Al[s]) && mlb::aligned16(h_Bh[s]) && mlb::aligned16(h_Bl[s]),
+                    "mlb_cgemm_tc: operands not 16-byte aligned");
+        if (int rc = mlb::make_map(&maps.m[b][0], h_Ah[s], rows, K, lda, mlb::TC_BM)) return rc;
+        if (int rc = mlb::make_map(&maps.m[b][1], h_Al[s], rows, K, lda, mlb::TC_BM)) return rc;
+        if (int rc = mlb::make_map(&maps.m[b][2], h_Bh[s], 2 * cols_c, K, ldb, mlb::TC_BN)) return rc;
+        if (int rc = mlb::make_map(&maps.m[b][3], h_Bl[s], 2 * cols_c, K, ldb, mlb::TC_BN)) return rc;
+        a.out_hi[b] = h_out_hi[s];
+        a.out_lo[b] = (mode == 1) ? h_out_lo[s] : nullptr;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         MLB_CUDA(cudaFuncSetAttribute(mlb::cgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlb::TC_SMEM));
         attr_set = true;
     }
-    mlb::TcArgs a;
-    a.out_hi = out_hi; a.out_lo = out_lo; a.ldo = ldo; a.rows = rows; a.cols_c = cols_c;
+    a.ldo = ldo; a.rows = rows; a.cols_c = cols_c;
     a.k_blocks = (K + mlb::TC_BK - 1) / mlb::TC_BK; a.mode = mode;
-    dim3 grid((2 * cols_c + mlb::TC_BN - 1) / mlb::TC_BN, (rows + mlb::TC_BM - 1) / mlb::TC_BM);
-    mlb::cgemm_tc_kernel<<<grid, mlb::TC_THREADS, mlb::TC_SMEM, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, a);
+    dim3 grid((2 * cols_c + mlb::TC_BN - 1) / mlb::TC_BN, (rows + mlb::TC_BM - 1) / mlb::TC_BM, batch);
+    mlb::cgemm_tc_kernel<<<grid, mlb::TC_THREADS, mlb::TC_SMEM, (cudaStream_t)stream>>>(maps, a);
     return mlb::check_launch("mlb_cgemm_tc");
 }

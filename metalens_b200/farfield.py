@@ -248,19 +248,24 @@ class FarfieldPlan:
                 _lib.check(lib.mlb_tf32_split(ops[f].data_ptr(), 2 * ld, self.Jh[f].data_ptr(), self.Jl[f].data_ptr(),
                                               ldj, Mx, 2 * My, _stream_ptr()), "mlb_tf32_split")
 
-        def stage1():
-            for f in range(4):
-                _lib.check(lib.mlb_cgemm_tc(self.Jh[f].data_ptr(), self.Jl[f].data_ptr(), ldj,
-                                            self.AyB[0].data_ptr(), self.AyB[1].data_ptr(), self.AyB[0].shape[1],
-                                            Mx, Ky, My, 1, self.TBh[f].data_ptr(), self.TBl[f].data_ptr(),
-                                            self.TBh[f].shape[1], _stream_ptr()), "mlb_cgemm_tc(stage 1)")
+        pJh, k1 = _lib.ptr_array(self.Jh)
+        pJl, k2 = _lib.ptr_array(self.Jl)
+        pTh, k3 = _lib.ptr_array(self.TBh)
+        pTl, k4 = _lib.ptr_array(self.TBl)
+        pAyh, k5 = _lib.ptr_array([self.AyB[0]] * 4)
+        pAyl, k6 = _lib.ptr_array([self.AyB[1]] * 4)
+        pAxh, k7 = _lib.ptr_array([self.AxA[0]] * 4)
+        pAxl, k8 = _lib.ptr_array([self.AxA[1]] * 4)
+        pF, k9 = _lib.ptr_array(self.Fhat)
 
-        def stage2():
-            for f in range(4):
-                _lib.check(lib.mlb_cgemm_tc(self.AxA[0].data_ptr(), self.AxA[1].data_ptr(), self.AxA[0].shape[1],
-                                            self.TBh[f].data_ptr(), self.TBl[f].data_ptr(), self.TBh[f].shape[1],
-                                            Kx, Ky, Mx, 2, self.Fhat[f].data_ptr(), None, self.Fhat[f].shape[1],
-                                            _stream_ptr()), "mlb_cgemm_tc(stage 2)")
+        def stage1(keep=(k1, k2, k3, k4, k5, k6)):       # all four fields in one launch
+            _lib.check(lib.mlb_cgemm_tc(pJh, pJl, ldj, pAyh, pAyl, self.AyB[0].shape[1], Mx, Ky, My, 1,
+                                        pTh, pTl, self.TBh[0].shape[1], 4, _stream_ptr()), "mlb_cgemm_tc(stage 1)")
+
+        def stage2(keep=(k7, k8, k9)):
+            _lib.check(lib.mlb_cgemm_tc(pAxh, pAxl, self.AxA[0].shape[1], pTh, pTl, self.TBh[0].shape[1],
+                                        Kx, Ky, Mx, 2, pF, None, self.Fhat[0].shape[1], 4, _stream_ptr()),
+                       "mlb_cgemm_tc(stage 2)")
         return [("tf32_split", split, 4 * 24 * Mx * My, 0.0),
                 ("tc_stage1", stage1, 4 * (16 * Mx * My + 32 * Ky * Mx) + 16 * Ky * My, 32.0 * Mx * My * Ky),
                 ("tc_stage2", stage2, 4 * (32 * Ky * Mx + 8 * Kx * Ky) + 16 * Kx * Mx, 32.0 * Kx * Mx * Ky)]
