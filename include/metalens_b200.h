@@ -106,7 +106,9 @@ int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, co
                  float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream);
 
 /* ---- A1 (FFT formulation): shared-memory FFT passes, power-of-two lengths ---- */
-/* out[t] = exp(-2 pi i t / N), float64 phases rounded once to fp32 */
+/* Twiddle tables for the FFT passes, 2*N entries: out[t] = exp(-2 pi i t / N) for t < N, followed by the
+ * same values re-ordered per Stockham stage (conflict-free shared-memory reads); float64 phases rounded
+ * once to fp32 */
 int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);
 /* Tuning knobs of the row pass (defaults are the B200-tuned values): loader variant (1 = consecutive
  * samples per thread, all stages in shared memory; 0 = first radix-4 stage done by the loader),

@@ -117,18 +117,27 @@ __device__ __forceinline__ void load_folded(const FftArgs &a, const float2 *__re
     }
 }
 
+// Threads per CTA of the compile-time-sized kernels: transforms of >= 4096 points leave room for only
+// one CTA per SM (shared memory), so those CTAs are 1024 threads wide to keep enough loads in flight.
+template <int LGN> struct FftThreads { static constexpr int value = (LGN >= 12) ? 1024 : 256; };
+
 // ---- compile-time-sized stages: all index math folds into constants, loops fully unrolled ----------
 template <int R, int LGN, int LGNS, int LANES, int PITCH>
 __device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *__restrict__ y,
                                          const float2 *__restrict__ tw) {
     constexpr int lgR = (R == 4) ? 2 : 1;
     constexpr int lgPer = LGN - lgR, per = 1 << lgPer, total = per * LANES, Ns = 1 << LGNS;
-    constexpr int lgTstep = LGN - LGNS - lgR;
-    constexpr int iters = (total + 255) / 256;
+    // staged twiddle table (built by mlb_fft_twiddle after the plain one): for the radix-4 stage with
+    // sub-length Ns = 4^s the entries W^(r k), r = 1..3, k < Ns sit at [4^s - 1 + 3k + (r-1)]; for a final
+    // radix-2 stage at [Ns - 1 + k].  Consecutive threads read consecutive 24-byte triples instead of
+    // one strided word of the length-N table: no shared-memory bank conflicts on the twiddle loads.
+    constexpr int tbase = Ns - 1;
+    constexpr int T = FftThreads<LGN>::value;
+    constexpr int iters = (total + T - 1) / T;
 #pragma unroll
     for (int it = 0; it < iters; ++it) {
-        const int idx = it * 256 + threadIdx.x;
-        if (total % 256 != 0 && idx >= total) break;
+        const int idx = it * T + threadIdx.x;
+        if (total % T != 0 && idx >= total) break;
         const int lane = idx >> lgPer, j = idx & (per - 1);
         const int k = j & (Ns - 1);
         const int base_out = ((j - k) << lgR) + k;
@@ -138,7 +147,7 @@ __device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *_
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             v[r] = xl[j + r * per];
-            if (r > 0 && LGNS > 0) v[r] = cmulf(v[r], tw[(r * k) << lgTstep]);
+            if (r > 0 && LGNS > 0) v[r] = cmulf(v[r], tw[tbase + (R - 1) * k + (r - 1)]);
         }
         if (R == 4) {
             bfly4(v[0], v[1], v[2], v[3]);
@@ -146,8 +155,13 @@ __device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *_
             const float2 a0 = caddf(v[0], v[1]), a1 = csubf(v[0], v[1]);
             v[0] = a0; v[1] = a1;
         }
+        if (LGNS == 0 && R == 4 && (PITCH % 2 == 0)) {        // first stage: 4 consecutive outputs, two 16-byte stores
+            *reinterpret_cast<float4 *>(yl + base_out) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+            *reinterpret_cast<float4 *>(yl + base_out + 2) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) yl[base_out + (r << LGNS)] = v[r];
+            for (int r = 0; r < R; ++r) yl[base_out + (r << LGNS)] = v[r];
+        }
     }
 }
 
@@ -169,14 +183,14 @@ __device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *
 // s1 x s2 aliased copies (aperture fold), applies the input fftshift and performs the first radix-4
 // stage in registers, so its shared-memory writes are contiguous 64-byte runs.
 template <int VEC, int LGN>
-__global__ void __launch_bounds__(256, (LGN >= 8 && LGN <= 11) ? 8 : 1) fft_rows_kernel(const FftArgs a) {
+__global__ void __launch_bounds__(FftThreads<LGN>::value, (LGN >= 8 && LGN <= 11) ? 8 : 1) fft_rows_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int N = 1 << a.lgN, L = a.lanes;
     float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N, *stw = buf1 + (size_t)L * N;
     const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
     const int row0 = blockIdx.x * L;
-    for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[t];     // twiddle table -> shared memory
+    for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[(LGN > 0 ? N : 0) + t];   // (staged) twiddle table -> smem
     int lgNs0;
     if (a.plain_loader) {
         // plain loader: consecutive samples per thread, every FFT stage in shared memory
@@ -262,14 +276,14 @@ __global__ void __launch_bounds__(256, (LGN >= 8 && LGN <= 11) ? 8 : 1) fft_rows
 // columns: `lanes` adjacent columns per CTA, transform along the strided axis.  Columns are
 // transposed into [lane][n] shared-memory rows (pitch N+4) while the loader does the first stage.
 template <int LGN, int CL>
-__global__ void __launch_bounds__(256) fft_cols_kernel(const FftArgs a) {
+__global__ void __launch_bounds__(FftThreads<LGN>::value) fft_cols_kernel(const FftArgs a) {
     extern __shared__ __align__(16) float2 fsm[];
     const int N = 1 << a.lgN, L = a.lanes, P = N + 4;
     float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * P, *stw = buf1 + (size_t)L * P;
     const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
     const int c0 = blockIdx.x * L;
-    for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[t];
+    for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[(LGN > 0 ? N : 0) + t];
     int lgNs0;
     if (a.lgN >= 2) {
         lgNs0 = 2;
@@ -321,7 +335,27 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
     if (t >= N) return;
     double s, c;
     sincospi(-2.0 * (double)t / (double)N, &s, &c);
-    out[t] = make_float2((float)c, (float)s);
+    out[t] = make_float2((float)c, (float)s);                 // plain table W_N^t
+    // staged table entry t (see stage_ct): find the stage whose block contains t
+    float2 w = make_float2(1.f, 0.f);
+    int Ns = 1, lg = 0, lgN = 0;
+    while ((1 << lgN) < N) ++lgN;
+    bool done = false;
+    while (lg + 2 <= lgN && !done) {                          // radix-4 stages: block [Ns-1, 4Ns-1)
+        if (t >= Ns - 1 && t < 4 * Ns - 1) {
+            const int e = t - (Ns - 1), k = e / 3, r = e - 3 * k + 1;
+            sincospi(-2.0 * (double)(r * k) / (double)(4 * Ns), &s, &c);
+            w = make_float2((float)c, (float)s);
+            done = true;
+        }
+        Ns *= 4; lg += 2;
+    }
+    if (!done && lg < lgN && t >= Ns - 1 && t < 2 * Ns - 1) { // final radix-2 stage: block [Ns-1, 2Ns-1)
+        const int k = t - (Ns - 1);
+        sincospi(-2.0 * (double)k / (double)(2 * Ns), &s, &c);
+        w = make_float2((float)c, (float)s);
+    }
+    out[N + t] = w;
 }
 
 // tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
@@ -403,7 +437,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
                                           smem_max));                                                               \
             set_ = true;                                                                                            \
         }                                                                                                           \
-        mlb::fft_rows_kernel<V, LG><<<grid, mlb::g_rows_threads, smem, st>>>(a);                                    \
+        mlb::fft_rows_kernel<V, LG><<<grid, (LG >= 12) ? 1024 : mlb::g_rows_threads, smem, st>>>(a);                                    \
     } while (0)
 #define MLB_ROWS_CASE(LG)                                  \
     case LG:                                               \
@@ -450,7 +484,7 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
             set_ = true;                                                                                             \
         }                                                                                                            \
         dim3 grid((n_cols + lanes - 1) / lanes, batch);                                                              \
-        mlb::fft_cols_kernel<LG, CL><<<grid, 256, smem, st>>>(a);                                                    \
+        mlb::fft_cols_kernel<LG, CL><<<grid, (LG >= 12) ? 1024 : 256, smem, st>>>(a);                                                    \
     } while (0)
     // compile-time-sized kernels when the lane count is the canonical one for that length
     if (a.lgN == 8 && lanes == 16) MLB_COLS_LAUNCH(8, 16);

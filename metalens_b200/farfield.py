@@ -174,8 +174,8 @@ class FarfieldPlan:
             self.Rx, self.Ry = K1, K2
             self.G = None          # the row pass folds while loading: the folded aperture never exists in memory
             self.W = [_c64_buffer(K1, K2, dev) for _ in range(4)]          # row-pass output
-            self.tw1 = torch.empty(K1, dtype=torch.complex64, device=dev)
-            self.tw2 = torch.empty(K2, dtype=torch.complex64, device=dev)
+            self.tw1 = torch.empty(2 * K1, dtype=torch.complex64, device=dev)     # plain + staged tables
+            self.tw2 = torch.empty(2 * K2, dtype=torch.complex64, device=dev)
             for t, n in ((self.tw1, K1), (self.tw2, K2)):
                 _lib.check(self.lib.mlb_fft_twiddle(n, t.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
             self.AxT = self.Ay = None

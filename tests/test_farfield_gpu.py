@@ -209,7 +209,7 @@ def test_fft_passes_match_numpy():
     assert lib.mlb_fft_max_length() == 8192
     for N, other in ((2, 5), (4, 3), (8, 9), (16, 4), (64, 33), (128, 7), (512, 6), (1024, 5), (2048, 3), (8192, 2)):
         a = [(rng.standard_normal((other, N)) + 1j * rng.standard_normal((other, N))).astype(np.complex64) for _ in range(2)]
-        tw = torch.empty(N, dtype=torch.complex64).cuda()
+        tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
         _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
         ld = N + 2
         din = [torch.zeros(other, ld, dtype=torch.complex64).cuda() for _ in a]
@@ -243,7 +243,7 @@ def test_fft_passes_match_numpy():
     big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
     dbig = [torch.from_numpy(big).cuda()]
     dres = [torch.zeros(n_rows, N, dtype=torch.complex64).cuda()]
-    tw = torch.empty(N, dtype=torch.complex64).cuda()
+    tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
     _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
     pi_, k1 = _lib.ptr_array(dbig)
     po, k2 = _lib.ptr_array(dres)
