@@ -110,8 +110,9 @@ int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, co
  * same values re-ordered per Stockham stage (conflict-free shared-memory reads); float64 phases rounded
  * once to fp32 */
 int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);
-/* Tuning knobs of the row pass (defaults are the B200-tuned values): loader variant (1 = consecutive
- * samples per thread, all stages in shared memory; 0 = first radix-4 stage done by the loader),
+/* Tuning knobs of the row pass (defaults are the B200-tuned values): loader variant (2 = TMA-fed
+ * persistent producer/consumer kernel, the default for 256..2048 points; 1 = thread-issued loads, consecutive
+ * samples per thread; 0 = first radix-4 stage done by the loader),
  * points per CTA, threads per CTA (64/128/256), vector width of the loads (1 or 2 complex). */
 int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_threads, int rows_vec);
 /* longest transform the shared-memory passes support (8192 complex64) */

@@ -165,17 +165,130 @@ __device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *_
     }
 }
 
-template <int LGN, int LGNS, int LANES, int PITCH, int CUR>
+// barrier among the FFT threads: the whole CTA, or (NAMED) only the 256 consumer threads of the
+// TMA-fed kernel, whose producer warp must not take part
+template <bool NAMED>
+__device__ __forceinline__ void fft_sync() {
+    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+
+template <int LGN, int LGNS, int LANES, int PITCH, int CUR, bool NAMED = false>
 __device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *tw) {
-    __syncthreads();
+    fft_sync<NAMED>();
     if constexpr (LGNS + 2 <= LGN) {
         stage_ct<4, LGN, LGNS, LANES, PITCH>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
-        return fft_ct<LGN, LGNS + 2, LANES, PITCH, CUR ^ 1>(buf0, buf1, tw);
+        return fft_ct<LGN, LGNS + 2, LANES, PITCH, CUR ^ 1, NAMED>(buf0, buf1, tw);
     } else if constexpr (LGNS < LGN) {
         stage_ct<2, LGN, LGNS, LANES, PITCH>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
-        return fft_ct<LGN, LGNS + 1, LANES, PITCH, CUR ^ 1>(buf0, buf1, tw);
+        return fft_ct<LGN, LGNS + 1, LANES, PITCH, CUR ^ 1, NAMED>(buf0, buf1, tw);
     } else {
         return CUR;
+    }
+}
+
+// ---- TMA-fed persistent row pass ------------------------------------------------------------------------
+// The HBM-bound part of NF->FF as a producer/consumer pipeline: one producer warp streams the s1*s2 aliased
+// row segments of each folded row into a ring of shared-memory slots with 1-D bulk copies (cp.async.bulk,
+// mbarrier transaction counts); 256 consumer threads add the segments into registers as they land, then run
+// the row FFT and store the row.  The producer keeps prefetching the next rows while the consumers are in
+// their butterfly stages, so loads stay in flight all the time (the thread-issued loader loses ~20 % of the
+// HBM bandwidth to that phase alternation).  CTAs are persistent and stride over (field, row) work items.
+constexpr int TMA_CONSUMERS = 256;
+
+template <int LGN>
+struct RowsTmaCfg {
+    static constexpr int N = 1 << LGN;
+    static constexpr int SLOT_BYTES = N * 8;
+    static constexpr int SLOTS = (64 * 1024 / SLOT_BYTES) > 16 ? 16 : ((64 * 1024 / SLOT_BYTES) < 4 ? 4 : (64 * 1024 / SLOT_BYTES));
+    static constexpr int EPT = N / TMA_CONSUMERS;                       // complex elements per consumer thread
+    static constexpr size_t SMEM = (size_t)SLOTS * SLOT_BYTES + 3 * (size_t)N * 8 + 2 * SLOTS * sizeof(uint64_t) + 16;
+};
+
+template <int LGN>
+__global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(const FftArgs a, int batch) {
+    using Cfg = RowsTmaCfg<LGN>;
+    constexpr int N = Cfg::N, S = Cfg::SLOTS, EPT = Cfg::EPT;
+    extern __shared__ __align__(128) unsigned char tsm[];
+    float2 *ring = reinterpret_cast<float2 *>(tsm);
+    float2 *buf0 = ring + (size_t)S * N, *buf1 = buf0 + N, *stw = buf1 + N;
+    uint64_t *full = reinterpret_cast<uint64_t *>(stw + N), *empty = full + S;
+    const int tid = threadIdx.x;
+    const int nseg = a.s1 * a.s2;
+    const int work = a.other * batch;
+
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TMA_CONSUMERS / 32); }
+        mbar_fence_init();
+    }
+    for (int t = tid; t < N; t += blockDim.x) stw[t] = a.tw[N + t];          // staged twiddle table
+    __syncthreads();
+
+    if (tid >= TMA_CONSUMERS) {
+        // ------------------------------------------------ producer warp (one lane issues)
+        if (tid == TMA_CONSUMERS) {
+            long long g = 0;
+            for (int w = blockIdx.x; w < work; w += gridDim.x) {
+                const int f = w / a.other, r = w - f * a.other;
+                int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
+                const float2 *src = pick4(a.in, f);
+                for (int t = 0; t < nseg; ++t, ++g) {
+                    const int slot = (int)(g % S);
+                    const long long use = g / S;
+                    if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
+                    const int t1 = t / a.s2, t2 = t - t1 * a.s2;
+                    mbar_expect_tx(&full[slot], Cfg::SLOT_BYTES);
+                    bulk_g2s(ring + (size_t)slot * N, src + (size_t)(rs + t1 * a.other) * a.ld_in + ((size_t)t2 << LGN),
+                             Cfg::SLOT_BYTES, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------- consumers
+    long long g = 0;
+    for (int w = blockIdx.x; w < work; w += gridDim.x) {
+        const int f = w / a.other, r = w - f * a.other;
+        float acc[2 * EPT];
+#pragma unroll
+        for (int v = 0; v < 2 * EPT; ++v) acc[v] = 0.f;
+        for (int t = 0; t < nseg; ++t, ++g) {
+            const int slot = (int)(g % S);
+            mbar_wait(&full[slot], (uint32_t)((g / S) & 1));
+            const float2 *sl = ring + (size_t)slot * N;
+            if (EPT >= 2) {
+#pragma unroll
+                for (int v = 0; v < EPT / 2; ++v) {
+                    const float4 x = *reinterpret_cast<const float4 *>(sl + (v * TMA_CONSUMERS + tid) * 2);
+                    acc[4 * v] += x.x; acc[4 * v + 1] += x.y; acc[4 * v + 2] += x.z; acc[4 * v + 3] += x.w;
+                }
+            } else {
+                const float2 x = sl[tid];
+                acc[0] += x.x; acc[1] += x.y;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
+        }
+        // rotate by the input fftshift while handing the folded row to the FFT buffer
+        if (EPT >= 2) {
+#pragma unroll
+            for (int v = 0; v < EPT / 2; ++v) {
+                const int c = (v * TMA_CONSUMERS + tid) * 2;
+                buf0[(c + a.in_roll_c) & (N - 1)] = make_float2(acc[4 * v], acc[4 * v + 1]);
+                buf0[(c + 1 + a.in_roll_c) & (N - 1)] = make_float2(acc[4 * v + 2], acc[4 * v + 3]);
+            }
+        } else {
+            buf0[(tid + a.in_roll_c) & (N - 1)] = make_float2(acc[0], acc[1]);
+        }
+        const int cur = fft_ct<LGN, 0, 1, N, 0, true>(buf0, buf1, stw);
+        const float2 *res = cur ? buf1 : buf0;
+        float2 *dst = pick4(a.out, f) + (size_t)r * a.ld_out;
+#pragma unroll
+        for (int v = 0; v < EPT; ++v) {
+            const int n = v * TMA_CONSUMERS + tid;                            // position in the OUTPUT row
+            dst[n] = res[(n - a.out_roll) & (N - 1)];
+        }
+        fft_sync<true>();                                                     // buffers free for the next row
     }
 }
 
@@ -359,7 +472,7 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
 }
 
 // tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
-static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2;
+static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1;
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
@@ -385,6 +498,9 @@ extern "C" int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream) {
 }
 
 extern "C" int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_threads, int rows_vec) {
+    // rows_plain_loader: 2 = TMA-fed persistent kernel (default), 1 = thread-issued loads, 0 = first stage in loader
+    mlb::g_rows_tma = (rows_plain_loader == 2);
+    if (rows_plain_loader == 2) rows_plain_loader = 1;
     MLB_REQUIRE((rows_threads == 64 || rows_threads == 128 || rows_threads == 256) && rows_points_per_cta >= 1 &&
                     (rows_vec == 1 || rows_vec == 2),
                 "mlb_fft_tune: bad arguments");
@@ -422,6 +538,39 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     bool vec = (mlb::g_rows_vec == 2) && (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
+    // TMA-fed persistent kernel (256..2048 points): needs 16-byte aligned row segments
+    {
+        bool tma_ok = mlb::g_rows_tma && a.lgN >= 8 && a.lgN <= 11 && (ld_in % 2 == 0);
+        for (int b = 0; b < batch; ++b) tma_ok = tma_ok && mlb::aligned16(a.in[b]) && a.in[b] != a.out[b];
+        if (tma_ok) {
+            static int n_sm = 0;
+            if (!n_sm) {
+                int dev = 0;
+                MLB_CUDA(cudaGetDevice(&dev));
+                MLB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            }
+            cudaStream_t st = (cudaStream_t)stream;
+#define MLB_ROWS_TMA(LG)                                                                                              \
+    case LG: {                                                                                                       \
+        using Cfg = mlb::RowsTmaCfg<LG>;                                                                             \
+        static bool set_ = false;                                                                                    \
+        if (!set_) {                                                                                                 \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_tma_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)Cfg::SMEM));                                                          \
+            set_ = true;                                                                                             \
+        }                                                                                                            \
+        int per_sm = (int)((220 * 1024) / (Cfg::SMEM + 1024));                                                       \
+        if (per_sm > 3) per_sm = 3;                                                                                  \
+        if (per_sm < 1) per_sm = 1;                                                                                  \
+        int grid = n_sm * per_sm;                                                                                    \
+        if (grid > n_rows * batch) grid = n_rows * batch;                                                            \
+        mlb::fft_rows_tma_kernel<LG><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch);                    \
+        return mlb::check_launch("mlb_fft_rows(tma)");                                                               \
+    }
+            switch (a.lgN) { MLB_ROWS_TMA(8) MLB_ROWS_TMA(9) MLB_ROWS_TMA(10) MLB_ROWS_TMA(11) }
+#undef MLB_ROWS_TMA
+        }
+    }
     // Compile-time-sized kernels for 256..8192 points (always 256 threads and max(1, 1024/N) rows per CTA);
     // the runtime-sized kernel covers the small transforms and the tuning knobs.
     const int lgN = a.lgN;

@@ -22,7 +22,7 @@ def t_kernel(k):
     for i in range(30): steps[i % 3][k][1]()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 30 * 1e3
-for plain, pts, thr, vec in ((1, 1024, 256, 2), (0, 1024, 256, 2), (1, 2048, 256, 2), (1, 1024, 256, 1)):
+for plain, pts, thr, vec in ((2, 1024, 256, 2), (1, 1024, 256, 2), (2, 1024, 256, 2)):
     _lib.check(lib.mlb_fft_tune(plain, pts, thr, vec), "tune")
     try:
         us = t_kernel(0)
