@@ -125,10 +125,14 @@ int mlb_fft_max_length(void);
  *   out_b[r][(q + out_roll) % N] = sum_p G_b[r][p] e^{-2 pi i q p / N}
  * For a strided far-field grid this is the only kernel that touches the full aperture: it reads
  * 8*n_rows*s1*N*s2 bytes per field exactly once (HBM-bound).
+ * transpose_out != 0 stores out_b[(q + out_roll) % N][r] instead (pitch ld_out >= n_rows): two such passes
+ * make a 2-D transform with contiguous (TMA-streamed) reads in both; only where
+ * mlb_fft_rows_can_transpose(N) returns 1 (TMA-fed kernel: 256..2048 points).
  */
+int mlb_fft_rows_can_transpose(int N);
 int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
-                 int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int batch,
-                 void *stream);
+                 int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
+                 int batch, void *stream);
 /* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}; in-place allowed */
 int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N, int n_cols,
                  const mlb_c64 *tw, int out_roll, int batch, void *stream);

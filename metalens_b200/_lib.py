@@ -37,8 +37,9 @@ SIGNATURES = {
     "mlb_fft_twiddle": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_fft_max_length": (C.c_int, []),
     "mlb_fft_tune": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mlb_fft_rows_can_transpose": (C.c_int, [C.c_int]),
     "mlb_fft_rows": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mlb_fft_cols": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p]),
     "mlb_ff_epilogue_blocks": (C.c_int, [C.c_int, C.c_int]),

@@ -90,7 +90,7 @@ struct FftArgs {
     const float2 *in[4];
     float2 *out[4];
     const float2 *tw;
-    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader;
+    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader, transpose_out;
 };
 
 // folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
@@ -282,11 +282,22 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
         }
         const int cur = fft_ct<LGN, 0, 1, N, 0, true>(buf0, buf1, stw);
         const float2 *res = cur ? buf1 : buf0;
-        float2 *dst = pick4(a.out, f) + (size_t)r * a.ld_out;
+        if (a.transpose_out) {
+            // out[n][r]: the next pass transforms along r, so it finds ITS rows contiguous.  8-byte stores one
+            // row pitch apart; the 33 MB intermediate lives in L2, which merges them into full sectors.
+            float2 *dst = pick4(a.out, f) + r;
 #pragma unroll
-        for (int v = 0; v < EPT; ++v) {
-            const int n = v * TMA_CONSUMERS + tid;                            // position in the OUTPUT row
-            dst[n] = res[(n - a.out_roll) & (N - 1)];
+            for (int v = 0; v < EPT; ++v) {
+                const int n = v * TMA_CONSUMERS + tid;
+                dst[(size_t)n * a.ld_out] = res[(n - a.out_roll) & (N - 1)];
+            }
+        } else {
+            float2 *dst = pick4(a.out, f) + (size_t)r * a.ld_out;
+#pragma unroll
+            for (int v = 0; v < EPT; ++v) {
+                const int n = v * TMA_CONSUMERS + tid;                        // position in the OUTPUT row
+                dst[n] = res[(n - a.out_roll) & (N - 1)];
+            }
         }
         fft_sync<true>();                                                     // buffers free for the next row
     }
@@ -513,15 +524,20 @@ extern "C" int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int 
 
 extern "C" int mlb_fft_max_length(void) { return mlb::FFT_MAX_N; }
 
+extern "C" int mlb_fft_rows_can_transpose(int N) {
+    return (mlb::g_rows_tma && mlb::is_pow2(N) && N >= 256 && N <= 2048) ? 1 : 0;
+}
+
 extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
                             int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
-                            int batch, void *stream) {
+                            int transpose_out, int batch, void *stream) {
     mlb::FftArgs a;
     if (int rc = mlb::fill_args(a, h_in, h_out, batch, "mlb_fft_rows")) return rc;
     MLB_REQUIRE(mlb::is_pow2(N) && N >= 2 && N <= mlb::FFT_MAX_N, "mlb_fft_rows: length %d must be a power of two <= %d",
                 N, mlb::FFT_MAX_N);
     MLB_REQUIRE(s1 >= 1 && s2 >= 1, "mlb_fft_rows: fold factors must be >= 1");
-    MLB_REQUIRE(tw && n_rows > 0 && ld_in >= N * s2 && ld_out >= N, "mlb_fft_rows: bad sizes");
+    MLB_REQUIRE(tw && n_rows > 0 && ld_in >= N * s2 && ld_out >= (transpose_out ? n_rows : N), "mlb_fft_rows: bad sizes");
+    a.transpose_out = transpose_out ? 1 : 0;
     MLB_REQUIRE(in_roll_r >= 0 && in_roll_r < n_rows && in_roll_c >= 0 && in_roll_c < N && out_roll >= 0 && out_roll < N,
                 "mlb_fft_rows: rolls out of range");
     for (int b = 0; b < batch; ++b)
@@ -571,6 +587,8 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
 #undef MLB_ROWS_TMA
         }
     }
+    MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs the TMA-fed kernel (256..2048 points, "
+                                "16-byte aligned even-pitch input, out != in); see mlb_fft_rows_can_transpose");
     // Compile-time-sized kernels for 256..8192 points (always 256 threads and max(1, 1024/N) rows per CTA);
     // the runtime-sized kernel covers the small transforms and the tuning knobs.
     const int lgN = a.lgN;

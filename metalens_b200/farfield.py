@@ -173,7 +173,10 @@ class FarfieldPlan:
             assert K1 == Kx and K2 == Ky
             self.Rx, self.Ry = K1, K2
             self.G = None          # the row pass folds while loading: the folded aperture never exists in memory
-            self.W = [_c64_buffer(K1, K2, dev) for _ in range(4)]          # row-pass output
+            # two transposing row passes (both read contiguous rows through TMA) where the sizes allow it,
+            # otherwise a row pass followed by a strided column pass
+            self.two_pass_t = bool(self.lib.mlb_fft_rows_can_transpose(K1) and self.lib.mlb_fft_rows_can_transpose(K2))
+            self.W = [_c64_buffer(K2, K1, dev) if self.two_pass_t else _c64_buffer(K1, K2, dev) for _ in range(4)]
             self.tw1 = torch.empty(2 * K1, dtype=torch.complex64, device=dev)     # plain + staged tables
             self.tw2 = torch.empty(2 * K2, dtype=torch.complex64, device=dev)
             for t, n in ((self.tw1, K1), (self.tw2, K2)):
@@ -323,16 +326,22 @@ class FarfieldPlan:
             pf, k5 = _lib.ptr_array(self.Fhat)
             ldw, ldf = self.W[0].shape[1], self.Fhat[0].shape[1]
 
-            def rows(pi_=pi_, ld=ld, keep=(k3, k4)):
-                _lib.check(lib.mlb_fft_rows(pi_, ld, pw, ldw, Rx, Ry, self.sx, self.sy, self.tw2.data_ptr(),
-                                            roll_r, roll_c, (h2 // self.sy) % Ry, 4, _stream_ptr()), "mlb_fft_rows")
+            tr = 1 if self.two_pass_t else 0
 
-            def cols(keep=k5):
-                _lib.check(lib.mlb_fft_cols(pw, ldw, pf, ldf, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx, 4,
-                                            _stream_ptr()), "mlb_fft_cols")
+            def rows(pi_=pi_, ld=ld, keep=(k3, k4)):      # along y; stored transposed (W[qy][p1]) in two-pass mode
+                _lib.check(lib.mlb_fft_rows(pi_, ld, pw, ldw, Rx, Ry, self.sx, self.sy, self.tw2.data_ptr(),
+                                            roll_r, roll_c, (h2 // self.sy) % Ry, tr, 4, _stream_ptr()), "mlb_fft_rows")
+
+            def cols(keep=k5):                            # along x
+                if tr:                                    # rows of W = fixed qy, contiguous p1 -> Fhat[qx][qy]
+                    _lib.check(lib.mlb_fft_rows(pw, ldw, pf, ldf, Ry, Rx, 1, 1, self.tw1.data_ptr(), 0, 0,
+                                                (h1 // self.sx) % Rx, 1, 4, _stream_ptr()), "mlb_fft_rows(pass 2)")
+                else:
+                    _lib.check(lib.mlb_fft_cols(pw, ldw, pf, ldf, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx, 4,
+                                                _stream_ptr()), "mlb_fft_cols")
             out.append(("fold_fft_rows" if (self.sx > 1 or self.sy > 1) else "fft_rows", rows,
                         32 * (self.Mx * self.My + Rx * Ry), 4 * 5.0 * Rx * Ry * math.log2(Ry)))
-            out.append(("fft_cols", cols, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
+            out.append(("fft_rows_pass2" if tr else "fft_cols", cols, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
         else:
             pa, k6 = _lib.ptr_array(ops)
             pu, k7 = _lib.ptr_array(self.UT)

@@ -219,7 +219,7 @@ def test_fft_passes_match_numpy():
         rr, rc, ro = other // 2, N // 2, (N // 2 + 1) % N
         pi_, k1 = _lib.ptr_array(din)
         po, k2 = _lib.ptr_array(dout)
-        _lib.check(lib.mlb_fft_rows(pi_, ld, po, ld, other, N, 1, 1, tw.data_ptr(), rr, rc, ro, 2, None), "rows")
+        _lib.check(lib.mlb_fft_rows(pi_, ld, po, ld, other, N, 1, 1, tw.data_ptr(), rr, rc, ro, 0, 2, None), "rows")
         torch.cuda.synchronize()
         for v, d in zip(a, dout):
             ref = np.roll(np.fft.fft(np.roll(v.astype(complex), (rr, rc), axis=(0, 1)), axis=1), ro, axis=1)
@@ -237,7 +237,7 @@ def test_fft_passes_match_numpy():
             assert field_error(d[:, :other].cpu().numpy(), ref) < 3e-6, ("cols", N)
     bad = torch.zeros(4, 12, dtype=torch.complex64).cuda()
     pb, k4 = _lib.ptr_array([bad])
-    assert lib.mlb_fft_rows(pb, 12, pb, 12, 4, 12, 1, 1, bad.data_ptr(), 0, 0, 0, 1, None) != 0   # not a power of two
+    assert lib.mlb_fft_rows(pb, 12, pb, 12, 4, 12, 1, 1, bad.data_ptr(), 0, 0, 0, 0, 1, None) != 0   # not a power of two
     # fused fold: [n_rows*s1][N*s2] input, summed over the aliased copies while loading
     n_rows, N, s1, s2 = 6, 64, 3, 4
     big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
@@ -247,11 +247,32 @@ def test_fft_passes_match_numpy():
     _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
     pi_, k1 = _lib.ptr_array(dbig)
     po, k2 = _lib.ptr_array(dres)
-    _lib.check(lib.mlb_fft_rows(pi_, N * s2, po, N, n_rows, N, s1, s2, tw.data_ptr(), 2, 10, 5, 1, None), "fold rows")
+    _lib.check(lib.mlb_fft_rows(pi_, N * s2, po, N, n_rows, N, s1, s2, tw.data_ptr(), 2, 10, 5, 0, 1, None), "fold rows")
     torch.cuda.synchronize()
     folded = big.astype(complex).reshape(s1, n_rows, s2, N).sum(axis=(0, 2))
     ref = np.roll(np.fft.fft(np.roll(folded, (2, 10), axis=(0, 1)), axis=1), 5, axis=1)
     assert field_error(dres[0].cpu().numpy(), ref) < 3e-6
+    # TMA-fed persistent kernel (256..2048 points), plain and transposed output, ragged row count
+    for N, n_rows, s1, s2 in ((256, 7, 2, 3), (1024, 5, 1, 1), (2048, 3, 2, 2), (512, 301, 1, 1)):
+        assert lib.mlb_fft_rows_can_transpose(N) == 1
+        big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
+        dbig = [torch.from_numpy(big).cuda()]
+        tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
+        _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
+        folded = big.astype(complex).reshape(s1, n_rows, s2, N).sum(axis=(0, 2))
+        rr, rc, ro = n_rows // 2, 10, N // 2 + 3
+        ref = np.roll(np.fft.fft(np.roll(folded, (rr, rc), axis=(0, 1)), axis=1), ro, axis=1)
+        for tr in (0, 1):
+            ldo = (n_rows + (n_rows & 1) + 2) if tr else N
+            dres = [torch.zeros((N, ldo) if tr else (n_rows, ldo), dtype=torch.complex64).cuda()]
+            pi_, k1 = _lib.ptr_array(dbig)
+            po, k2 = _lib.ptr_array(dres)
+            _lib.check(lib.mlb_fft_rows(pi_, N * s2, po, ldo, n_rows, N, s1, s2, tw.data_ptr(), rr, rc, ro, tr, 1, None), "tma rows")
+            torch.cuda.synchronize()
+            got = dres[0].cpu().numpy()
+            got = got[:, :n_rows].T if tr else got
+            assert field_error(got, ref) < 3e-6, (N, tr)
+    assert lib.mlb_fft_rows_can_transpose(4096) == 0 and lib.mlb_fft_rows_can_transpose(128) == 0
 
 
 def test_twiddle_float64_phase_accuracy():
