@@ -25,6 +25,9 @@ from . import _lib
 from .units import Z0
 
 
+TWO_PASS_TRANSPOSE = False      # experiment switch, see FarfieldPlan._build
+
+
 def fft_bin_direction_cosines(num, spacing, wavelength, n_glass):
     """Un-shifted direction cosines of the FFT bins, same arithmetic as the reference
     (nearfield_farfield.py:35-39) so the NaN mask of evanescent bins is bit-identical."""
@@ -173,9 +176,12 @@ class FarfieldPlan:
             assert K1 == Kx and K2 == Ky
             self.Rx, self.Ry = K1, K2
             self.G = None          # the row pass folds while loading: the folded aperture never exists in memory
-            # two transposing row passes (both read contiguous rows through TMA) where the sizes allow it,
-            # otherwise a row pass followed by a strided column pass
-            self.two_pass_t = bool(self.lib.mlb_fft_rows_can_transpose(K1) and self.lib.mlb_fft_rows_can_transpose(K2))
+            # Row pass followed by a strided column pass.  (Two transposing row passes, both streaming
+            # contiguous rows through TMA, are implemented -- transpose_out of mlb_fft_rows -- but measured
+            # slower on B200: 98 + 54 us instead of 92 + 45 us at 1024^2, the 8-byte transposed stores and the
+            # one-row-at-a-time FFT latency of the second pass cost more than the strided reads they avoid.)
+            self.two_pass_t = bool(TWO_PASS_TRANSPOSE and self.lib.mlb_fft_rows_can_transpose(K1)
+                                   and self.lib.mlb_fft_rows_can_transpose(K2))
             self.W = [_c64_buffer(K2, K1, dev) if self.two_pass_t else _c64_buffer(K1, K2, dev) for _ in range(4)]
             self.tw1 = torch.empty(2 * K1, dtype=torch.complex64, device=dev)     # plain + staged tables
             self.tw2 = torch.empty(2 * K2, dtype=torch.complex64, device=dev)
