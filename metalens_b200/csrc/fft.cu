@@ -408,9 +408,39 @@ __global__ void __launch_bounds__(FftThreads<LGN>::value) fft_cols_kernel(const 
     float2 *__restrict__ out = pick4(a.out, blockIdx.y);
     const int c0 = blockIdx.x * L;
     for (int t = threadIdx.x; t < N; t += blockDim.x) stw[t] = a.tw[(LGN > 0 ? N : 0) + t];
-    int lgNs0;
-    if (a.lgN >= 2) {
-        lgNs0 = 2;
+    int lgNs0 = 2;
+    if constexpr (LGN > 0) {
+        // compile-time sized: every load of the thread is issued before the first butterfly (16 loads in
+        // flight per thread at 1024 x 4), lane/row splits are shifts
+        constexpr int CN = 1 << LGN, per = CN >> 2, total = per * CL, T = FftThreads<LGN>::value;
+        constexpr int iters = (total + T - 1) / T;
+        constexpr int lgCL = (CL == 16) ? 4 : (CL == 8) ? 3 : (CL == 4) ? 2 : (CL == 2) ? 1 : 0;
+        float2 v[iters][4];
+        const size_t step = (size_t)per * a.ld_in;
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int idx = it * T + threadIdx.x;
+            const int j = idx >> lgCL, lane = idx & (CL - 1);
+            const int c = c0 + lane;
+            if (idx < total && c < a.other) {
+                const float2 *src = in + (size_t)j * a.ld_in + c;
+                v[it][0] = src[0]; v[it][1] = src[step]; v[it][2] = src[2 * step]; v[it][3] = src[3 * step];
+            } else {
+                v[it][0] = v[it][1] = v[it][2] = v[it][3] = make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int idx = it * T + threadIdx.x;
+            if (idx < total) {
+                const int j = idx >> lgCL, lane = idx & (CL - 1);
+                bfly4(v[it][0], v[it][1], v[it][2], v[it][3]);
+                float2 *y = buf0 + lane * P + 4 * j;
+                *reinterpret_cast<float4 *>(y) = make_float4(v[it][0].x, v[it][0].y, v[it][1].x, v[it][1].y);
+                *reinterpret_cast<float4 *>(y + 2) = make_float4(v[it][2].x, v[it][2].y, v[it][3].x, v[it][3].y);
+            }
+        }
+    } else if (a.lgN >= 2) {
         const int per = N >> 2;
         const int total = per * L;
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -443,13 +473,25 @@ __global__ void __launch_bounds__(FftThreads<LGN>::value) fft_cols_kernel(const 
     if constexpr (LGN > 0) cur = fft_ct<LGN, 2, CL, (1 << LGN) + 4, 0>(buf0, buf1, stw);
     else cur = fft_in_smem(buf0, buf1, a.lgN, lgNs0, L, P, stw);
     const float2 *res = cur ? buf1 : buf0;
-    const int total = L << a.lgN;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int n = idx / L, lane = idx - n * L;              // n = OUTPUT row
-        const int c = c0 + lane;
-        if (c < a.other) {
-            const int q = (n - a.out_roll) & (N - 1);
-            out[(size_t)n * a.ld_out + c] = res[lane * P + q];
+    if constexpr (LGN > 0) {
+        constexpr int CN = 1 << LGN, total = CN * CL, T = FftThreads<LGN>::value, iters = total / T;
+        constexpr int lgCL = (CL == 16) ? 4 : (CL == 8) ? 3 : (CL == 4) ? 2 : (CL == 2) ? 1 : 0;
+#pragma unroll 8
+        for (int it = 0; it < iters; ++it) {
+            const int idx = it * T + threadIdx.x;
+            const int n = idx >> lgCL, lane = idx & (CL - 1);       // n = OUTPUT row
+            const int c = c0 + lane;
+            if (c < a.other) out[(size_t)n * a.ld_out + c] = res[lane * P + ((n - a.out_roll) & (CN - 1))];
+        }
+    } else {
+        const int total = L << a.lgN;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int n = idx / L, lane = idx - n * L;              // n = OUTPUT row
+            const int c = c0 + lane;
+            if (c < a.other) {
+                const int q = (n - a.out_roll) & (N - 1);
+                out[(size_t)n * a.ld_out + c] = res[lane * P + q];
+            }
         }
     }
 }
@@ -483,7 +525,7 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
 }
 
 // tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
-static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1;
+static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
@@ -510,8 +552,9 @@ extern "C" int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream) {
 
 extern "C" int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_threads, int rows_vec) {
     // rows_plain_loader: 2 = TMA-fed persistent kernel (default), 1 = thread-issued loads, 0 = first stage in loader
-    mlb::g_rows_tma = (rows_plain_loader == 2);
-    if (rows_plain_loader == 2) rows_plain_loader = 1;
+    mlb::g_rows_tma = (rows_plain_loader == 2 || rows_plain_loader == 3);
+    mlb::g_cols_half = (rows_plain_loader == 3);      // 3 = TMA rows + half-width column tiles
+    if (rows_plain_loader >= 2) rows_plain_loader = 1;
     MLB_REQUIRE((rows_threads == 64 || rows_threads == 128 || rows_threads == 256) && rows_points_per_cta >= 1 &&
                     (rows_vec == 1 || rows_vec == 2),
                 "mlb_fft_tune: bad arguments");
@@ -638,6 +681,7 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     // as many adjacent columns as fit 64 KB (so 3 CTAs share an SM), at most 16 (128-byte row segments)
     int lanes = 1;
     while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 4) * sizeof(float2) <= 66 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
+    if (mlb::g_cols_half && lanes >= 2) lanes /= 2;      // tuning: narrower column tiles, twice the CTAs per SM
     a.lanes = lanes;
     const size_t smem = (2 * (size_t)lanes * (N + 4) + N) * sizeof(float2);
     cudaStream_t st = (cudaStream_t)stream;
@@ -657,6 +701,9 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     if (a.lgN == 8 && lanes == 16) MLB_COLS_LAUNCH(8, 16);
     else if (a.lgN == 9 && lanes == 8) MLB_COLS_LAUNCH(9, 8);
     else if (a.lgN == 10 && lanes == 4) MLB_COLS_LAUNCH(10, 4);
+    else if (a.lgN == 10 && lanes == 2) MLB_COLS_LAUNCH(10, 2);
+    else if (a.lgN == 9 && lanes == 4) MLB_COLS_LAUNCH(9, 4);
+    else if (a.lgN == 11 && lanes == 1) MLB_COLS_LAUNCH(11, 1);
     else if (a.lgN == 11 && lanes == 2) MLB_COLS_LAUNCH(11, 2);
     else if (a.lgN == 12 && lanes == 1) MLB_COLS_LAUNCH(12, 1);
     else if (a.lgN == 13 && lanes == 1) MLB_COLS_LAUNCH(13, 1);

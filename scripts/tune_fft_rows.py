@@ -22,14 +22,14 @@ def t_kernel(k):
     for i in range(30): steps[i % 3][k][1]()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 30 * 1e3
-for plain, pts, thr, vec in ((2, 1024, 256, 2), (1, 1024, 256, 2), (2, 1024, 256, 2)):
+for plain, pts, thr, vec in ((3, 1024, 256, 2), (2, 1024, 256, 2)):
     _lib.check(lib.mlb_fft_tune(plain, pts, thr, vec), "tune")
     try:
         us = t_kernel(0)
         plans[0].run(fields[0]); P = plans[0].P.clone()
         if ref is None: ref = P
         ok = bool(torch.allclose(torch.nan_to_num(P), torch.nan_to_num(ref), rtol=1e-4, atol=0))
-        print("plain=%d points/cta=%d threads=%d vec=%d : rows %.1f us  (%.0f GB/s)  same=%s" % (plain, pts, thr, vec, us, 32 * (M * M + 1024 * 1024) / us / 1e3, ok), flush=True)
+        print("plain=%d points/cta=%d threads=%d vec=%d : rows %.1f us  (%.0f GB/s)  cols %.1f us  epilogue %.1f us  same=%s" % (plain, pts, thr, vec, us, 32 * (M * M + 1024 * 1024) / us / 1e3, t_kernel(1), t_kernel(2), ok), flush=True)
     except Exception as e:
         print("plain=%d pts=%d thr=%d vec=%d failed: %s" % (plain, pts, thr, vec, e), flush=True)
 print("cols %.1f us" % t_kernel(1))
