@@ -406,3 +406,68 @@ def test_tensor_core_path_matches_reference(golden_dir):
     P_ref, F_ref = fo.farfield_dense(Ex, Ey, Hx, Hy, x[1] - x[0], y[1] - y[0], ux, uy, WL, NG)
     assert power_map_error(P1, P_ref) < FF_TOL and power_map_error(P2, P_ref) < FF_TOL
     assert field_error(a1[0], F_ref[0]) < 2e-5 and field_error(a2[0], F_ref[0]) < 3e-6
+
+
+def test_random_shapes_all_methods_against_oracle():
+    """Seeded sweep over ragged aperture shapes, strides and arbitrary grids: every applicable method
+    against the float64 direct sum (oracle), plus the all-zero aperture (empty input)."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import FarfieldPlan
+    rng = np.random.default_rng(2024)
+    d = WL / 2.2
+    for trial in range(14):
+        Mx, My = int(rng.integers(6, 150)), int(rng.integers(6, 150))
+        fields = [(rng.standard_normal((Mx, My)) + 1j * rng.standard_normal((Mx, My))).astype(np.complex64) for _ in range(4)]
+        dev = [torch.from_numpy(a).cuda() for a in fields]
+        if trial % 2 == 0:                       # arbitrary direction-cosine grid
+            ux = np.sort(rng.uniform(-0.95, 0.95, int(rng.integers(1, 70))))
+            uy = np.sort(rng.uniform(-0.95, 0.95, int(rng.integers(1, 70))))
+            kw, methods = dict(ux=ux, uy=uy), ("dense", "tc")
+        else:                                    # strided FFT-bin grid
+            sx = int(rng.choice([s for s in (1, 2, 3, 4) if Mx % s == 0 and (Mx // 2) % s == 0]))
+            sy = int(rng.choice([s for s in (1, 2, 3, 4) if My % s == 0 and (My // 2) % s == 0]))
+            kw, methods = dict(stride=(sx, sy)), ("auto", "dense", "tc") + (("fold",) if sx * sy > 1 else ())
+        ref = None
+        for m in methods:
+            plan = FarfieldPlan((Mx, My), d, d, WL, NG, method=m, **kw)
+            P = plan.run(dev)[0].cpu().numpy()
+            if ref is None:
+                ref, _ = fo.farfield_dense(*fields, d, d, plan.ux, plan.uy, WL, NG)
+            if np.isfinite(ref).any():
+                assert power_map_error(P, ref) < (3e-5 if m == "tc" else FF_TOL), (trial, Mx, My, m, kw.get("stride"))
+            else:
+                assert np.isnan(P).all()
+    zero = [torch.zeros(64, 64, dtype=torch.complex64).cuda() for _ in range(4)]
+    plan = FarfieldPlan((64, 64), d, d, WL, NG, stride=1)
+    P, total = plan.run(zero)
+    P = P.cpu().numpy()
+    assert total.item() == 0.0 and np.all((P == 0) | np.isnan(P)) and np.isnan(P).sum() > 0
+
+
+def test_config3_full_size_fft_path():
+    """BASELINE config 3 size (4096^2 -> 1024^2): the TMA-fed fold+FFT path against the float64 direct
+    sum on a sample of bins, and against the stand-alone fold + tiled reduction."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import FarfieldPlan
+    M, s = 4096, 4
+    wl, ng = 635e-9, apertures.N_GLASS[635]
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 7, wl, ng)
+    d = x[1] - x[0]
+    dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+    fft = FarfieldPlan((M, M), d, d, wl, ng, stride=s)
+    assert fft.method == "fft"
+    Pq, tq = fft.run(dev)
+    Pq = Pq.cpu().numpy()
+    fold = FarfieldPlan((M, M), d, d, wl, ng, stride=s, method="fold")
+    Pf, tf = fold.run(dev)
+    assert power_map_error(Pq, Pf.cpu().numpy()) < FF_TOL
+    assert abs(tq.item() - tf.item()) <= FF_TOL * abs(tf.item())
+    ii = np.array([0, 100, 511, 512, 513, 700, 1023])
+    jj = np.array([5, 512, 520, 900])
+    P_ref, _ = fo.farfield_dense(Ex, Ey, Hx, Hy, d, d, fft.ux[ii], fft.uy[jj], wl, ng)
+    sub = Pq[np.ix_(ii, jj)]
+    assert np.array_equal(np.isnan(sub), np.isnan(P_ref))
+    fin = np.isfinite(P_ref)
+    assert np.abs(sub - P_ref)[fin].max() / np.nanmax(Pq) < FF_TOL
+    P_in = float((Ex * np.conj(Hy) - Ey * np.conj(Hx)).real.sum()) * d * d
+    assert abs(tq.item() / P_in - 1) < 5e-3
