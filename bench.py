@@ -208,6 +208,42 @@ def bench_nearfield(M, torch, cpu_cols=384):
     return res
 
 
+def bench_sweep(torch, steps=56, M=256):
+    """BASELINE config 5 shape: a 5..60 degree sweep of 256 x 256 beam-deflector patches, one NF->FF
+    + figure-of-merit evaluation per step; eager launches vs one captured CUDA graph replayed per step."""
+    from metalens_b200.farfield import FarfieldPlan
+    from metalens_b200.fom import FarfieldFOM
+    wl, ng = 532e-9, apertures.N_GLASS[532]
+    plan = FarfieldPlan((M, M), wl / 2.2, wl / 2.2, wl, ng, stride=1)
+    fom = FarfieldFOM(plan, 0.3, 0.0, 0.05)
+    angles = np.linspace(5.0, 60.0, steps)
+    patches = []
+    for a in angles[:8]:
+        Ex, Ey, Hx, Hy, x, y = apertures.tilted_te(M, wl, ng, angle_deg=float(a))
+        patches.append(torch.stack([torch.from_numpy(v.astype(np.complex64)) for v in (Ex, Ey, Hx, Hy)]).cuda())
+
+    def run(replay):
+        vals = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            fom.static_fields[:, :, :M].copy_(patches[k % len(patches)])      # the step's new aperture
+            r = fom.replay() if replay else fom.evaluate()
+            vals.append(r.clone())
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps * 1e6, vals
+    fom.evaluate()
+    run(False)
+    eager_us, v0 = run(False)
+    fom.capture()
+    run(True)
+    graph_us, v1 = run(True)
+    same = all(bool(torch.equal(a, b)) for a, b in zip(v0, v1))
+    return dict(steps=steps, aperture=[M, M], far_field=[plan.Kx, plan.Ky], method=plan.method,
+                eager_us_per_step=eager_us, graph_us_per_step=graph_us, identical_results=same,
+                note="wall clock per step incl. the device copy of the step's aperture; 56 angles 5..60 deg")
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def ours(args):
     import torch
@@ -415,6 +451,10 @@ def ours(args):
         torch.cuda.empty_cache()
         nf = bench_nearfield(args.nearfield_m, torch)
 
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_paths:
+        sweep = bench_sweep(torch)
+
     if rank == 0:
         line = {
             "metric": "far-field points/sec (NF->FF)", "value": value, "unit": "far-field points/s",
@@ -435,6 +475,7 @@ def ours(args):
             "paths_points_per_s": paths,
             "other_workloads": other,
             "nearfield_assembly": nf,
+            "fom_sweep": sweep,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
