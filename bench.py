@@ -157,7 +157,7 @@ def reference_arm(args):
         "e2e": {"value": base["value"], "unit": "far-field points/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- hot path B
@@ -299,7 +299,8 @@ def ours(args):
         return [dev_fields[item][f] for f in range(4)]
 
     def step_device():
-        return sharded.run(fields_of)            # local tiles + the one all-gather
+        # local tiles + the one all-gather, which overlaps the next step's kernels (double-buffered)
+        return sharded.run(fields_of, overlap=True)
 
     def host_runner(plan, pin):
         plan.run_host(pin)                       # pinned host -> H2D -> kernels -> D2H of P and total_P
@@ -328,6 +329,7 @@ def ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        sharded.finish()                          # outstanding asynchronous all-gathers
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -478,12 +480,31 @@ def ours(args):
             "fom_sweep": sweep,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner, torchrun its OMP note) must not pollute the ONE JSON line:
+    everything written to fd 1 from here on goes to stderr; the JSON line is written to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_STDOUT_FD, data)
+
+
+_STDOUT_FD = 1
+
+
 def main():
+    global _STDOUT_FD
+    _STDOUT_FD = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

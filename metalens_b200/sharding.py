@@ -39,20 +39,24 @@ def tile_schedule(n_items, n_rows, world):
     return [tiles[r * per_rank:(r + 1) * per_rank] for r in range(world)]
 
 
-def gather_tiles(local, n_items, n_rows, world, group=None):
+def gather_tiles(local, n_items, n_rows, world, group=None, out=None, async_op=False):
     """All-gather the per-rank tile stacks into the full far field on every rank.
 
     local : (tiles_per_rank, rows_per_tile, n_cols) tensor of this rank's tiles in schedule order.
-    Returns (n_items, n_rows, n_cols).  Tiles are ordered item-major, slab-minor and ranks own
-    consecutive tiles, so the gathered buffer IS the result: no reshuffle after the collective.
+    Returns (n_items, n_rows, n_cols) [, work handle when async_op].  Tiles are ordered item-major,
+    slab-minor and ranks own consecutive tiles, so the gathered buffer IS the result: no reshuffle
+    after the collective.
     """
     t, rows, cols = local.shape
-    out = torch.empty((world * t, rows, cols), dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty((world * t, rows, cols), dtype=local.dtype, device=local.device)
+    work = None
     if world == 1:
         out.copy_(local)
     else:
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out.view(n_items, n_rows, cols)
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=group, async_op=async_op)
+    res = out.view(n_items, n_rows, cols)
+    return (res, work) if async_op else res
 
 
 class ShardedFarfield:
@@ -71,21 +75,47 @@ class ShardedFarfield:
         self.schedule = tile_schedule(n_items, n_rows, self.world)
         self.tiles = self.schedule[self.rank]
         self.plans = [make_plan(t.item, t.row0, t.row1) for t in self.tiles]
-        self._local = None
+        # double-buffered tile stacks / gather targets so that the all-gather of step i can overlap the
+        # kernels of step i+1 (overlap=True): a buffer is reused only after its collective has completed
+        self._local = [None, None]
+        self._out = [None, None]
+        self._work = [None, None]
+        self._flip = 0
 
     @property
     def items_needed(self):
         return sorted({t.item for t in self.tiles})
 
-    def run(self, fields_of, runner=None):
+    def run(self, fields_of, runner=None, overlap=False):
         """Compute this rank's tiles, then the single all-gather.  Returns
         (P (n_items, n_rows, Ky) on every rank, partial total_P per local tile).
-        `runner(plan, fields)` defaults to ``plan.run(fields)``."""
+        `runner(plan, fields)` defaults to ``plan.run(fields)``.  With overlap=True the collective is
+        asynchronous (the result is complete after ``finish()`` or a device synchronize) and runs
+        concurrently with the next call's kernels."""
+        b = self._flip
+        self._flip ^= 1
+        if self._work[b] is not None:            # the collective that last used this buffer pair
+            self._work[b].wait()
+            self._work[b] = None
         totals = []
         for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
             P, total = plan.run(fields_of(tile.item)) if runner is None else runner(plan, fields_of(tile.item))
-            if self._local is None:
-                self._local = torch.empty((len(self.tiles),) + tuple(P.shape), dtype=P.dtype, device=P.device)
-            self._local[k].copy_(P)
+            if self._local[b] is None:
+                shape = (len(self.tiles),) + tuple(P.shape)
+                self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
+                self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
+            self._local[b][k].copy_(P)
             totals.append(total)
-        return gather_tiles(self._local, self.n_items, self.n_rows, self.world, self.group), totals
+        if overlap and self.world > 1:
+            res, self._work[b] = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group,
+                                              out=self._out[b], async_op=True)
+        else:
+            res = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group, out=self._out[b])
+        return res, totals
+
+    def finish(self):
+        """Wait for outstanding asynchronous all-gathers."""
+        for b in (0, 1):
+            if self._work[b] is not None:
+                self._work[b].wait()
+                self._work[b] = None

@@ -38,6 +38,11 @@ def _worker(rank, world, port, n_items, method, q):
         dev = {i: [torch.from_numpy(a).cuda() for a in _fields(i)[:4]] for i in sh.items_needed}
         P, _ = sh.run(lambda item: dev[item])
         torch.cuda.synchronize()
+        # overlapped (asynchronous, double-buffered) gathers give the same result
+        outs = [sh.run(lambda item: dev[item], overlap=True)[0] for _ in range(3)]
+        sh.finish()
+        torch.cuda.synchronize()
+        assert all(bool(((o == P) | (torch.isnan(o) & torch.isnan(P))).all()) for o in outs)
         ref = []
         for i in range(n_items):
             plan = FarfieldPlan((M, M), d, d, WL, NG, stride=4, method=method)
