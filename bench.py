@@ -15,7 +15,11 @@ e2e    = same metric through FarfieldPlan.run_host(): pinned host fields -> H2D 
          kernels -> D2H of P, every step
 N > 1  : one process per GPU (torchrun), weak scaling -- every rank owns a full batch of its
          own apertures (far-field tiles of different sources); one NCCL all-gather of the P
-         tiles per step is inside the timed region.
+         tiles per step is inside the timed region (asynchronous, double-buffered: it overlaps the
+         kernels of the next step).
+Extra keys on the same line: roofline (dominant kernel), kernels (CUDA-event time of every kernel of a
+step), paths_points_per_s (other formulations on the same workload), other_workloads (cfg2),
+nearfield_assembly (hot path B), fom_sweep (cfg5 shape), cpu_baseline.
 """
 import argparse
 import json

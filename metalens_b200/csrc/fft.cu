@@ -7,8 +7,12 @@
 //   * the row pass folds the aperture while loading (sum of the s1*s2 aliased samples per point,
 //     see fold.cu), so for a strided grid the full aperture is read from HBM exactly once and the
 //     folded aperture never goes to memory: this kernel is the HBM-bound hot kernel of NF->FF;
+//   * for 256..2048-point rows that pass is a persistent TMA-fed producer/consumer pipeline
+//     (fft_rows_tma_kernel: 94 % of the measured HBM copy bandwidth on B200); other sizes use the
+//     thread-issued-load kernels (fft_rows_kernel), compile-time sized for 256..8192 points;
 //   * fftshift of input and output is index arithmetic ("rolls") at load/store time;
-//   * twiddles come from a table built with float64 phases.
+//   * twiddles come from tables built with float64 phases, re-ordered per Stockham stage so that the
+//     shared-memory reads are conflict-free.
 // All sizes are powers of two, so index math is shifts and masks.
 #include "common.cuh"
 
