@@ -133,7 +133,9 @@ int mlb_fft_rows_can_transpose(int N);
 int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
                  int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
                  int batch, void *stream);
-/* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}; in-place allowed */
+/* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}.  In-place allowed
+ * for N <= 2048; for N >= 4096 the transform is a four-step decomposition that uses the INPUT buffer as
+ * scratch (it is overwritten) and needs out != in. */
 int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N, int n_cols,
                  const mlb_c64 *tw, int out_roll, int batch, void *stream);
 

@@ -500,6 +500,92 @@ __global__ void __launch_bounds__(FftThreads<LGN>::value) fft_cols_kernel(const 
     }
 }
 
+// ---- long column transforms (N >= 4096): four-step decomposition N = A * B ------------------------------
+// A strided column of 4096/8192 points does not fit a shared-memory tile that is also wide enough for
+// coalesced 128-byte row segments, so the column pass becomes two passes over 16-column tiles:
+//   pass 1, for every n2 < B:  A-point DFT over rows n2 + n1*B, times W_N^(n2*k1), stored in place
+//   pass 2, for every k1 < A:  B-point DFT over rows k1*B + n2, stored at row (k1 + A*k2 + roll) mod N
+// (X[k1 + A k2] = sum_n2 W_B^(n2 k2) W_N^(n2 k1) sum_n1 x[B n1 + n2] W_A^(n1 k1)).  Both passes move
+// 128-byte row segments; the sub-transforms reuse the compile-time Stockham stages.
+struct FftSubArgs {
+    const float2 *in[4];
+    float2 *out[4];
+    const float2 *tw;          // plain table W_N^t of the FULL length N (first N entries of mlb_fft_twiddle)
+    int ld_in, ld_out, lgNtot, n_cols;
+    int in_gs, in_rs;          // input row  = g*in_gs  + n*in_rs
+    int out_gs, out_rs, roll;  // output row = (g*out_gs + q*out_rs + roll) mod N
+    int twiddle;               // multiply output q of sub-transform g by W_N^(g*q)
+};
+
+template <int LGA, int CL>
+__global__ void __launch_bounds__(256) fft_cols_sub_kernel(const FftSubArgs a) {
+    constexpr int A = 1 << LGA, P = A + 4, per = A >> 2, total = per * CL, iters = (total + 255) / 256;
+    constexpr int lgCL = (CL == 16) ? 4 : (CL == 8) ? 3 : (CL == 4) ? 2 : (CL == 2) ? 1 : 0;
+    __shared__ __align__(16) float2 buf0[CL * P];
+    __shared__ __align__(16) float2 buf1[CL * P];
+    __shared__ float2 stw[A];
+    const float2 *__restrict__ in = pick4(a.in, blockIdx.z);
+    float2 *__restrict__ out = pick4(a.out, blockIdx.z);
+    const int c0 = blockIdx.x * CL, g = blockIdx.y;
+    const int Nmask = (1 << a.lgNtot) - 1;
+    // staged twiddle table of the A-point sub-transform, taken from the length-N table: W_A^t = W_N^(t N/A)
+    for (int t = threadIdx.x; t < A; t += 256) {
+        float2 w = make_float2(1.f, 0.f);
+        int Ns = 1, lg = 0;
+        bool done = false;
+        while (lg + 2 <= LGA && !done) {
+            if (t >= Ns - 1 && t < 4 * Ns - 1) {
+                const int e = t - (Ns - 1), k = e / 3, r = e - 3 * k + 1;
+                w = __ldg(a.tw + (((r * k) << (a.lgNtot - lg - 2)) & Nmask));
+                done = true;
+            }
+            Ns *= 4; lg += 2;
+        }
+        if (!done && lg < LGA && t >= Ns - 1 && t < 2 * Ns - 1) w = __ldg(a.tw + (((t - (Ns - 1)) << (a.lgNtot - lg - 1)) & Nmask));
+        stw[t] = w;
+    }
+    float2 v[iters][4];
+#pragma unroll
+    for (int it = 0; it < iters; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        const int j = idx >> lgCL, lane = idx & (CL - 1);
+        const int c = c0 + lane;
+        if (idx < total && c < a.n_cols) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                v[it][r] = in[(size_t)(g * a.in_gs + (j + r * per) * a.in_rs) * a.ld_in + c];
+        } else {
+            v[it][0] = v[it][1] = v[it][2] = v[it][3] = make_float2(0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < iters; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        if (idx < total) {
+            const int j = idx >> lgCL, lane = idx & (CL - 1);
+            bfly4(v[it][0], v[it][1], v[it][2], v[it][3]);
+            float2 *y = buf0 + lane * P + 4 * j;
+            *reinterpret_cast<float4 *>(y) = make_float4(v[it][0].x, v[it][0].y, v[it][1].x, v[it][1].y);
+            *reinterpret_cast<float4 *>(y + 2) = make_float4(v[it][2].x, v[it][2].y, v[it][3].x, v[it][3].y);
+        }
+    }
+    const int cur = fft_ct<LGA, 2, CL, P, 0>(buf0, buf1, stw);
+    const float2 *res = cur ? buf1 : buf0;
+    constexpr int otot = A * CL, oit = (otot + 255) / 256;
+#pragma unroll 4
+    for (int it = 0; it < oit; ++it) {
+        const int idx = it * 256 + threadIdx.x;
+        const int q = idx >> lgCL, lane = idx & (CL - 1);
+        const int c = c0 + lane;
+        if (idx < otot && c < a.n_cols) {
+            float2 w = res[lane * P + q];
+            if (a.twiddle) w = cmulf(w, __ldg(a.tw + ((g * q) & Nmask)));
+            const int orow = (g * a.out_gs + q * a.out_rs + a.roll) & Nmask;
+            out[(size_t)orow * a.ld_out + c] = w;
+        }
+    }
+}
+
 __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
@@ -682,6 +768,29 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.tw = reinterpret_cast<const float2 *>(tw);
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1;
+    if (a.lgN >= 12) {
+        for (int b = 0; b < batch; ++b)
+            MLB_REQUIRE(a.in[b] != a.out[b], "mlb_fft_cols: N >= 4096 needs out != in (the input is used as scratch)");
+        // four-step: N = A*B with A = 64; pass 1 works in place on the INPUT buffer (it is overwritten)
+        const int lgA = 6, lgB = a.lgN - lgA, Asz = 1 << lgA, Bsz = 1 << lgB;
+        mlb::FftSubArgs s1, s2;
+        for (int b = 0; b < 4; ++b) {
+            s1.in[b] = a.in[b]; s1.out[b] = const_cast<float2 *>(a.in[b]);
+            s2.in[b] = a.in[b]; s2.out[b] = a.out[b];
+        }
+        s1.tw = s2.tw = a.tw;
+        s1.ld_in = s1.ld_out = ld_in; s2.ld_in = ld_in; s2.ld_out = ld_out;
+        s1.lgNtot = s2.lgNtot = a.lgN; s1.n_cols = s2.n_cols = n_cols;
+        s1.in_gs = 1; s1.in_rs = Bsz; s1.out_gs = 1; s1.out_rs = Bsz; s1.roll = 0; s1.twiddle = 1;
+        s2.in_gs = Bsz; s2.in_rs = 1; s2.out_gs = 1; s2.out_rs = Asz; s2.roll = out_roll; s2.twiddle = 0;
+        cudaStream_t st = (cudaStream_t)stream;
+        dim3 g1((n_cols + 15) / 16, Bsz, batch), g2((n_cols + 15) / 16, Asz, batch);
+        mlb::fft_cols_sub_kernel<6, 16><<<g1, 256, 0, st>>>(s1);
+        if (int rc = mlb::check_launch("mlb_fft_cols(four-step pass 1)")) return rc;
+        if (lgB == 6) mlb::fft_cols_sub_kernel<6, 16><<<g2, 256, 0, st>>>(s2);
+        else mlb::fft_cols_sub_kernel<7, 16><<<g2, 256, 0, st>>>(s2);
+        return mlb::check_launch("mlb_fft_cols(four-step pass 2)");
+    }
     // as many adjacent columns as fit 64 KB (so 3 CTAs share an SM), at most 16 (128-byte row segments)
     int lanes = 1;
     while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 4) * sizeof(float2) <= 66 * 1024 && lanes * 2 <= n_cols) lanes *= 2;

@@ -207,7 +207,8 @@ def test_fft_passes_match_numpy():
     lib = _lib.load()
     rng = np.random.default_rng(9)
     assert lib.mlb_fft_max_length() == 8192
-    for N, other in ((2, 5), (4, 3), (8, 9), (16, 4), (64, 33), (128, 7), (512, 6), (1024, 5), (2048, 3), (8192, 2)):
+    for N, other in ((2, 5), (4, 3), (8, 9), (16, 4), (64, 33), (128, 7), (512, 6), (1024, 5), (2048, 3), (4096, 19),
+                     (8192, 2)):
         a = [(rng.standard_normal((other, N)) + 1j * rng.standard_normal((other, N))).astype(np.complex64) for _ in range(2)]
         tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
         _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
@@ -230,7 +231,14 @@ def test_fft_passes_match_numpy():
         for d, v in zip(dcol, a):
             d[:, :other].copy_(torch.from_numpy(v.T.copy()))
         pc, k3 = _lib.ptr_array(dcol)
-        _lib.check(lib.mlb_fft_cols(pc, ldc, pc, ldc, N, other, tw.data_ptr(), ro, 2, None), "cols")
+        if N >= 4096:       # four-step decomposition: input is scratch, output must be a different buffer
+            assert lib.mlb_fft_cols(pc, ldc, pc, ldc, N, other, tw.data_ptr(), ro, 2, None) != 0
+            dco = [torch.zeros(N, ldc, dtype=torch.complex64).cuda() for _ in a]
+            pco, k4 = _lib.ptr_array(dco)
+            _lib.check(lib.mlb_fft_cols(pc, ldc, pco, ldc, N, other, tw.data_ptr(), ro, 2, None), "cols")
+            dcol = dco
+        else:
+            _lib.check(lib.mlb_fft_cols(pc, ldc, pc, ldc, N, other, tw.data_ptr(), ro, 2, None), "cols")
         torch.cuda.synchronize()
         for v, d in zip(a, dcol):
             ref = np.roll(np.fft.fft(v.astype(complex).T, axis=0), ro, axis=0)
