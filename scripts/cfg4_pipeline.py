@@ -43,6 +43,7 @@ for stride in (4, 1):
     t = timed(lambda: plan.run(fields))
     K = plan.Kx
     P, total = plan.run(fields)
+    P = P.clone()          # the per-kernel timings below reuse (and for N >= 4096 scratch over) the plan's buffers
     print("NF->FF stride %d (%s): %dx%d far field in %.3f ms = %.2e points/s; total_P/P_in = %.4f" % (
         stride, plan.method, K, K, t, K * K / t * 1e3, total.item() / nf.run(0.0, 0.0, -f, "x", x, x, out=out)[1].item()), flush=True)
     for name, fn, nbytes, flops in plan.steps(fields):

@@ -479,3 +479,26 @@ def test_config3_full_size_fft_path():
     assert np.abs(sub - P_ref)[fin].max() / np.nanmax(Pq) < FF_TOL
     P_in = float((Ex * np.conj(Hy) - Ey * np.conj(Hx)).real.sum()) * d * d
     assert abs(tq.item() / P_in - 1) < 5e-3
+
+
+def test_long_column_transform_all_bins():
+    """4096 x 256 aperture, all FFT bins: the x transform has 4096 points and takes the four-step column
+    pass (its input buffer is scratch); compared with the float64 direct sum on a sample of bins and
+    with the tiled reduction; a second run() must give the same answer (scratch is re-filled)."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import FarfieldPlan
+    Mx, My = 4096, 256
+    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(Mx, 33, WL, My=My)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
+    plan = FarfieldPlan((Mx, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=1)
+    assert plan.method == "fft"
+    P1 = plan.run(dev)[0].clone()
+    P2 = plan.run(dev)[0].clone()
+    assert bool(((P1 == P2) | (torch.isnan(P1) & torch.isnan(P2))).all())
+    ii = np.array([0, 1, 63, 64, 65, 2047, 2048, 2049, 4032, 4095])
+    jj = np.array([0, 17, 128, 200, 255])
+    P_ref, _ = fo.farfield_dense(Ex, Ey, Hx, Hy, x[1] - x[0], y[1] - y[0], plan.ux[ii], plan.uy[jj], WL, NG)
+    sub = P1.cpu().numpy()[np.ix_(ii, jj)]
+    assert np.array_equal(np.isnan(sub), np.isnan(P_ref))
+    fin = np.isfinite(P_ref)
+    assert np.abs(sub - P_ref)[fin].max() / np.nanmax(P1.cpu().numpy()) < FF_TOL
