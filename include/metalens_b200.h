@@ -178,6 +178,8 @@ int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream
  *            lens_center.py:188-226 tables with the four values one corner needs adjacent
  *   values_f32 : the same table as complex64 (float pairs), read by the complex64-output path
  *   orders : int32 [n_orders][2] = (ox,oy) in the reference's loop order (nearfield.py:264)
+ *   order_map : int32 [(2R+1)^2], entry (ox+R)*(2R+1)+(oy+R) = index of (ox,oy) in `orders` or -1;
+ *            R = order_radius = max |ox|,|oy|.  Lets the kernel visit only the orders that can propagate
  *   bounds : interpolator_bounds 6-tuple (grating.py:1230-1232)
  *   stats_slot : first slot of this pack in the `stats` array of mlb_nearfield_assemble */
 typedef struct mlb_table_pack {
@@ -185,10 +187,11 @@ typedef struct mlb_table_pack {
     const double *values;
     const float *values_f32;
     const int *orders;
+    const int *order_map;
     int n_ux, n_uy, n_g, n_orders;
     double bounds[6];
     int stats_slot;
-    int _pad;
+    int order_radius;
 } mlb_table_pack;
 
 /* Everything build_nearfield (nearfield.py:66-480) reads, as device arrays + scalars. */

@@ -284,20 +284,26 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                 Interp3 q;
                 bool located = false;
                 const double qx = 2.0 * PI / gp, qy = 2.0 * PI / lat;
+                // Orders that can propagate in air satisfy |ux + ox*lambda/gp| <= 1 and |uy + oy*lambda/lat| <= 1:
+                // only that (small) index box is visited, through the pack's dense (ox,oy) -> order map; an
+                // fp32 screen with margin picks the box, the exact float64 test of :279 decides.
                 const float fux = (float)uxp, fuy = (float)uyp, fqx = (float)(qx / kvac), fqy = (float)(qy / kvac);
-                for (int o = 0; o < p.n_orders; ++o) {
-                    const int ox = p.orders[2 * o], oy = p.orders[2 * o + 1];
-                    // cheap fp32 screen: clearly evanescent-in-air orders are skipped before any float64 work
-                    const float sx = fmaf((float)ox, fqx, fux), sy = fmaf((float)oy, fqy, fuy);
-                    if (fmaf(sx, sx, sy * sy) > 1.001f) continue;
+                const int R = p.order_radius, W = 2 * R + 1;
+                const int ox_lo = max(-R, (int)ceilf((-1.001f - fux) / fqx)), ox_hi = min(R, (int)floorf((1.001f - fux) / fqx));
+                const int oy_lo = max(-R, (int)ceilf((-1.001f - fuy) / fqy)), oy_hi = min(R, (int)floorf((1.001f - fuy) / fqy));
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
                     const double kxp = kvac * uxp + ox * qx;                               // :268
-                    const double kyp = kvac * uyp + oy * qy;                               // :269
-                    if (kxp * kxp + kyp * kyp <= kvac * kvac) {                            // :279
-                        record<STATS>(p, o, uxp, uyp, gp, true, out.stats, out.violation);
-                        if (!located) { q = locate(p, uxp, uyp, gp); located = true; }
-                        // kzp (:287), phase about the grating centre (:291), table gathers, accumulation
-                        order_term<FAST>(p, o, q, Hw_x, Hw_y, kxp, kyp, kg, kvac, inv_kg_n, L.Z0, kxp * xp + kyp * yp,
-                                         Exp, Eyp, Hxp, Hyp);
+                    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+                        const int o = p.order_map[(ox + R) * W + (oy + R)];
+                        if (o < 0) continue;                                               // order not in the tables
+                        const double kyp = kvac * uyp + oy * qy;                           // :269
+                        if (kxp * kxp + kyp * kyp <= kvac * kvac) {                        // :279
+                            record<STATS>(p, o, uxp, uyp, gp, true, out.stats, out.violation);
+                            if (!located) { q = locate(p, uxp, uyp, gp); located = true; }
+                            // kzp (:287), phase about the grating centre (:291), table gathers, accumulation
+                            order_term<FAST>(p, o, q, Hw_x, Hw_y, kxp, kyp, kg, kvac, inv_kg_n, L.Z0, kxp * xp + kyp * yp,
+                                             Exp, Eyp, Hxp, Hyp);
+                        }
                     }
                 }
             }
@@ -354,18 +360,22 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                 bool located = false;
                 const double qx = 2.0 * PI / L.hex_x_period, qy = 2.0 * PI / L.hex_y_period;
                 const float fux = (float)ux, fuy = (float)uy, fqx = (float)(qx / kvac), fqy = (float)(qy / kvac);
-                for (int o = 0; o < p.n_orders; ++o) {
-                    const int ox = p.orders[2 * o], oy = p.orders[2 * o + 1];
-                    const float sx = fmaf((float)ox, fqx, fux), sy = fmaf((float)oy, fqy, fuy);
-                    if (fmaf(sx, sx, sy * sy) > 1.001f) continue;
+                const int R = p.order_radius, W = 2 * R + 1;
+                const int ox_lo = max(-R, (int)ceilf((-1.001f - fux) / fqx)), ox_hi = min(R, (int)floorf((1.001f - fux) / fqx));
+                const int oy_lo = max(-R, (int)ceilf((-1.001f - fuy) / fqy)), oy_hi = min(R, (int)floorf((1.001f - fuy) / fqy));
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
                     const double kx = kvac * ux + ox * qx;                                         // :395
-                    const double ky = kvac * uy + oy * qy;                                         // :396
-                    if (kx * kx + ky * ky <= kvac * kvac) {                                        // :398
-                        record<STATS>(p, o, ux, uy, which, false, out.stats, out.violation);
-                        if (!located) { q = locate(p, ux, uy, which); located = true; }
-                        // kz (:404), phase about the cell centre (:408-409), gathers, accumulation
-                        order_term<FAST>(p, o, q, Hw_x, Hw_y, kx, ky, kg, kvac, inv_kg_n, L.Z0,
-                                         kx * (x - cx) + ky * (y - cy), Ex, Ey, Hx, Hy);
+                    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+                        const int o = p.order_map[(ox + R) * W + (oy + R)];
+                        if (o < 0) continue;
+                        const double ky = kvac * uy + oy * qy;                                     // :396
+                        if (kx * kx + ky * ky <= kvac * kvac) {                                    // :398
+                            record<STATS>(p, o, ux, uy, which, false, out.stats, out.violation);
+                            if (!located) { q = locate(p, ux, uy, which); located = true; }
+                            // kz (:404), phase about the cell centre (:408-409), gathers, accumulation
+                            order_term<FAST>(p, o, q, Hw_x, Hw_y, kx, ky, kg, kvac, inv_kg_n, L.Z0,
+                                             kx * (x - cx) + ky * (y - cy), Ex, Ey, Hx, Hy);
+                        }
                     }
                 }
                 if (!L.plane_wave) {                                                // :453-461
@@ -438,6 +448,7 @@ extern "C" int mlb_nearfield_blocks(int nx, int ny) { return nx * ((ny + mlb::NF
 static int check_pack(const mlb_table_pack &p, const char *what) {
     MLB_REQUIRE(p.axes && p.values && p.values_f32 && p.orders, "mlb_nearfield_assemble: %s pack has NULL arrays", what);
     MLB_REQUIRE(mlb::aligned16(p.values_f32), "mlb_nearfield_assemble: %s pack values_f32 not 16-byte aligned", what);
+    MLB_REQUIRE(p.order_map && p.order_radius >= 0 && p.order_radius <= 64, "mlb_nearfield_assemble: %s pack has no order map", what);
     MLB_REQUIRE(p.n_ux >= 2 && p.n_uy >= 2 && p.n_g >= 2 && p.n_orders >= 0,
                 "mlb_nearfield_assemble: %s pack needs >= 2 nodes per axis (%d,%d,%d)", what, p.n_ux, p.n_uy, p.n_g);
     MLB_REQUIRE(mlb::aligned16(p.values), "mlb_nearfield_assemble: %s pack values not 16-byte aligned", what);

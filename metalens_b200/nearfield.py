@@ -27,8 +27,9 @@ STATS_PER_ORDER = 8
 
 class _PackC(C.Structure):
     _fields_ = [("axes", C.c_void_p), ("values", C.c_void_p), ("values_f32", C.c_void_p), ("orders", C.c_void_p),
+                ("order_map", C.c_void_p),
                 ("n_ux", C.c_int), ("n_uy", C.c_int), ("n_g", C.c_int), ("n_orders", C.c_int),
-                ("bounds", C.c_double * 6), ("stats_slot", C.c_int), ("_pad", C.c_int)]
+                ("bounds", C.c_double * 6), ("stats_slot", C.c_int), ("order_radius", C.c_int)]
 
 
 class _LensC(C.Structure):
@@ -135,7 +136,7 @@ class NearfieldPlan:
             flat = p.values.reshape(-1)
             self._pack_dev.append((up(p.axes, np.float64), up(flat.view(np.float64), np.float64),
                                    up(flat.astype(np.complex64).view(np.float32), np.float32),
-                                   up(p.order_array, np.int32)))
+                                   up(p.order_array, np.int32), up(p.order_map, np.int32)))
         self.n_stats = slot
 
         # centre cells -> uniform bin grid (replaces the reference's cKDTree, nearfield.py:363)
@@ -168,7 +169,8 @@ class NearfieldPlan:
     # ------------------------------------------------------------------
     def _pack_struct(self, pack, dev_arrays):
         s = _PackC()
-        s.axes, s.values, s.values_f32, s.orders = (t.data_ptr() for t in dev_arrays)
+        s.axes, s.values, s.values_f32, s.orders, s.order_map = (t.data_ptr() for t in dev_arrays)
+        s.order_radius = pack.order_radius
         s.n_ux, s.n_uy, s.n_g = pack.n
         s.n_orders = len(pack.orders)
         for k in range(6):

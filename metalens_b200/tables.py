@@ -105,3 +105,9 @@ class TablePack:
         self.bounds = tuple(float(b) for b in owner.interpolator_bounds)
         self.axes = np.concatenate(grid)
         self.order_array = np.asarray(self.orders, dtype=np.int32).reshape(-1, 2)
+        # dense (ox,oy) -> order index map so the kernel can visit just the orders that may propagate
+        self.order_radius = int(np.abs(self.order_array).max()) if len(self.orders) else 0
+        w = 2 * self.order_radius + 1
+        self.order_map = np.full(w * w, -1, dtype=np.int32)
+        for k, (ox, oy) in enumerate(self.orders):
+            self.order_map[(ox + self.order_radius) * w + (oy + self.order_radius)] = k
