@@ -147,7 +147,8 @@ int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, i
  * evanescent bins; theta/phi components with the 1e-9 regulariser; Cartesian
  * components at the exact ux==uy==0 bin; P = k^2/(32 pi^2 Z) (...)/(uz+1e-5) * 2.
  * `amp_scale` multiplies every Fhat before use (dx*dy, and 1/len factors).
- * P is written as float (p_is_double=0) or double (1).  If `block_sums` is not
+ * P is written as float (p_is_double=0) or double (1); adding 2 to p_is_double ACCUMULATES into P instead
+ * (incoherent sum over sources / polarisations, nearfield.py:69-73).  If `block_sums` is not
  * NULL, each block writes the sum of its finite P values to block_sums[blockIdx]
  * (mlb_ff_epilogue_blocks() entries) for a deterministic total_P.
  */

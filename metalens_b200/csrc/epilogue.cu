@@ -13,7 +13,7 @@ struct EpiArgs {
     void *P;
     double *block_sums;
     double amp_scale, pref, Z;
-    int ldf, ldp, Kx, Ky, p_is_double;
+    int ldf, ldp, Kx, Ky, p_is_double, accumulate;
 };
 
 struct cd { double re, im; };
@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
             const float Zf = (float)a.Z;
             const float mag = fabs2(fadd(lph, fmul(nth, Zf))) + fabs2(fsub(lth, fmul(nph, Zf)));
             p = a.pref * s_ * s_ * (double)mag / ((double)uzf + 1e-5) * 2.0;
-            const float pf = (float)p;
-            reinterpret_cast<float *>(a.P)[(size_t)i * a.ldp + j] = pf;
+            float pf = (float)p;
+            float *dst = reinterpret_cast<float *>(a.P) + (size_t)i * a.ldp + j;
+            if (a.accumulate) pf += *dst;                   // incoherent sum over sources
+            *dst = pf;
             finite = isfinite(pf);
         } else {
         const double uz = (uz2 < 0.0) ? CUDART_NAN : sqrt(uz2);
@@ -101,8 +103,13 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
         const cd t2 = csub(Lth, cmul(Nph, a.Z));
         p = a.pref * (cabs2(t1) + cabs2(t2)) / (uz + 1e-5) * 2.0;         // :184-189
         const size_t po = (size_t)i * a.ldp + j;
-        if (a.p_is_double) reinterpret_cast<double *>(a.P)[po] = p;
-        else reinterpret_cast<float *>(a.P)[po] = (float)p;
+        if (a.p_is_double) {
+            double *dst = reinterpret_cast<double *>(a.P) + po;
+            *dst = a.accumulate ? *dst + p : p;
+        } else {
+            float *dst = reinterpret_cast<float *>(a.P) + po;
+            *dst = a.accumulate ? *dst + (float)p : (float)p;
+        }
         finite = isfinite(p);
         }
     }
@@ -200,7 +207,8 @@ extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const doub
     const double pi = 3.14159265358979323846;
     const double k = 2 * pi * n_glass / wavelength;
     a.pref = k * k / (32 * pi * pi * a.Z);                                  // :184
-    a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double;
+    a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double & 1; a.accumulate = (p_is_double >> 1) & 1;
+    p_is_double &= 1;
     if (p_is_double) mlb::ff_epilogue_kernel<false><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
     else mlb::ff_epilogue_kernel<true><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_ff_epilogue");

@@ -374,15 +374,16 @@ class FarfieldPlan:
             fn()
         return self.Fhat
 
-    def power(self, Fhat=None, amp_scale=None):
-        """Epilogue: aperture sums -> P (device), total_P (device scalar, float64)."""
+    def power(self, Fhat=None, amp_scale=None, accumulate=False):
+        """Epilogue: aperture sums -> P (device), total_P (device scalar, float64).  With
+        accumulate=True this run's power is ADDED to P (incoherent sum over sources)."""
         Fhat = self.Fhat if Fhat is None else Fhat
         amp = self.dxp * self.dyp if amp_scale is None else amp_scale
         pf, _k = _lib.ptr_array(Fhat)
         rc = self.lib.mlb_ff_epilogue(pf, Fhat[0].shape[1], self.d_ux.data_ptr(), self.d_uy.data_ptr(),
                                       self.Kx, self.Ky, float(amp), self.wavelength, self.n_glass, Z0,
                                       self.P.data_ptr(), self.P.shape[1],
-                                      1 if self.p_dtype == torch.float64 else 0,
+                                      (1 if self.p_dtype == torch.float64 else 0) + (2 if accumulate else 0),
                                       self.block_sums.data_ptr(), _stream_ptr())
         _lib.check(rc, "mlb_ff_epilogue")
         rc = self.lib.mlb_sum_f64(self.block_sums.data_ptr(), self.nblocks, self.dux * self.duy,
@@ -390,10 +391,20 @@ class FarfieldPlan:
         _lib.check(rc, "mlb_sum_f64")
         return self.P, self.total
 
-    def run(self, fields):
-        """Device-resident fields (4 CUDA complex64 (Mx,My) tensors) -> (P, total_P) on device."""
+    def run(self, fields, accumulate=False):
+        """Device-resident fields (4 CUDA complex64 (Mx,My) tensors) -> (P, total_P) on device.
+        accumulate=True adds this item's power to P (total_P is that of this item alone)."""
         self.aperture_sums(fields)
-        return self.power()
+        return self.power(accumulate=accumulate)
+
+    def run_incoherent(self, field_sets):
+        """Incoherent sum over several sources / polarisations (the x-, y-, z-dipole recipe of
+        nearfield.py:69-73): P = sum_k P_k, total_P = sum_k total_k, everything on the device."""
+        total = torch.zeros(1, dtype=torch.float64, device=self.device)
+        for k, fields in enumerate(field_sets):
+            _, t = self.run(fields, accumulate=(k > 0))
+            total += t
+        return self.P, total
 
     def amplitudes(self):
         """Complex aperture sums of the last run as a (4, Kx, Ky) device tensor."""

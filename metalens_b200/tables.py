@@ -111,3 +111,82 @@ class TablePack:
         self.order_map = np.full(w * w, -1, dtype=np.int32)
         for k, (ox, oy) in enumerate(self.orders):
             self.order_map[(ox + self.order_radius) * w + (oy + self.order_radius)] = k
+
+
+# ---------------------------------------------------------------------------------------------
+# Packed on-disk library format.  The reference persists a characterised collection as a
+# multi-megabyte Python repr() and rebuilds the interpolators from the row dicts on every start
+# (README.md:29-34, grating.py:1186-1232).  Here the dense tables themselves are stored (one
+# compressed .npz, versioned) and come back as ready interpolators -- no row loop at load time.
+LIBRARY_FORMAT_VERSION = 1
+
+
+def save_library(path, owner):
+    """Write a GratingCollection or HexGridSet with built interpolators to `path` (.npz)."""
+    is_hgs = hasattr(owner, "sep")
+    keys = sorted(owner.interpolators, key=repr)
+    first = owner.interpolators[keys[0]]
+    gl = owner.grating_list
+    arrays = dict(
+        format_version=np.int64(LIBRARY_FORMAT_VERSION),
+        kind=np.str_("hexgridset" if is_hgs else "gratingcollection"),
+        axis0=np.asarray(first.grid[0], float), axis1=np.asarray(first.grid[1], float),
+        axis2=np.asarray(first.grid[2], float),
+        key_wavelength=np.array([k[0] for k in keys], np.int64),
+        key_order=np.array([k[1] for k in keys], np.int64),
+        key_pol=np.array([k[2] for k in keys]), key_amp=np.array([k[3] for k in keys]),
+        values=np.stack([np.asarray(owner.interpolators[k].values, np.complex128) for k in keys]),
+        bounds=np.asarray(owner.interpolator_bounds, float),
+        orders=np.asarray(list(orders_of(gl)), np.int64).reshape(-1, 2),
+        g_grating_period=np.array([g.grating_period for g in gl], float),
+        g_lateral_period=np.array([g.lateral_period for g in gl], float),
+        g_cyl_height=np.array([g.cyl_height for g in gl], float),
+        g_n_glass=np.array([g.n_glass for g in gl], float), g_n_tio2=np.array([g.n_tio2 for g in gl], float))
+    if is_hgs:
+        arrays.update(sep=np.float64(owner.sep), cyl_height=np.float64(owner.cyl_height),
+                      n_glass=np.float64(owner.n_glass), n_tio2=np.float64(owner.n_tio2),
+                      x_amp_list=np.asarray(owner.x_amp_list, np.complex128))
+    else:
+        arrays.update(target_wavelength=np.float64(owner.target_wavelength),
+                      lateral_period=np.float64(owner.lateral_period), lens_type=np.str_(owner.lens_type))
+    np.savez_compressed(path, **arrays)
+
+
+def load_library(path):
+    """Inverse of save_library: returns a GratingCollection / HexGridSet whose `.interpolators` and
+    `.interpolator_bounds` are ready.  `Grating.data` holds only the order list build_nearfield needs
+    (one stub row per order); the characterisation rows themselves are not stored."""
+    from . import grating as G
+    from . import lens_center as LC
+    z = np.load(path, allow_pickle=False)
+    if int(z["format_version"]) != LIBRARY_FORMAT_VERSION:
+        raise ValueError("unsupported library format version %d" % int(z["format_version"]))
+    gratings = []
+    for gp, lp, ch, ng, nt in zip(z["g_grating_period"], z["g_lateral_period"], z["g_cyl_height"], z["g_n_glass"],
+                                  z["g_n_tio2"]):
+        def num(v):
+            return int(v) if float(v) == int(v) else float(v)
+        g = G.Grating(lateral_period=float(lp), cyl_height=float(ch), grating_period=float(gp), n_glass=num(ng),
+                      n_tio2=num(nt))
+        g.data = []
+        gratings.append(g)
+    gratings[0].data = [{"ox": int(ox), "oy": int(oy)} for ox, oy in z["orders"]]
+    if str(z["kind"]) == "hexgridset":
+        owner = LC.HexGridSet(sep=float(z["sep"]), cyl_height=float(z["cyl_height"]), n_glass=num(z["n_glass"]),
+                              n_tio2=num(z["n_tio2"]), grating_list=gratings, x_amp_list=z["x_amp_list"])
+    else:
+        owner = G.GratingCollection.__new__(G.GratingCollection)
+        owner.target_wavelength = float(z["target_wavelength"])
+        owner.lateral_period = float(z["lateral_period"])
+        owner.target_kvac = 2 * np.pi / owner.target_wavelength
+        owner.lens_type = str(z["lens_type"])
+        owner.grating_list = gratings
+    grid = (z["axis0"], z["axis1"], z["axis2"])
+    owner.interpolators = {}
+    for i in range(z["values"].shape[0]):
+        key = (int(z["key_wavelength"][i]), (int(z["key_order"][i][0]), int(z["key_order"][i][1])),
+               str(z["key_pol"][i]), str(z["key_amp"][i]))
+        owner.interpolators[key] = AmplitudeTable(grid, z["values"][i])
+    b = z["bounds"]
+    owner.interpolator_bounds = tuple(float(v) for v in b)
+    return owner

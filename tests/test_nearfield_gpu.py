@@ -182,3 +182,31 @@ def test_lens_to_far_field_pipeline_on_device(golden_dir):
     assert abs(p_in.item() - ref_fields[6]) <= 1e-11 * abs(ref_fields[6])
     # the lens transmits most of the incident power into propagating far-field bins
     assert 0.05 < total.item() / p_in.item() < 1.5
+
+
+def test_incoherent_xyz_dipoles_on_device(golden_dir):
+    """isotropic source = incoherent sum of x-, y- and z-polarised dipoles (nearfield.py:69-73):
+    the accumulated device far field equals the sum of the three separate ones."""
+    from metalens_b200.farfield import FarfieldPlan
+    from metalens_b200.nearfield import NearfieldPlan
+    g = np.load(os.path.join(golden_dir, "nearfield_small_x_onaxis.npz"))
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    periph = periphery_from(g, collections)
+    f = float(-g["source"][2])
+    x = np.linspace(-12e-6, 12e-6, 128)
+    nf = NearfieldPlan(580e-9, periph, g["center"], hgs)
+    ff = FarfieldPlan((128, 128), x[1] - x[0], x[1] - x[0], 580e-9, nf.n_glass, stride=1)
+    sets, singles, totals = [], [], 0.0
+    for pol in "xyz":
+        fields, _ = nf.run(0.0, 0.0, -f, pol, x, x)
+        fs = [fields[i][:, :128].clone() for i in range(4)]
+        sets.append(fs)
+        P, t = ff.run(fs)
+        singles.append(P.clone())
+        totals += t.item()
+    P_sum, total = ff.run_incoherent(sets)
+    ref = singles[0] + singles[1] + singles[2]
+    fin = torch.isfinite(ref)
+    assert bool((torch.isnan(P_sum) == torch.isnan(ref)).all())
+    assert ((P_sum - ref).abs()[fin].max() / ref[fin].max()).item() < 1e-6
+    assert abs(total.item() - totals) <= 1e-12 * abs(totals)

@@ -112,3 +112,31 @@ def test_table_builders_shapes():
     assert grating.n_glass(580) == 1.459
     g2 = gc.grating_list[0].copy()
     assert g2.grating_period == pytest.approx(gc.grating_list[0].grating_period, rel=1e-12) and len(g2.data) == len(gc.grating_list[0].data)
+
+
+def test_packed_library_round_trip(tmp_path, golden_dir):
+    """collections saved in the packed .npz format come back with identical tables, and the
+    oracle near field computed from the re-loaded library equals the reference fixture."""
+    from metalens_b200 import tables
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    loaded = []
+    for i, (band, gc) in enumerate(collections):
+        path = str(tmp_path / ("gc%d.npz" % i))
+        tables.save_library(path, gc)
+        back = tables.load_library(path)
+        assert sorted(back.interpolators, key=repr) == sorted(gc.interpolators, key=repr)
+        for k in gc.interpolators:
+            assert np.array_equal(back.interpolators[k].values, gc.interpolators[k].values)
+            assert all(np.array_equal(a, b) for a, b in zip(back.interpolators[k].grid, gc.interpolators[k].grid))
+        assert back.interpolator_bounds == tuple(gc.interpolator_bounds)
+        assert back.lateral_period == gc.lateral_period and back.lens_type == "round"
+        loaded.append([band, back])
+    path = str(tmp_path / "hgs.npz")
+    tables.save_library(path, hgs)
+    hgs2 = tables.load_library(path)
+    assert np.array_equal(hgs2.x_amp_list, hgs.x_amp_list) and hgs2.interpolator_bounds == tuple(hgs.interpolator_bounds)
+    g = np.load(os.path.join(golden_dir, "nearfield_small_y_offaxis.npz"))
+    sx, sy, sz = g["source"]
+    res = no.build_nearfield(sx, sy, sz, "y", 580e-9, periphery_from(g, loaded), g["center"], hgs2)
+    scale = max(np.abs(g["Ex"]).max(), np.abs(g["Ey"]).max())
+    assert np.abs(res[0] - g["Ex"]).max() / scale < 1e-11 and np.abs(res[1] - g["Ey"]).max() / scale < 1e-11
