@@ -105,7 +105,8 @@ int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, co
                  const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
                  float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream);
 
-/* ---- A1 (FFT formulation): shared-memory FFT passes, power-of-two lengths ---- */
+/* ---- A1 (FFT formulation): shared-memory FFT passes.  Lengths 2^a 3^b 5^c <= 8192 (the
+ * sizes good_fft_number() produces); powers of two take the tuned kernels, others mixed-radix ones. ---- */
 /* Twiddle tables for the FFT passes, 2*N entries: out[t] = exp(-2 pi i t / N) for t < N, followed by the
  * same values re-ordered per Stockham stage (conflict-free shared-memory reads); float64 phases rounded
  * once to fp32 */

@@ -586,6 +586,157 @@ __global__ void __launch_bounds__(256) fft_cols_sub_kernel(const FftSubArgs a) {
     }
 }
 
+// ---- mixed-radix passes: any length N = 2^a 3^b 5^c <= 8192 ---------------------------------------------
+// The reference sizes its aperture with good_fft_number() (nearfield.py:30-36: only factors 2, 3, 5), so
+// the typical grid is NOT a power of two (e.g. 675 = 3^3 5^2).  These kernels run the same Stockham
+// autosort scheme with radix-4/2/3/5 stages chosen at run time; index math is integer division instead
+// of shifts, which is why the power-of-two kernels above stay separate.
+struct MixArgs {
+    const float2 *in[4];
+    float2 *out[4];
+    const float2 *tw;                 // plain table W_N^t, t < N
+    int ld_in, ld_out, N, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2;
+    int nstage;
+    int radix[16];
+};
+
+template <int R>
+__device__ __forceinline__ void dft_small(float2 (&v)[R]) {
+    if (R == 2) {
+        const float2 a = caddf(v[0], v[1]), b = csubf(v[0], v[1]);
+        v[0] = a; v[1] = b;
+    } else if (R == 4) {
+        bfly4(v[0], v[1], v[2], v[3]);
+    } else if (R == 3) {
+        const float s3 = 0.86602540378443864676f;                      // sin(2 pi / 3)
+        const float2 t1 = caddf(v[1], v[2]), t2 = csubf(v[1], v[2]);
+        const float2 m = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+        const float2 r = make_float2(s3 * t2.y, -s3 * t2.x);          // -i * s3 * t2
+        v[0] = caddf(v[0], t1);
+        v[1] = caddf(m, r);
+        v[2] = csubf(m, r);
+    } else {                                                           // R == 5
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
+        const float2 a1 = caddf(v[1], v[4]), b1 = csubf(v[1], v[4]);
+        const float2 a2 = caddf(v[2], v[3]), b2 = csubf(v[2], v[3]);
+        const float2 m1 = make_float2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+        const float2 m2 = make_float2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+        // -i * (s1 b1 + s2 b2)  and  -i * (s2 b1 - s1 b2)
+        const float2 n1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));
+        const float2 n2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));
+        v[0] = caddf(v[0], caddf(a1, a2));
+        v[1] = caddf(m1, n1);
+        v[4] = csubf(m1, n1);
+        v[2] = caddf(m2, n2);
+        v[3] = csubf(m2, n2);
+    }
+}
+
+// one Stockham stage, radix R, sub-length Ns, `lanes` transforms at lane*pitch
+template <int R>
+__device__ __forceinline__ void mixed_stage(const float2 *__restrict__ x, float2 *__restrict__ y, int N, int Ns, int lanes,
+                                            int pitch, const float2 *__restrict__ tw) {
+    const int per = N / R, total = per * lanes, tstep = N / (Ns * R);
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int lane = idx / per, j = idx - lane * per;
+        const int k = j % Ns;
+        const int base_out = (j - k) * R + k;
+        const float2 *xl = x + lane * pitch;
+        float2 *yl = y + lane * pitch;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = xl[j + r * per];
+            if (r > 0 && Ns > 1) v[r] = cmulf(v[r], __ldg(tw + r * k * tstep));
+        }
+        dft_small<R>(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) yl[base_out + r * Ns] = v[r];
+    }
+}
+
+__device__ __forceinline__ int mixed_fft(float2 *buf0, float2 *buf1, const MixArgs &a, int lanes, int pitch) {
+    int cur = 0, Ns = 1;
+    for (int s = 0; s < a.nstage; ++s) {
+        __syncthreads();
+        const float2 *x = cur ? buf1 : buf0;
+        float2 *y = cur ? buf0 : buf1;
+        switch (a.radix[s]) {
+            case 2: mixed_stage<2>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
+            case 3: mixed_stage<3>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
+            case 4: mixed_stage<4>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
+            default: mixed_stage<5>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
+        }
+        Ns *= a.radix[s];
+        cur ^= 1;
+    }
+    __syncthreads();
+    return cur;
+}
+
+// rows: `lanes` rows per CTA; loader folds s1 x s2 aliased copies and applies the input fftshift
+__global__ void __launch_bounds__(256) fft_rows_mixed_kernel(const MixArgs a) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int N = a.N, L = a.lanes;
+    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N;
+    const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
+    float2 *__restrict__ out = pick4(a.out, blockIdx.y);
+    const int row0 = blockIdx.x * L, total = L * N;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int lane = idx / N, n = idx - lane * N;
+        const int r = row0 + lane;
+        float re = 0.f, im = 0.f;
+        if (r < a.other) {
+            int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
+            int cs = n - a.in_roll_c; if (cs < 0) cs += N;
+            for (int t1 = 0; t1 < a.s1; ++t1) {
+                const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in + cs;
+                for (int t2 = 0; t2 < a.s2; ++t2) {
+                    const float2 v = __ldcs(row + (size_t)t2 * N);
+                    re += v.x; im += v.y;
+                }
+            }
+        }
+        buf0[idx] = make_float2(re, im);
+    }
+    const int cur = mixed_fft(buf0, buf1, a, L, N);
+    const float2 *res = cur ? buf1 : buf0;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int lane = idx / N, n = idx - lane * N;
+        const int r = row0 + lane;
+        if (r < a.other) {
+            int q = n - a.out_roll; if (q < 0) q += N;
+            out[(size_t)r * a.ld_out + n] = res[lane * N + q];
+        }
+    }
+}
+
+// columns: `lanes` adjacent columns per CTA, transposed into [lane][n] shared-memory rows
+__global__ void __launch_bounds__(256) fft_cols_mixed_kernel(const MixArgs a) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int N = a.N, L = a.lanes, P = N + 1;
+    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * P;
+    const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
+    float2 *__restrict__ out = pick4(a.out, blockIdx.y);
+    const int c0 = blockIdx.x * L, total = L * N;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int n = idx / L, lane = idx - n * L;
+        const int c = c0 + lane;
+        buf0[lane * P + n] = (c < a.other) ? in[(size_t)n * a.ld_in + c] : make_float2(0.f, 0.f);
+    }
+    const int cur = mixed_fft(buf0, buf1, a, L, P);
+    const float2 *res = cur ? buf1 : buf0;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int n = idx / L, lane = idx - n * L;
+        const int c = c0 + lane;
+        if (c < a.other) {
+            int q = n - a.out_roll; if (q < 0) q += N;
+            out[(size_t)n * a.ld_out + c] = res[lane * P + q];
+        }
+    }
+}
+
 __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
@@ -618,6 +769,22 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
 static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+// radix sequence (4s first, then 2, 3s, 5s) of a 5-smooth length; returns the stage count or 0
+static int factor_235(int n, int *radix) {
+    int ns = 0;
+    while (n % 4 == 0) { radix[ns++] = 4; n /= 4; }
+    while (n % 2 == 0) { radix[ns++] = 2; n /= 2; }
+    while (n % 3 == 0) { radix[ns++] = 3; n /= 3; }
+    while (n % 5 == 0) { radix[ns++] = 5; n /= 5; }
+    return (n == 1 && ns <= 16) ? ns : 0;
+}
+template <typename A>
+static int fill_mixed(MixArgs &m, const A &a, int N) {
+    for (int b = 0; b < 4; ++b) { m.in[b] = a.in[b]; m.out[b] = a.out[b]; }
+    m.N = N;
+    m.nstage = factor_235(N, m.radix);
+    return m.nstage;
+}
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 constexpr int FFT_MAX_N = 8192;                     // 2 x 8192 x 8 B = 128 KB of shared memory
 
@@ -666,8 +833,9 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
                             int transpose_out, int batch, void *stream) {
     mlb::FftArgs a;
     if (int rc = mlb::fill_args(a, h_in, h_out, batch, "mlb_fft_rows")) return rc;
-    MLB_REQUIRE(mlb::is_pow2(N) && N >= 2 && N <= mlb::FFT_MAX_N, "mlb_fft_rows: length %d must be a power of two <= %d",
-                N, mlb::FFT_MAX_N);
+    int radix_probe[16];
+    MLB_REQUIRE(N >= 2 && N <= mlb::FFT_MAX_N && mlb::factor_235(N, radix_probe) > 0,
+                "mlb_fft_rows: length %d must be of the form 2^a 3^b 5^c and <= %d", N, mlb::FFT_MAX_N);
     MLB_REQUIRE(s1 >= 1 && s2 >= 1, "mlb_fft_rows: fold factors must be >= 1");
     MLB_REQUIRE(tw && n_rows > 0 && ld_in >= N * s2 && ld_out >= (transpose_out ? n_rows : N), "mlb_fft_rows: bad sizes");
     a.transpose_out = transpose_out ? 1 : 0;
@@ -677,6 +845,25 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
         MLB_REQUIRE((in_roll_r == 0 && s1 == 1 && s2 == 1) || a.in[b] != a.out[b],
                     "mlb_fft_rows: in-place needs in_roll_r == 0 and no fold");
     a.tw = reinterpret_cast<const float2 *>(tw);
+    if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
+        MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs a power-of-two length");
+        mlb::MixArgs m;
+        mlb::fill_mixed(m, a, N);
+        m.tw = a.tw; m.ld_in = ld_in; m.ld_out = ld_out; m.other = n_rows;
+        m.in_roll_r = in_roll_r; m.in_roll_c = in_roll_c; m.out_roll = out_roll; m.s1 = s1; m.s2 = s2;
+        int lanes = 1;
+        while (lanes * 2 * N <= 1024 && lanes * 2 <= n_rows) lanes *= 2;
+        m.lanes = lanes;
+        const size_t smem = 2 * (size_t)lanes * N * sizeof(float2);
+        static bool set_ = false;
+        if (!set_) {
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
+            set_ = true;
+        }
+        dim3 grid((n_rows + lanes - 1) / lanes, batch);
+        mlb::fft_rows_mixed_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(m);
+        return mlb::check_launch("mlb_fft_rows(mixed radix)");
+    }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_rows;
     a.in_roll_r = in_roll_r; a.in_roll_c = in_roll_c; a.out_roll = out_roll; a.s1 = s1; a.s2 = s2;
     int lanes = 1;
@@ -761,11 +948,30 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
                             int n_cols, const mlb_c64 *tw, int out_roll, int batch, void *stream) {
     mlb::FftArgs a;
     if (int rc = mlb::fill_args(a, h_in, h_out, batch, "mlb_fft_cols")) return rc;
-    MLB_REQUIRE(mlb::is_pow2(N) && N >= 2 && N <= mlb::FFT_MAX_N, "mlb_fft_cols: length %d must be a power of two <= %d",
-                N, mlb::FFT_MAX_N);
+    int radix_probe[16];
+    MLB_REQUIRE(N >= 2 && N <= mlb::FFT_MAX_N && mlb::factor_235(N, radix_probe) > 0,
+                "mlb_fft_cols: length %d must be of the form 2^a 3^b 5^c and <= %d", N, mlb::FFT_MAX_N);
     MLB_REQUIRE(tw && n_cols > 0 && ld_in >= n_cols && ld_out >= n_cols, "mlb_fft_cols: bad sizes");
     MLB_REQUIRE(out_roll >= 0 && out_roll < N, "mlb_fft_cols: roll out of range");
     a.tw = reinterpret_cast<const float2 *>(tw);
+    if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
+        mlb::MixArgs m;
+        mlb::fill_mixed(m, a, N);
+        m.tw = a.tw; m.ld_in = ld_in; m.ld_out = ld_out; m.other = n_cols;
+        m.in_roll_r = m.in_roll_c = 0; m.out_roll = out_roll; m.s1 = m.s2 = 1;
+        int lanes = 1;
+        while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 1) * sizeof(float2) <= 96 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
+        m.lanes = lanes;
+        const size_t smem = 2 * (size_t)lanes * (N + 1) * sizeof(float2);
+        static bool set_ = false;
+        if (!set_) {
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (mlb::FFT_MAX_N + 1) * 8));
+            set_ = true;
+        }
+        dim3 grid((n_cols + lanes - 1) / lanes, batch);
+        mlb::fft_cols_mixed_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(m);
+        return mlb::check_launch("mlb_fft_cols(mixed radix)");
+    }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1;
     if (a.lgN >= 12) {

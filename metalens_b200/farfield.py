@@ -78,7 +78,9 @@ class FarfieldPlan:
                  sx | Mx//2 and sy | My//2
         fft   -- shared-memory row/column FFT passes, the row pass folding the aperture while it
                  loads (stride > 1): the reference's own algorithm, every kernel memory-bound,
-                 the aperture read from HBM exactly once; needs power-of-two folded sizes <= 8192
+                 the aperture read from HBM exactly once; folded sizes of the form 2^a 3^b 5^c
+                 (what good_fft_number() yields) up to 8192 -- powers of two take the tuned
+                 kernels (TMA-fed row pass), other sizes the mixed-radix ones
         tc    -- the dense separable reduction on the tensor cores: tcgen05 UMMA (TF32 operands split
                  hi/lo, three products per term -> fp32-class accuracy), TMEM accumulators, TMA-fed
         auto  -- fft if eligible, else fold, else dense
@@ -123,13 +125,18 @@ class FarfieldPlan:
         can_fold = (self.fft_bin_grid and self.Mx % self.sx == 0 and self.My % self.sy == 0
                     and (self.Mx // 2) % self.sx == 0 and (self.My // 2) % self.sy == 0
                     and (self.sx > 1 or self.sy > 1))
-        def pow2(n):
-            return n >= 2 and (n & (n - 1)) == 0
+        def smooth(n):                 # 2^a 3^b 5^c: what good_fft_number() produces (nearfield.py:30-36)
+            if n < 2:
+                return False
+            for f in (2, 3, 5):
+                while n % f == 0:
+                    n //= f
+            return n == 1
         can_fft = False
         if self.fft_bin_grid and self.Mx % self.sx == 0 and self.My % self.sy == 0:
             k1, k2 = self.Mx // self.sx, self.My // self.sy
             nmax = self.lib.mlb_fft_max_length()
-            can_fft = (pow2(k1) and pow2(k2) and k1 <= nmax and k2 <= nmax
+            can_fft = (smooth(k1) and smooth(k2) and k1 <= nmax and k2 <= nmax
                        and (can_fold or (self.sx == 1 and self.sy == 1)))
         if self.rows is not None and self.rows != (0, self.Kx_full):
             if method == "fft":
@@ -140,7 +147,7 @@ class FarfieldPlan:
         if method == "fold" and not can_fold:
             raise ValueError("fold needs an FFT-bin-stride grid with stride dividing M and M//2")
         if method == "fft" and not can_fft:
-            raise ValueError("fft needs an FFT-bin(-stride) grid whose folded sizes are powers of two <= %d"
+            raise ValueError("fft needs an FFT-bin(-stride) grid whose folded sizes are 2^a 3^b 5^c and <= %d"
                              % self.lib.mlb_fft_max_length())
         assert method in ("dense", "fold", "fft", "tc")
         self.method = method

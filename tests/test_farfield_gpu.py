@@ -74,10 +74,7 @@ def test_strided_bins(name, stride, method, golden_dir):
     g = golden(golden_dir, name)
     Ex, Ey, Hx, Hy, x, y = CASES[name]()
     sx, sy = (stride, stride) if np.isscalar(stride) else stride
-    if method == "fft" and name.startswith("rand_48x40"):       # folded size 12 x 20 is not a power of two
-        with pytest.raises(ValueError):
-            farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=stride, method=method)
-        return
+    # (folded size 12 x 20 of the 48 x 40 case is not a power of two: mixed-radix passes)
     P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, WL, NG, stride=stride, method=method,
                                                       p_dtype=torch.float32)
     ref = g["P"][::sx, ::sy]
@@ -135,6 +132,8 @@ def test_row_slabs_equal_full_far_field(golden_dir):
             bool(((torch.cat(parts, dim=0) == P_full) | (torch.isnan(P_full))).all())
     with pytest.raises(ValueError):
         FarfieldPlan((256, 256), d, d, WL, NG, stride=4, method="fft", rows=(0, 16))
+    with pytest.raises(ValueError):
+        FarfieldPlan((154, 256), d, d, WL, NG, stride=1, method="fft")          # 154 = 2*7*11 is not 5-smooth
 
 
 def test_cgemm_tn_ragged_shapes():
@@ -243,9 +242,37 @@ def test_fft_passes_match_numpy():
         for v, d in zip(a, dcol):
             ref = np.roll(np.fft.fft(v.astype(complex).T, axis=0), ro, axis=0)
             assert field_error(d[:, :other].cpu().numpy(), ref) < 3e-6, ("cols", N)
-    bad = torch.zeros(4, 12, dtype=torch.complex64).cuda()
+    bad = torch.zeros(4, 14, dtype=torch.complex64).cuda()
     pb, k4 = _lib.ptr_array([bad])
-    assert lib.mlb_fft_rows(pb, 12, pb, 12, 4, 12, 1, 1, bad.data_ptr(), 0, 0, 0, 0, 1, None) != 0   # not a power of two
+    assert lib.mlb_fft_rows(pb, 14, pb, 14, 4, 14, 1, 1, bad.data_ptr(), 0, 0, 0, 0, 1, None) != 0   # 14 = 2*7: not 5-smooth
+    # mixed radix (good_fft_number sizes): rows with fold + rolls, and columns
+    for N, other, s1, s2 in ((6, 5, 1, 1), (12, 7, 2, 3), (45, 9, 1, 2), (100, 4, 3, 1), (675, 3, 1, 1), (720, 5, 2, 2),
+                             (1000, 2, 1, 1), (6000, 2, 1, 1)):
+        big = (rng.standard_normal((other * s1, N * s2)) + 1j * rng.standard_normal((other * s1, N * s2))).astype(np.complex64)
+        ldi = N * s2 + 3
+        dbig = [torch.zeros(other * s1, ldi, dtype=torch.complex64).cuda()]
+        dbig[0][:, :N * s2].copy_(torch.from_numpy(big))
+        tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
+        _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
+        rr, rc, ro = other // 2, N // 2, (N // 2 + 1) % N
+        dres = [torch.zeros(other, N + 1, dtype=torch.complex64).cuda()]
+        pi_, k1 = _lib.ptr_array(dbig)
+        po, k2 = _lib.ptr_array(dres)
+        _lib.check(lib.mlb_fft_rows(pi_, ldi, po, N + 1, other, N, s1, s2, tw.data_ptr(), rr, rc, ro, 0, 1, None), "mixed rows")
+        folded = big.astype(complex).reshape(s1, other, s2, N).sum(axis=(0, 2))
+        ref = np.roll(np.fft.fft(np.roll(folded, (rr, rc), axis=(0, 1)), axis=1), ro, axis=1)
+        torch.cuda.synchronize()
+        assert field_error(dres[0][:, :N].cpu().numpy(), ref) < 3e-6, ("mixed rows", N)
+        ldc = other + 3
+        dcol = [torch.zeros(N, ldc, dtype=torch.complex64).cuda()]
+        dcol[0][:, :other].copy_(torch.from_numpy(folded.T.astype(np.complex64).copy()))
+        dco = [torch.zeros(N, ldc, dtype=torch.complex64).cuda()]
+        pc, k3 = _lib.ptr_array(dcol)
+        pco, k5 = _lib.ptr_array(dco)
+        _lib.check(lib.mlb_fft_cols(pc, ldc, pco, ldc, N, other, tw.data_ptr(), ro, 1, None), "mixed cols")
+        torch.cuda.synchronize()
+        refc = np.roll(np.fft.fft(folded.T.astype(np.complex64).astype(complex), axis=0), ro, axis=0)
+        assert field_error(dco[0][:, :other].cpu().numpy(), refc) < 3e-6, ("mixed cols", N)
     # fused fold: [n_rows*s1][N*s2] input, summed over the aliased copies while loading
     n_rows, N, s1, s2 = 6, 64, 3, 4
     big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
