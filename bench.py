@@ -450,6 +450,18 @@ def ours(args):
                           "value": len(p2) * K2 * K2 * args.steps / t2, "ms_per_step": t2 / args.steps * 1e3,
                           "note": "268 MB of inputs per step: larger than L2"}}
         del f2, p2
+        # the reference's own usage: a good_fft_number() grid (3375 = 3^3 5^3), ALL FFT bins
+        M3 = 3375
+        wl3, ng3 = 580e-9, apertures.N_GLASS[580]
+        Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M3, 2100, wl3, ng3)
+        f3 = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+        p3 = FarfieldPlan((M3, M3), float(x[1] - x[0]), float(x[1] - x[0]), wl3, ng3, stride=1, method=args.method)
+        t3, _, _, _ = timed(lambda: p3.run(f3), 5, 2)
+        other["ref_default_grid"] = {"workload": "3375x3375 aperture (good_fft_number size) -> all 3375x3375 FFT bins, 580 nm",
+                                     "method": p3.method, "value": M3 * M3 * 5 / t3, "ms_per_step": t3 / 5 * 1e3,
+                                     "note": "mixed-radix (3,5) shared-memory FFT passes"}
+        del f3, p3
+        torch.cuda.empty_cache()
 
     nf = None
     if rank == 0 and world == 1 and not args.no_nearfield:
