@@ -140,6 +140,28 @@ int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, i
 int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N, int n_cols,
                  const mlb_c64 *tw, int out_roll, int batch, void *stream);
 
+/*
+ * Fused column pass + radiated-power epilogue (float32 P): the column DFT of all four row-pass outputs
+ * in_f [N][ld_in] (f = Ex,Ey,Hx,Hy; same index convention as mlb_fft_cols) and, straight from registers,
+ * P[(q + out_roll) % N][c] of mlb_ff_epilogue (nearfield_farfield.py:135-189; ux has N entries in the
+ * OUTPUT row order, uy n_cols entries).  The 4 x N x n_cols aperture sums never go to memory unless h_Fhat
+ * (4 device pointers, pitch ldf) is given.  block_sums receives mlb_fft_cols_power_blocks(N, n_cols) partial
+ * sums of the finite P values (query it after any mlb_set_option call).  Powers of two 256..2048 only:
+ * mlb_fft_cols_power_blocks returns 0 for every other length and the caller uses mlb_fft_cols + mlb_ff_epilogue.
+ */
+int mlb_fft_cols_power_blocks(int N, int n_cols);
+int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw, int out_roll,
+                       const double *ux, const double *uy, double amp_scale, double wavelength, double n_glass,
+                       double Z0, float *P, int ldp, int accumulate, double *block_sums,
+                       mlb_c64 *const *h_Fhat, int ldf, void *stream);
+/* Named integer tuning options (defaults are the B200-tuned values):
+ *   rows_ctas_per_sm     resident CTAs per SM of the TMA-fed row pass, 0 = as many as fit (default)
+ *   rows_l2_evict_first  1 (default) = stream the aperture through L2 with an evict-first policy
+ *   cols_power_wide      1 = 4096-point column tiles / 1024 threads in the fused pass (default 0: 2048 / 512)
+ * mlb_get_option returns -1 for an unknown name. */
+int mlb_set_option(const char *name, int value);
+int mlb_get_option(const char *name);
+
 /* ---- A2/A3: radiated power ------------------------------------------------ */
 /*
  * Fhat (4 x Kx x Ky c64: Ex,Ey,Hx,Hy aperture sums) -> P (Kx x Ky) following

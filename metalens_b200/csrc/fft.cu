@@ -14,6 +14,10 @@
 //   * twiddles come from tables built with float64 phases, re-ordered per Stockham stage so that the
 //     shared-memory reads are conflict-free.
 // All sizes are powers of two, so index math is shifts and masks.
+#include <math_constants.h>
+
+#include <string>
+
 #include "common.cuh"
 
 namespace mlb {
@@ -94,7 +98,7 @@ struct FftArgs {
     const float2 *in[4];
     float2 *out[4];
     const float2 *tw;
-    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader, transpose_out;
+    int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader, transpose_out, evict_first;
 };
 
 // folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
@@ -126,7 +130,7 @@ __device__ __forceinline__ void load_folded(const FftArgs &a, const float2 *__re
 template <int LGN> struct FftThreads { static constexpr int value = (LGN >= 12) ? 1024 : 256; };
 
 // ---- compile-time-sized stages: all index math folds into constants, loops fully unrolled ----------
-template <int R, int LGN, int LGNS, int LANES, int PITCH>
+template <int R, int LGN, int LGNS, int LANES, int PITCH, int T = FftThreads<LGN>::value>
 __device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *__restrict__ y,
                                          const float2 *__restrict__ tw) {
     constexpr int lgR = (R == 4) ? 2 : 1;
@@ -136,7 +140,6 @@ __device__ __forceinline__ void stage_ct(const float2 *__restrict__ x, float2 *_
     // radix-2 stage at [Ns - 1 + k].  Consecutive threads read consecutive 24-byte triples instead of
     // one strided word of the length-N table: no shared-memory bank conflicts on the twiddle loads.
     constexpr int tbase = Ns - 1;
-    constexpr int T = FftThreads<LGN>::value;
     constexpr int iters = (total + T - 1) / T;
 #pragma unroll
     for (int it = 0; it < iters; ++it) {
@@ -177,15 +180,15 @@ __device__ __forceinline__ void fft_sync() {
     else __syncthreads();
 }
 
-template <int LGN, int LGNS, int LANES, int PITCH, int CUR, bool NAMED = false>
+template <int LGN, int LGNS, int LANES, int PITCH, int CUR, bool NAMED = false, int T = FftThreads<LGN>::value>
 __device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *tw) {
     fft_sync<NAMED>();
     if constexpr (LGNS + 2 <= LGN) {
-        stage_ct<4, LGN, LGNS, LANES, PITCH>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
-        return fft_ct<LGN, LGNS + 2, LANES, PITCH, CUR ^ 1, NAMED>(buf0, buf1, tw);
+        stage_ct<4, LGN, LGNS, LANES, PITCH, T>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
+        return fft_ct<LGN, LGNS + 2, LANES, PITCH, CUR ^ 1, NAMED, T>(buf0, buf1, tw);
     } else if constexpr (LGNS < LGN) {
-        stage_ct<2, LGN, LGNS, LANES, PITCH>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
-        return fft_ct<LGN, LGNS + 1, LANES, PITCH, CUR ^ 1, NAMED>(buf0, buf1, tw);
+        stage_ct<2, LGN, LGNS, LANES, PITCH, T>(CUR ? buf1 : buf0, CUR ? buf0 : buf1, tw);
+        return fft_ct<LGN, LGNS + 1, LANES, PITCH, CUR ^ 1, NAMED, T>(buf0, buf1, tw);
     } else {
         return CUR;
     }
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
         // ------------------------------------------------ producer warp (one lane issues)
         if (tid == TMA_CONSUMERS) {
             long long g = 0;
+            const uint64_t pol = l2_evict_first_policy();
             for (int w = blockIdx.x; w < work; w += gridDim.x) {
                 const int f = w / a.other, r = w - f * a.other;
                 int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
@@ -242,8 +246,9 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
                     if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
                     const int t1 = t / a.s2, t2 = t - t1 * a.s2;
                     mbar_expect_tx(&full[slot], Cfg::SLOT_BYTES);
-                    bulk_g2s(ring + (size_t)slot * N, src + (size_t)(rs + t1 * a.other) * a.ld_in + ((size_t)t2 << LGN),
-                             Cfg::SLOT_BYTES, &full[slot]);
+                    const float2 *seg = src + (size_t)(rs + t1 * a.other) * a.ld_in + ((size_t)t2 << LGN);
+                    if (a.evict_first) bulk_g2s_hint(ring + (size_t)slot * N, seg, Cfg::SLOT_BYTES, &full[slot], pol);
+                    else bulk_g2s(ring + (size_t)slot * N, seg, Cfg::SLOT_BYTES, &full[slot]);
                 }
             }
         }
@@ -496,6 +501,138 @@ __global__ void __launch_bounds__(FftThreads<LGN>::value) fft_cols_kernel(const 
                 const int q = (n - a.out_roll) & (N - 1);
                 out[(size_t)n * a.ld_out + c] = res[lane * P + q];
             }
+        }
+    }
+}
+
+// ---- fused column pass + radiated-power epilogue ---------------------------------------------------------
+// The last two kernels of an FFT-path item in one: a CTA transforms CL adjacent columns of ALL FOUR fields
+// (one field after the other through the same shared-memory ping-pong buffers) and keeps, per far-field point,
+// only the two complex projections the radiated power needs,
+//     t1 = L_phi + Z N_theta,   t2 = L_theta - Z N_phi          (nearfield_farfield.py:158-167, :184)
+// which are real-coefficient combinations of the four aperture sums:
+//     t1 = -px Fex - py Fey + Z cy Fhx - Z cx Fhy,   t2 = -cy Fex + cx Fey - Z px Fhx - Z py Fhy
+// with (px,py) = (ux,uy)/(sin(theta)+1e-9), (cx,cy) = (px,py) uz; the DC bin (:161-169) is (px,py,cx,cy) =
+// (1,0,1,0).  So the K x K x 4 aperture sums never go to memory (optional: fhat != NULL stores them), and
+// P = k^2/(32 pi^2 Z) (|t1|^2+|t2|^2)/(uz+1e-5) * 2 (:184-189) is written straight from registers.
+// Same arithmetic as ff_epilogue_kernel<true>: float64 evanescent mask / DC test, fp32 projections.
+struct ColsPowerArgs {
+    const float2 *in[4];
+    float2 *fhat[4];
+    const float2 *tw;
+    const double *ux, *uy;
+    float *P;
+    double *block_sums;
+    double scale;                  // pref * amp_scale^2 * 2
+    float Z;
+    int ld_in, ldf, ldp, n_cols, out_roll, accumulate, store_fhat;
+};
+
+template <int LGN, int CL, int T>
+__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1) fft_cols_power_kernel(const ColsPowerArgs a) {
+    constexpr int N = 1 << LGN, PITCH = N + 4, per = N >> 2, ltotal = per * CL, liters = ltotal / T;
+    constexpr int total = N * CL, EPT = total / T;
+    constexpr int lgCL = (CL == 16) ? 4 : (CL == 8) ? 3 : (CL == 4) ? 2 : (CL == 2) ? 1 : 0;
+    static_assert(total % T == 0 && ltotal % T == 0 && T % CL == 0, "tile must divide evenly over the threads");
+    extern __shared__ __align__(16) float2 fsm[];
+    float2 *buf0 = fsm, *buf1 = fsm + CL * PITCH, *stw = buf1 + CL * PITCH;
+    const int tid = threadIdx.x, c0 = blockIdx.x * CL;
+    for (int t = tid; t < N; t += T) stw[t] = a.tw[N + t];
+    // every element of this thread sits in the same column (T % CL == 0)
+    const int lane = tid & (CL - 1), c = c0 + lane;
+    const bool col_ok = c < a.n_cols;
+    const double uy = col_ok ? a.uy[c] : 0.0;
+    const double uy2 = __dmul_rn(uy, uy);
+    // per point only 1/(sin(theta)+1e-9) and uz stay in registers; (float)ux comes from a shared-memory table
+    float *uxf = reinterpret_cast<float *>(stw + N);
+    for (int t = tid; t < N; t += T) uxf[t] = (float)a.ux[t];
+    const float uyf = (float)uy;
+    float inv[EPT], uzf[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int n = (e * T + tid) >> lgCL;                       // far-field row (ux index)
+        const double ux = a.ux[n];
+        // uz^2 exactly as numpy evaluates (1 - ux**2 - uy**2): bit-identical evanescent mask (:153-155)
+        const double ux2 = __dmul_rn(ux, ux);
+        const double uz2 = __dsub_rn(__dsub_rn(1.0, ux2), uy2);
+        uzf[e] = (uz2 < 0.0) ? CUDART_NAN_F : sqrtf((float)uz2);
+        inv[e] = 1.0f / ((float)sqrt(__dadd_rn(ux2, uy2)) + 1e-9f);
+    }
+    float2 t1[EPT], t2[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) t1[e] = t2[e] = make_float2(0.f, 0.f);
+    const float Z = a.Z;
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        const float2 *__restrict__ in = pick4(a.in, f);
+        float2 *__restrict__ fh = pick4(a.fhat, f);
+        float2 v[liters][4];
+        const size_t step = (size_t)per * a.ld_in;
+#pragma unroll
+        for (int it = 0; it < liters; ++it) {
+            const int idx = it * T + tid;
+            const int j = idx >> lgCL;
+            if (col_ok) {
+                const float2 *src = in + (size_t)j * a.ld_in + c;
+                v[it][0] = src[0]; v[it][1] = src[step]; v[it][2] = src[2 * step]; v[it][3] = src[3 * step];
+            } else {
+                v[it][0] = v[it][1] = v[it][2] = v[it][3] = make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < liters; ++it) {
+            const int j = (it * T + tid) >> lgCL;
+            bfly4(v[it][0], v[it][1], v[it][2], v[it][3]);
+            float2 *y = buf0 + lane * PITCH + 4 * j;
+            *reinterpret_cast<float4 *>(y) = make_float4(v[it][0].x, v[it][0].y, v[it][1].x, v[it][1].y);
+            *reinterpret_cast<float4 *>(y + 2) = make_float4(v[it][2].x, v[it][2].y, v[it][3].x, v[it][3].y);
+        }
+        const int cur = fft_ct<LGN, 2, CL, PITCH, 0, false, T>(buf0, buf1, stw);
+        const float2 *res = (cur ? buf1 : buf0) + lane * PITCH;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int n = (e * T + tid) >> lgCL;
+            const float2 w = res[(n - a.out_roll) & (N - 1)];
+            if (a.store_fhat && col_ok) fh[(size_t)n * a.ldf + c] = w;
+            const float uxn = uxf[n];
+            const bool dc = (uxn == 0.f) && (uyf == 0.f);          // (float)u == 0 iff u == 0 on these grids
+            const float pxe = dc ? 1.f : uxn * inv[e], pye = uyf * inv[e];
+            const float cx = pxe * uzf[e], cy = pye * uzf[e];
+            float k1, k2;
+            if (f == 0) { k1 = -pxe; k2 = -cy; }                   // Ex:  L_y = -Fex
+            else if (f == 1) { k1 = -pye; k2 = cx; }               // Ey:  L_x =  Fey
+            else if (f == 2) { k1 = Z * cy; k2 = -(Z * pxe); }     // Hx:  N_y =  Fhx
+            else { k1 = -(Z * cx); k2 = -(Z * pye); }              // Hy:  N_x = -Fhy
+            t1[e].x = fmaf(k1, w.x, t1[e].x); t1[e].y = fmaf(k1, w.y, t1[e].y);
+            t2[e].x = fmaf(k2, w.x, t2[e].x); t2[e].y = fmaf(k2, w.y, t2[e].y);
+        }
+        __syncthreads();                                           // buffers free for the next field
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int n = (e * T + tid) >> lgCL;
+        const float mag = t1[e].x * t1[e].x + t1[e].y * t1[e].y + t2[e].x * t2[e].x + t2[e].y * t2[e].y;
+        const double p = a.scale * (double)mag / ((double)uzf[e] + 1e-5);
+        if (col_ok) {
+            float pf = (float)p;
+            float *dst = a.P + (size_t)n * a.ldp + c;
+            if (a.accumulate) pf += *dst;                          // incoherent sum over sources
+            *dst = pf;
+            if (isfinite(pf)) sum += p;
+        }
+    }
+    if (a.block_sums) {                                            // :74 total_P over finite bins
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __shared__ double ws[T / 32];
+        if ((tid & 31) == 0) ws[tid >> 5] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < T / 32; ++w) s += ws[w];
+            a.block_sums[blockIdx.x] = s;
         }
     }
 }
@@ -766,6 +903,9 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
 }
 
 // tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
+static int g_rows_per_sm = 0;          // TMA row pass: resident CTAs per SM (0 = as many as fit, at most 3)
+static int g_rows_evict_first = 1;     // TMA row pass: stream the aperture through L2 with an evict-first policy
+static int g_cols_power_wide = 0;      // fused column+power pass: 1 = twice as wide column tiles, 512 threads
 static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -822,6 +962,25 @@ extern "C" int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int 
     return MLB_OK;
 }
 
+extern "C" int mlb_set_option(const char *name, int value) {
+    MLB_REQUIRE(name != nullptr, "mlb_set_option: NULL name");
+    const std::string n(name);
+    if (n == "rows_ctas_per_sm") { MLB_REQUIRE(value >= 0 && value <= 3, "rows_ctas_per_sm: 0..3"); mlb::g_rows_per_sm = value; }
+    else if (n == "rows_l2_evict_first") mlb::g_rows_evict_first = value ? 1 : 0;
+    else if (n == "cols_power_wide") mlb::g_cols_power_wide = value ? 1 : 0;
+    else MLB_REQUIRE(false, "mlb_set_option: unknown option '%s'", name);
+    return MLB_OK;
+}
+
+extern "C" int mlb_get_option(const char *name) {
+    if (!name) return -1;
+    const std::string n(name);
+    if (n == "rows_ctas_per_sm") return mlb::g_rows_per_sm;
+    if (n == "rows_l2_evict_first") return mlb::g_rows_evict_first;
+    if (n == "cols_power_wide") return mlb::g_cols_power_wide;
+    return -1;
+}
+
 extern "C" int mlb_fft_max_length(void) { return mlb::FFT_MAX_N; }
 
 extern "C" int mlb_fft_rows_can_transpose(int N) {
@@ -866,6 +1025,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_rows;
     a.in_roll_r = in_roll_r; a.in_roll_c = in_roll_c; a.out_roll = out_roll; a.s1 = s1; a.s2 = s2;
+    a.evict_first = mlb::g_rows_evict_first;
     int lanes = 1;
     while (lanes * 2 * N <= mlb::g_rows_points && lanes * 2 <= n_rows) lanes *= 2;   // small transforms: several rows per CTA
     a.lanes = lanes;
@@ -897,6 +1057,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
         }                                                                                                            \
         int per_sm = (int)((220 * 1024) / (Cfg::SMEM + 1024));                                                       \
         if (per_sm > 3) per_sm = 3;                                                                                  \
+        if (mlb::g_rows_per_sm > 0 && mlb::g_rows_per_sm < per_sm) per_sm = mlb::g_rows_per_sm;                      \
         if (per_sm < 1) per_sm = 1;                                                                                  \
         int grid = n_sm * per_sm;                                                                                    \
         if (grid > n_rows * batch) grid = n_rows * batch;                                                            \
@@ -973,7 +1134,7 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
         return mlb::check_launch("mlb_fft_cols(mixed radix)");
     }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
-    a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1;
+    a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1; a.evict_first = 0;
     if (a.lgN >= 12) {
         for (int b = 0; b < batch; ++b)
             MLB_REQUIRE(a.in[b] != a.out[b], "mlb_fft_cols: N >= 4096 needs out != in (the input is used as scratch)");
@@ -1029,4 +1190,77 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     else MLB_COLS_LAUNCH(0, 0);
 #undef MLB_COLS_LAUNCH
     return mlb::check_launch("mlb_fft_cols");
+}
+
+// column tile width of the fused column+power pass for a length-N transform (0: not supported)
+static int cols_power_tile(int N) {
+    if (!mlb::is_pow2(N) || N < 256 || N > 2048) return 0;
+    return (mlb::g_cols_power_wide ? 4096 : 2048) / N;
+}
+
+extern "C" int mlb_fft_cols_power_blocks(int N, int n_cols) {
+    const int cl = cols_power_tile(N);
+    return (cl && n_cols > 0) ? (n_cols + cl - 1) / cl : 0;
+}
+
+extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw,
+                                  int out_roll, const double *ux, const double *uy, double amp_scale,
+                                  double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
+                                  double *block_sums, mlb_c64 *const *h_Fhat, int ldf, void *stream) {
+    const int cl = cols_power_tile(N);
+    MLB_REQUIRE(cl > 0, "mlb_fft_cols_power: length %d must be a power of two in 256..2048", N);
+    MLB_REQUIRE(h_in && tw && ux && uy && P, "mlb_fft_cols_power: NULL pointer");
+    MLB_REQUIRE(n_cols > 0 && ld_in >= n_cols && ldp >= n_cols && out_roll >= 0 && out_roll < N,
+                "mlb_fft_cols_power: bad sizes");
+    MLB_REQUIRE(wavelength > 0 && n_glass > 0 && Z0 > 0, "mlb_fft_cols_power: bad physical constants");
+    mlb::ColsPowerArgs a;
+    for (int f = 0; f < 4; ++f) {
+        MLB_REQUIRE(h_in[f] != nullptr, "mlb_fft_cols_power: field %d is NULL", f);
+        a.in[f] = reinterpret_cast<const float2 *>(h_in[f]);
+        a.fhat[f] = nullptr;
+        if (h_Fhat) {
+            MLB_REQUIRE(h_Fhat[f] != nullptr && ldf >= n_cols, "mlb_fft_cols_power: bad Fhat operand %d", f);
+            a.fhat[f] = reinterpret_cast<float2 *>(h_Fhat[f]);
+        }
+    }
+    a.store_fhat = h_Fhat ? 1 : 0;
+    a.tw = reinterpret_cast<const float2 *>(tw);
+    a.ux = ux; a.uy = uy; a.P = P; a.block_sums = block_sums;
+    const double pi = 3.14159265358979323846;
+    const double Zd = Z0 / n_glass;                                            // nearfield_farfield.py:183
+    const double k = 2 * pi * n_glass / wavelength;
+    a.scale = k * k / (32 * pi * pi * Zd) * amp_scale * amp_scale * 2.0;       // :184, :189
+    a.Z = (float)Zd;
+    a.ld_in = ld_in; a.ldf = ldf; a.ldp = ldp; a.n_cols = n_cols; a.out_roll = out_roll; a.accumulate = accumulate ? 1 : 0;
+    const int lgN = mlb::ilog2(N);
+    const int grid = (n_cols + cl - 1) / cl;
+    const size_t smem = (2 * (size_t)cl * (N + 4) + N) * sizeof(float2) + (size_t)N * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MLB_CP_LAUNCH(LG, CL, T)                                                                                      \
+    do {                                                                                                              \
+        static bool set_ = false;                                                                                     \
+        if (!set_) {                                                                                                  \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_power_kernel<LG, CL, T>,                                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+            set_ = true;                                                                                              \
+        }                                                                                                             \
+        mlb::fft_cols_power_kernel<LG, CL, T><<<grid, T, smem, st>>>(a);                                              \
+    } while (0)
+    if (!mlb::g_cols_power_wide) {                       // 2048-point tiles, 512 threads, 4 points per thread and field
+        switch (lgN) {
+            case 8: MLB_CP_LAUNCH(8, 8, 512); break;
+            case 9: MLB_CP_LAUNCH(9, 4, 512); break;
+            case 10: MLB_CP_LAUNCH(10, 2, 512); break;
+            default: MLB_CP_LAUNCH(11, 1, 512); break;
+        }
+    } else {                                             // 4096-point tiles, 1024 threads
+        switch (lgN) {
+            case 8: MLB_CP_LAUNCH(8, 16, 1024); break;
+            case 9: MLB_CP_LAUNCH(9, 8, 1024); break;
+            case 10: MLB_CP_LAUNCH(10, 4, 1024); break;
+            default: MLB_CP_LAUNCH(11, 2, 1024); break;
+        }
+    }
+#undef MLB_CP_LAUNCH
+    return mlb::check_launch("mlb_fft_cols_power");
 }

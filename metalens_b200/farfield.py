@@ -88,10 +88,13 @@ class FarfieldPlan:
     rows : optional (row0, row1): compute only that slab of far-field rows (ux indices) -- the
         multi-GPU tile of metalens_b200/sharding.py.  Supported by 'dense' and 'fold', whose work
         scales with the slab; the FFT passes produce all rows at once.
+    fuse_power : with method 'fft', float32 P and power-of-two column lengths 256..2048, run() uses the
+        fused column-pass + power kernel (mlb_fft_cols_power): the 4 x Kx x Ky aperture sums then stay in
+        registers; amplitudes() re-runs the unfused passes when asked.  False = always separate kernels.
     """
 
     def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride=None, ux=None, uy=None,
-                 method="auto", p_dtype=torch.float32, device=None, rows=None):
+                 method="auto", p_dtype=torch.float32, device=None, rows=None, fuse_power=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
@@ -101,6 +104,7 @@ class FarfieldPlan:
         self.wavelength, self.n_glass = float(wavelength), float(n_glass)
         assert p_dtype in (torch.float32, torch.float64)
         self.p_dtype = p_dtype
+        self._want_fused = bool(fuse_power)
 
         if ux is None and uy is None:
             stride = 1 if stride is None else stride
@@ -195,6 +199,8 @@ class FarfieldPlan:
             for t, n in ((self.tw1, K1), (self.tw2, K2)):
                 _lib.check(self.lib.mlb_fft_twiddle(n, t.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
             self.AxT = self.Ay = None
+            self.fused = bool(self._want_fused and not self.two_pass_t and self.p_dtype == torch.float32
+                              and self.lib.mlb_fft_cols_power_blocks(K1, K2) > 0)
         else:
             # folded aperture (K1 x K2) and exact integer DFT twiddles exp(-2 pi i p q / K)
             K1, K2 = Mx // self.sx, My // self.sy
@@ -209,10 +215,14 @@ class FarfieldPlan:
             self.G = [_c64_buffer(K1, K2, dev) for _ in range(4)]
         self.UT = ([_c64_buffer(self.Ry, Kx, dev) for _ in range(4)]     # stage-1 output, [m2][i]
                    if self.method in ("dense", "fold") else None)
-        self.Fhat = [_c64_buffer(Kx, Ky, dev) for _ in range(4)]         # aperture sums, [i][j]
+        self.fused = bool(getattr(self, "fused", False))
+        self._Fhat = None if self.fused else [_c64_buffer(Kx, Ky, dev) for _ in range(4)]   # aperture sums, [i][j]
+        self._fields_last = None
+        self._steps_cache = {}
+        self._staged = False
         self.P = torch.empty((Kx, Ky), dtype=self.p_dtype, device=dev)
         self.nblocks = self.lib.mlb_ff_epilogue_blocks(Kx, Ky)
-        self.block_sums = torch.empty(self.nblocks, dtype=torch.float64, device=dev)
+        self.block_sums = torch.empty(max(self.nblocks, Ky), dtype=torch.float64, device=dev)
         self.total = torch.zeros(1, dtype=torch.float64, device=dev)
         self.d_ux = torch.from_numpy(self.ux).to(dev)
         self.d_uy = torch.from_numpy(self.uy).to(dev)
@@ -286,11 +296,19 @@ class FarfieldPlan:
                 ("tc_stage1", stage1, 4 * (16 * Mx * My + 32 * Ky * Mx) + 16 * Ky * My, 32.0 * Mx * My * Ky),
                 ("tc_stage2", stage2, 4 * (32 * Ky * Mx + 8 * Kx * Ky) + 16 * Kx * Mx, 32.0 * Kx * Mx * Ky)]
 
+    @property
+    def Fhat(self):
+        """The four aperture-sum buffers [Kx][even(Ky)] (allocated on first use by fused plans)."""
+        if self._Fhat is None:
+            self._Fhat = [_c64_buffer(self.Kx, self.Ky, self.device) for _ in range(4)]
+        return self._Fhat
+
     # ------------------------------------------------------------------ run
     def _as_operands(self, fields):
         """Return 4 pitched complex64 device tensors [Mx][even(My)] for the kernels;
         copies only when the caller's layout cannot be used in place."""
         out = []
+        self._staged = False
         for idx, f in enumerate(fields):
             assert f.is_cuda and f.dtype == torch.complex64 and tuple(f.shape[-2:]) == (self.Mx, self.My), \
                 "fields must be CUDA complex64 (Mx, My)"
@@ -302,14 +320,30 @@ class FarfieldPlan:
                 if self._staging is None:
                     self._staging = [_c64_buffer(self.Mx, self.My, self.device) for _ in range(4)]
                 self._staging[idx][:, :self.My].copy_(f)
+                self._staged = True
                 out.append((self._staging[idx], self._staging[idx].shape[1]))
         lds = {ld for _, ld in out}
         assert len(lds) == 1, "the four fields must share one row pitch"
         return [t for t, _ in out], lds.pop()
 
-    def steps(self, fields):
+    def steps(self, fields, fused=None, accumulate=False):
         """The kernel launches of one run() as (name, thunk, algorithmic bytes, algorithmic flops);
-        run() executes them in order, bench.py times them one by one for the roofline."""
+        run() executes them in order, bench.py times them one by one for the roofline.
+        fused=False forces the separate column pass + epilogue (aperture sums stored in Fhat)."""
+        fused = self.fused if fused is None else (bool(fused) and self.fused)
+        # the launch thunks only depend on the operand addresses: cache them per set of field buffers
+        key = (tuple((f.data_ptr(), f.stride(-2), f.stride(-1)) for f in fields), fused, bool(accumulate))
+        hit = self._steps_cache.get(key)
+        if hit is not None:
+            return hit
+        out = self._make_steps(fields, fused, accumulate)
+        if not self._staged:                     # staged operands are copied on every call: never cached
+            if len(self._steps_cache) >= 16:
+                self._steps_cache.clear()
+            self._steps_cache[key] = out
+        return out
+
+    def _make_steps(self, fields, fused, accumulate):
         lib = self.lib
         ops, ld = self._as_operands(fields)
         Kx, Ky, Rx, Ry = self.Kx, self.Ky, self.Rx, self.Ry
@@ -336,8 +370,12 @@ class FarfieldPlan:
             assert not folded
             pi_, k3 = _lib.ptr_array(ops)
             pw, k4 = _lib.ptr_array(self.W)
-            pf, k5 = _lib.ptr_array(self.Fhat)
-            ldw, ldf = self.W[0].shape[1], self.Fhat[0].shape[1]
+            ldw = self.W[0].shape[1]
+            if not fused:
+                pf, k5 = _lib.ptr_array(self.Fhat)
+                ldf = self.Fhat[0].shape[1]
+            else:
+                pf = k5 = ldf = None
 
             tr = 1 if self.two_pass_t else 0
 
@@ -354,6 +392,20 @@ class FarfieldPlan:
                                                 _stream_ptr()), "mlb_fft_cols")
             out.append(("fold_fft_rows" if (self.sx > 1 or self.sy > 1) else "fft_rows", rows,
                         32 * (self.Mx * self.My + Rx * Ry), 4 * 5.0 * Rx * Ry * math.log2(Ry)))
+            if fused:
+                def cols_power(keep=k4, accumulate=accumulate):   # column pass + radiated power in one kernel
+                    nb = lib.mlb_fft_cols_power_blocks(Rx, Ry)
+                    _lib.check(lib.mlb_fft_cols_power(pw, ldw, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx,
+                                                      self.d_ux.data_ptr(), self.d_uy.data_ptr(), self.dxp * self.dyp,
+                                                      self.wavelength, self.n_glass, Z0, self.P.data_ptr(),
+                                                      self.P.shape[1], 1 if accumulate else 0,
+                                                      self.block_sums.data_ptr(), None, 0, _stream_ptr()),
+                               "mlb_fft_cols_power")
+                    _lib.check(lib.mlb_sum_f64(self.block_sums.data_ptr(), nb, self.dux * self.duy,
+                                               self.total.data_ptr(), _stream_ptr()), "mlb_sum_f64")
+                    return self.P, self.total
+                out.append(("fft_cols_power", cols_power, (32 + 4) * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
+                return out
             out.append(("fft_rows_pass2" if tr else "fft_cols", cols, 64 * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
         else:
             pa, k6 = _lib.ptr_array(ops)
@@ -377,7 +429,7 @@ class FarfieldPlan:
         """[fold ->] separable reduction or FFT passes:
         Fhat_f[i,j] = sum_{m1,m2} J_f[m1,m2] e^{-ik(x'ux_i + y'uy_j)}.
         Returns the 4 pitched device tensors (logical view [:, :Ky])."""
-        for name, fn, _b, _f in self.steps(fields)[:-1]:
+        for name, fn, _b, _f in self.steps(fields, fused=False)[:-1]:
             fn()
         return self.Fhat
 
@@ -401,8 +453,29 @@ class FarfieldPlan:
     def run(self, fields, accumulate=False):
         """Device-resident fields (4 CUDA complex64 (Mx,My) tensors) -> (P, total_P) on device.
         accumulate=True adds this item's power to P (total_P is that of this item alone)."""
+        if self.fused:
+            self._fields_last = fields
+            for name, fn, _b, _f in self.steps(fields, accumulate=accumulate):
+                fn()
+            return self.P, self.total
         self.aperture_sums(fields)
         return self.power(accumulate=accumulate)
+
+    def run_split(self, fields, accumulate=False):
+        """run() as two halves for callers that pipeline items over two streams (sharding.py): returns
+        (first, second) thunks -- `first` is the HBM-bound pass over the aperture, `second` everything
+        after it (column pass, power epilogue, total_P) and returns (P, total_P)."""
+        st = self.steps(fields, accumulate=accumulate)
+        if self.fused:
+            self._fields_last = fields
+            return st[0][1], st[1][1]
+        head, tail = st[0][1], [fn for _n, fn, _b, _f in st[1:-1]]
+
+        def second():
+            for fn in tail:
+                fn()
+            return self.power(accumulate=accumulate)
+        return head, second
 
     def run_incoherent(self, field_sets):
         """Incoherent sum over several sources / polarisations (the x-, y-, z-dipole recipe of
@@ -414,7 +487,12 @@ class FarfieldPlan:
         return self.P, total
 
     def amplitudes(self):
-        """Complex aperture sums of the last run as a (4, Kx, Ky) device tensor."""
+        """Complex aperture sums of the last run as a (4, Kx, Ky) device tensor.  A fused plan keeps them
+        in registers during run(); here it re-runs the separate passes on the last run's fields."""
+        if self.fused:
+            if self._fields_last is None:
+                raise _lib.MetalensB200Error("amplitudes(): no run() yet")
+            self.aperture_sums(self._fields_last)
         return torch.stack([f[:, :self.Ky] for f in self.Fhat])
 
     def run_host(self, Ex, Ey=None, Hx=None, Hy=None):

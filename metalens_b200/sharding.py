@@ -81,6 +81,12 @@ class ShardedFarfield:
         self._out = [None, None]
         self._work = [None, None]
         self._flip = 0
+        # overlap=True pipelines the tiles over two streams: the HBM-bound pass over each aperture runs on the
+        # caller's stream, everything after it (column pass, power epilogue, tile copy, the collective) on a side
+        # stream, so the tail of tile k executes under the aperture pass of tile k+1
+        self._side = None
+        self._tail_done = [None] * len(self.tiles)     # per plan: its buffers are free again (side-stream event)
+        self._side_done = None
 
     @property
     def items_needed(self):
@@ -94,6 +100,9 @@ class ShardedFarfield:
         concurrently with the next call's kernels."""
         b = self._flip
         self._flip ^= 1
+        if overlap and runner is None and all(hasattr(p, "run_split") for p in self.plans) \
+                and self.plans and self.plans[0].P.is_cuda:
+            return self._run_pipelined(fields_of, b)
         if self._work[b] is not None:            # the collective that last used this buffer pair
             self._work[b].wait()
             self._work[b] = None
@@ -113,9 +122,82 @@ class ShardedFarfield:
             res = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group, out=self._out[b])
         return res, totals
 
+    def _run_pipelined(self, fields_of, b):
+        """overlap=True on CUDA: two-stream software pipeline over the local tiles (see __init__)."""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.plans[0].P.device)
+        side = self._side
+        totals = []
+        for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
+            first, second = plan.run_split(fields_of(tile.item))
+            if self._tail_done[k] is not None:           # the previous tail of this plan still reads its buffers
+                main.wait_event(self._tail_done[k])
+            first()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                if k == 0 and self._work[b] is not None:     # the collective that last used this buffer pair
+                    self._work[b].wait()
+                    self._work[b] = None
+                P, total = second()
+                if self._local[b] is None:
+                    shape = (len(self.tiles),) + tuple(P.shape)
+                    self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
+                    self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
+                self._local[b][k].copy_(P)
+                totals.append(total)
+                done = torch.cuda.Event()
+                done.record(side)
+                self._tail_done[k] = done
+        with torch.cuda.stream(side):
+            if self.world > 1:
+                res, self._work[b] = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group,
+                                                  out=self._out[b], async_op=True)
+            else:
+                res = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group, out=self._out[b])
+            self._side_done = torch.cuda.Event()
+            self._side_done.record(side)
+        return res, totals
+
+    def capture(self, fields_of):
+        """Capture one pipelined step (every local tile, both streams, the tile copies) into a CUDA graph and
+        return it; ``replay()`` then re-runs the step on whatever is in the same field buffers with a single
+        launch.  Single-rank only (world == 1): with more ranks the collective stays an eager NCCL call."""
+        if self.world != 1:
+            raise ValueError("capture() is for world == 1; use run(overlap=True) across ranks")
+        self.run(fields_of, overlap=True)                # warm-up outside capture (lazy allocations, attributes)
+        self.finish()
+        torch.cuda.synchronize()
+        self._tail_done = [None] * len(self.tiles)       # no dependencies on events recorded outside the capture
+        self._flip = 0
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_result = self.run(fields_of, overlap=True)
+            self.finish()                                # joins the side stream back into the capturing stream
+        self._tail_done = [None] * len(self.tiles)
+        self._graph = g
+        return g
+
+    def replay(self):
+        """Replay the captured step; returns (P (n_items, n_rows, Ky), totals) like run()."""
+        self._graph.replay()
+        return self._graph_result
+
     def finish(self):
-        """Wait for outstanding asynchronous all-gathers."""
+        """Wait for outstanding asynchronous all-gathers (and, in pipelined mode, make the caller's stream
+        wait for the side stream)."""
         for b in (0, 1):
             if self._work[b] is not None:
-                self._work[b].wait()
+                if self._side is not None:
+                    with torch.cuda.stream(self._side):
+                        self._work[b].wait()
+                    self._side_done = torch.cuda.Event()
+                    self._side_done.record(self._side)
+                else:
+                    self._work[b].wait()
                 self._work[b] = None
+        if self._side_done is not None:
+            torch.cuda.current_stream().wait_event(self._side_done)
+            self._side_done = None

@@ -529,3 +529,135 @@ def test_long_column_transform_all_bins():
     assert np.array_equal(np.isnan(sub), np.isnan(P_ref))
     fin = np.isfinite(P_ref)
     assert np.abs(sub - P_ref)[fin].max() / np.nanmax(P1.cpu().numpy()) < FF_TOL
+
+
+def _same(a, b):
+    return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+@pytest.mark.parametrize("shape,stride", [((256, 256), 1), ((1024, 1024), 4), ((1024, 2048), (4, 4)),
+                                          ((2048, 512), (2, 2)), ((2048, 1024), (1, 4)), ((512, 300), (1, 1))])
+def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
+    """fft_cols_power_kernel (column pass + radiated power in one kernel, aperture sums never stored) against
+    the separate column pass + epilogue on the same plan geometry: same NaN mask, P and total_P to fp32
+    rounding; column lengths 256..2048, square and rectangular, ragged column counts, both tile widths."""
+    from metalens_b200 import _lib
+    from metalens_b200.farfield import FarfieldPlan
+    lib = _lib.load()
+    Mx, My = shape
+    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(Mx, 71, WL, My=My)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
+    lib.mlb_set_option(b"cols_power_wide", wide)
+    try:
+        fused = FarfieldPlan((Mx, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=stride)
+        plain = FarfieldPlan((Mx, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=stride, fuse_power=False)
+        assert fused.method == "fft" and fused.fused and not plain.fused
+        assert [s[0] for s in fused.steps(dev)][-1] == "fft_cols_power"
+        P1, t1 = fused.run(dev)
+        P2, t2 = plain.run(dev)
+        P1, P2 = P1.cpu().numpy(), P2.cpu().numpy()
+        assert np.isnan(P1).sum() > 0 or max(fused.ux.max(), fused.uy.max()) < 0.7
+        assert power_map_error(P1, P2) < 2e-6
+        assert abs(t1.item() - t2.item()) <= 2e-6 * abs(t2.item())
+        # the aperture sums are still available on request (re-runs the separate passes)
+        a1, a2 = fused.amplitudes(), plain.amplitudes()
+        assert torch.equal(a1, a2)
+        # incoherent accumulation (SURVEY N4) through the fused kernel
+        Pa, ta = fused.run_incoherent([dev, dev])
+        Pa = Pa.cpu().numpy()
+        fin = np.isfinite(P2)
+        assert np.array_equal(np.isnan(Pa), np.isnan(P2))
+        assert np.abs(Pa[fin] - 2 * P2[fin]).max() <= 4e-6 * P2[fin].max()
+        assert abs(ta.item() - 2 * t2.item()) <= 4e-6 * abs(t2.item())
+    finally:
+        lib.mlb_set_option(b"cols_power_wide", 0)
+
+
+@pytest.mark.parametrize("name,stride", [("lens256_seed1", 1), ("lens256_seed1_rot", 1)])
+def test_fused_path_against_reference_golden(name, stride, golden_dir):
+    """The fused float32 path against the unmodified reference's output (committed fixture)."""
+    from metalens_b200.farfield import FarfieldPlan
+    g = golden(golden_dir, name)
+    Ex, Ey, Hx, Hy, x, y = CASES[name]()
+    plan = FarfieldPlan(Ex.shape, x[1] - x[0], y[1] - y[0], WL, NG, stride=stride)
+    assert plan.fused
+    P, total = plan.run([torch.from_numpy(np.ascontiguousarray(a.astype(np.complex64))).cuda() for a in (Ex, Ey, Hx, Hy)])
+    assert power_map_error(P.cpu().numpy(), g["P"]) < FF_TOL
+    assert abs(total.item() - g["total_P"]) <= FF_TOL * abs(g["total_P"])
+
+
+def test_options_api():
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    assert lib.mlb_get_option(b"rows_l2_evict_first") in (0, 1)
+    assert lib.mlb_get_option(b"no_such_option") == -1
+    assert lib.mlb_set_option(b"no_such_option", 1) != 0
+    assert b"unknown option" in lib.mlb_last_error()
+    assert lib.mlb_set_option(b"rows_ctas_per_sm", 7) != 0
+    assert lib.mlb_fft_cols_power_blocks(1000, 64) == 0 and lib.mlb_fft_cols_power_blocks(4096, 64) == 0
+    assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 512
+
+
+@pytest.mark.parametrize("evict,per_sm", [(0, 0), (1, 1), (1, 2)])
+def test_row_pass_options_do_not_change_results(evict, per_sm):
+    """L2 evict-first streaming and the resident-CTA count of the TMA-fed row pass are pure scheduling knobs."""
+    from metalens_b200 import _lib
+    from metalens_b200.farfield import FarfieldPlan
+    lib = _lib.load()
+    M = 1024
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 5, WL, NG)
+    dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+    plan = FarfieldPlan((M, M), x[1] - x[0], x[1] - x[0], WL, NG, stride=4)
+    ref = plan.run(dev)[0].clone()
+    lib.mlb_set_option(b"rows_l2_evict_first", evict)
+    lib.mlb_set_option(b"rows_ctas_per_sm", per_sm)
+    try:
+        assert _same(plan.run(dev)[0], ref)
+    finally:
+        lib.mlb_set_option(b"rows_l2_evict_first", 1)
+        lib.mlb_set_option(b"rows_ctas_per_sm", 0)
+
+
+@pytest.mark.parametrize("M,stride,method", [(1024, 4, "auto"), (512, 2, "auto"), (256, 4, "fold"), (96, 1, "dense")])
+def test_pipelined_tiles_equal_sequential(M, stride, method):
+    """ShardedFarfield.run(overlap=True) pipelines the local tiles over two streams (aperture pass of tile k+1
+    over the column pass / epilogue of tile k); results must equal the one-stream run bit for bit, over
+    several back-to-back steps (buffer reuse across steps), and so must a captured CUDA graph of the step."""
+    from metalens_b200.farfield import FarfieldPlan
+    from metalens_b200.sharding import ShardedFarfield
+    n_items = 3
+    K = M // stride
+    fields, d = {}, None
+    for i in range(n_items):
+        Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 90 + i, WL, NG, rotate=bool(i % 2))
+        d = x[1] - x[0]
+        fields[i] = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+
+    def make_plan(item, r0, r1):
+        return FarfieldPlan((M, M), d, d, WL, NG, stride=stride, method=method)
+    sh = ShardedFarfield(n_items, K, make_plan, rank=0, world=1)
+    P_seq, tot_seq = sh.run(lambda i: fields[i])
+    torch.cuda.synchronize()
+    P_seq = P_seq.clone()
+    tot_seq = [t.clone() for t in tot_seq]
+    for _ in range(4):
+        P_ov, tot_ov = sh.run(lambda i: fields[i], overlap=True)
+    sh.finish()
+    torch.cuda.synchronize()
+    assert _same(P_ov, P_seq)
+    assert all(torch.equal(a, b) for a, b in zip(tot_ov, tot_seq))
+    # one captured graph of the whole step; new apertures are written into the same buffers
+    sh.capture(lambda i: fields[i])
+    for i in range(n_items):
+        for f in fields[i]:
+            f.mul_(2.0)
+    P_g, tot_g = sh.replay()
+    torch.cuda.synchronize()
+    fin = torch.isfinite(P_seq)
+    assert _same(torch.isnan(P_g), torch.isnan(P_seq))
+    assert float((P_g[fin] - 4 * P_seq[fin]).abs().max()) <= 1e-6 * float(P_seq[fin].max()) * 4
+    for _ in range(3):
+        P_g2, _t = sh.replay()
+    torch.cuda.synchronize()
+    assert _same(P_g2, P_g)
