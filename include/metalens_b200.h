@@ -157,7 +157,8 @@ int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols,
 /* Named integer tuning options (defaults are the B200-tuned values):
  *   rows_ctas_per_sm     resident CTAs per SM of the TMA-fed row pass, 0 = as many as fit (default)
  *   rows_l2_evict_first  1 (default) = stream the aperture through L2 with an evict-first policy
- *   cols_power_wide      1 = 4096-point column tiles / 1024 threads in the fused pass (default 0: 2048 / 512)
+ *   cols_power_wide      fused pass tile: 1 = 4096-point column tiles / 1024 threads, 0 = 2048 / 512,
+ *                        -1 (default) = by length: wide from 1024 points up
  * mlb_get_option returns -1 for an unknown name. */
 int mlb_set_option(const char *name, int value);
 int mlb_get_option(const char *name);

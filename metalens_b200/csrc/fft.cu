@@ -19,6 +19,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "fft16.cuh"
 
 namespace mlb {
 
@@ -203,18 +204,18 @@ __device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *
 // HBM bandwidth to that phase alternation).  CTAs are persistent and stride over (field, row) work items.
 constexpr int TMA_CONSUMERS = 256;
 
-template <int LGN>
+template <int LGN, int RING_KB = 64>
 struct RowsTmaCfg {
     static constexpr int N = 1 << LGN;
     static constexpr int SLOT_BYTES = N * 8;
-    static constexpr int SLOTS = (64 * 1024 / SLOT_BYTES) > 16 ? 16 : ((64 * 1024 / SLOT_BYTES) < 4 ? 4 : (64 * 1024 / SLOT_BYTES));
+    static constexpr int SLOTS = (RING_KB * 1024 / SLOT_BYTES) > 32 ? 32 : ((RING_KB * 1024 / SLOT_BYTES) < 4 ? 4 : (RING_KB * 1024 / SLOT_BYTES));
     static constexpr int EPT = N / TMA_CONSUMERS;                       // complex elements per consumer thread
     static constexpr size_t SMEM = (size_t)SLOTS * SLOT_BYTES + 3 * (size_t)N * 8 + 2 * SLOTS * sizeof(uint64_t) + 16;
 };
 
-template <int LGN>
+template <int LGN, int RING_KB = 64>
 __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(const FftArgs a, int batch) {
-    using Cfg = RowsTmaCfg<LGN>;
+    using Cfg = RowsTmaCfg<LGN, RING_KB>;
     constexpr int N = Cfg::N, S = Cfg::SLOTS, EPT = Cfg::EPT;
     extern __shared__ __align__(128) unsigned char tsm[];
     float2 *ring = reinterpret_cast<float2 *>(tsm);
@@ -904,8 +905,12 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
 
 // tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
 static int g_rows_per_sm = 0;          // TMA row pass: resident CTAs per SM (0 = as many as fit, at most 3)
+static int g_rows_engine = 0;          // row pass: 0 = radix-4 shared-memory kernels (TMA-fed where possible), 1 = radix-16
+                                       // register kernels (256..8192 points), 2 = radix-16 only without a fold
+static int g_rows_ring_kb = 64;        // TMA row pass: bytes of shared memory in the slot ring per CTA (64 or 128 KB)
 static int g_rows_evict_first = 1;     // TMA row pass: stream the aperture through L2 with an evict-first policy
-static int g_cols_power_wide = 0;      // fused column+power pass: 1 = twice as wide column tiles, 512 threads
+static int g_cols_power_wide = -1;     // fused column+power pass: 1 = 4096-point tiles / 1024 threads, 0 = 2048 / 512,
+                                       // -1 = by length (wide from 1024 points up: measured faster on B200)
 static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -967,7 +972,9 @@ extern "C" int mlb_set_option(const char *name, int value) {
     const std::string n(name);
     if (n == "rows_ctas_per_sm") { MLB_REQUIRE(value >= 0 && value <= 3, "rows_ctas_per_sm: 0..3"); mlb::g_rows_per_sm = value; }
     else if (n == "rows_l2_evict_first") mlb::g_rows_evict_first = value ? 1 : 0;
-    else if (n == "cols_power_wide") mlb::g_cols_power_wide = value ? 1 : 0;
+    else if (n == "rows_engine") { MLB_REQUIRE(value >= 0 && value <= 2, "rows_engine: 0..2"); mlb::g_rows_engine = value; }
+    else if (n == "rows_ring_kb") { MLB_REQUIRE(value == 64 || value == 128, "rows_ring_kb: 64 or 128"); mlb::g_rows_ring_kb = value; }
+    else if (n == "cols_power_wide") mlb::g_cols_power_wide = value < 0 ? -1 : (value ? 1 : 0);
     else MLB_REQUIRE(false, "mlb_set_option: unknown option '%s'", name);
     return MLB_OK;
 }
@@ -977,6 +984,8 @@ extern "C" int mlb_get_option(const char *name) {
     const std::string n(name);
     if (n == "rows_ctas_per_sm") return mlb::g_rows_per_sm;
     if (n == "rows_l2_evict_first") return mlb::g_rows_evict_first;
+    if (n == "rows_ring_kb") return mlb::g_rows_ring_kb;
+    if (n == "rows_engine") return mlb::g_rows_engine;
     if (n == "cols_power_wide") return mlb::g_cols_power_wide;
     return -1;
 }
@@ -1034,6 +1043,35 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     bool vec = (mlb::g_rows_vec == 2) && (N >= 8) && (in_roll_c % 2 == 0) && (ld_in % 2 == 0);
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
+    // radix-16 register kernels (256..8192 points)
+    if (!transpose_out && a.lgN >= 8 && a.lgN <= 13 &&
+        (mlb::g_rows_engine == 1 || (mlb::g_rows_engine == 2 && s1 == 1 && s2 == 1))) {
+        bool inplace = false;
+        for (int b = 0; b < batch; ++b) inplace = inplace || (a.in[b] == a.out[b]);
+        mlb::R16Args r;
+        for (int b = 0; b < 4; ++b) { r.in[b] = a.in[b]; r.out[b] = a.out[b]; }
+        r.tw = a.tw; r.ld_in = ld_in; r.ld_out = ld_out; r.n_rows = n_rows; r.in_roll_r = in_roll_r;
+        r.in_roll_c = in_roll_c; r.out_roll = out_roll; r.s1 = s1; r.s2 = s2;
+        cudaStream_t st = (cudaStream_t)stream;
+        (void)inplace;      // in-place is safe: a CTA reads all of its rows before it writes them (in_roll_r == 0 checked above)
+#define MLB_R16_ROWS(LG)                                                                                              \
+    case LG: {                                                                                                       \
+        constexpr int T = mlb::R16Threads<LG>::value, TR = (1 << LG) >> 4, L = T / TR;                               \
+        constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 1;                                                      \
+        const size_t smem16 = (size_t)L * PITCH * sizeof(float2);                                                    \
+        static bool set_ = false;                                                                                    \
+        if (!set_) {                                                                                                 \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_rows_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          (int)smem16));                                                             \
+            set_ = true;                                                                                             \
+        }                                                                                                            \
+        dim3 g16((n_rows + L - 1) / L, batch);                                                                       \
+        mlb::fft16_rows_kernel<LG><<<g16, T, smem16, st>>>(r);                                                       \
+        return mlb::check_launch("mlb_fft_rows(radix 16)");                                                          \
+    }
+        switch (a.lgN) { MLB_R16_ROWS(8) MLB_R16_ROWS(9) MLB_R16_ROWS(10) MLB_R16_ROWS(11) MLB_R16_ROWS(12) MLB_R16_ROWS(13) }
+#undef MLB_R16_ROWS
+    }
     // TMA-fed persistent kernel (256..2048 points): needs 16-byte aligned row segments
     {
         bool tma_ok = mlb::g_rows_tma && a.lgN >= 8 && a.lgN <= 11 && (ld_in % 2 == 0);
@@ -1046,13 +1084,13 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
                 MLB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
             }
             cudaStream_t st = (cudaStream_t)stream;
-#define MLB_ROWS_TMA(LG)                                                                                              \
-    case LG: {                                                                                                       \
-        using Cfg = mlb::RowsTmaCfg<LG>;                                                                             \
+#define MLB_ROWS_TMA_RING(LG, KB)                                                                                     \
+    {                                                                                                                \
+        using Cfg = mlb::RowsTmaCfg<LG, KB>;                                                                         \
         static bool set_ = false;                                                                                    \
         if (!set_) {                                                                                                 \
-            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_tma_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)Cfg::SMEM));                                                          \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_tma_kernel<LG, KB>,                                          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));             \
             set_ = true;                                                                                             \
         }                                                                                                            \
         int per_sm = (int)((220 * 1024) / (Cfg::SMEM + 1024));                                                       \
@@ -1061,11 +1099,16 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
         if (per_sm < 1) per_sm = 1;                                                                                  \
         int grid = n_sm * per_sm;                                                                                    \
         if (grid > n_rows * batch) grid = n_rows * batch;                                                            \
-        mlb::fft_rows_tma_kernel<LG><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch);                    \
+        mlb::fft_rows_tma_kernel<LG, KB><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch);                \
         return mlb::check_launch("mlb_fft_rows(tma)");                                                               \
     }
+#define MLB_ROWS_TMA(LG)                                                                                              \
+    case LG:                                                                                                         \
+        if (mlb::g_rows_ring_kb == 128) MLB_ROWS_TMA_RING(LG, 128)                                                   \
+        else MLB_ROWS_TMA_RING(LG, 64)
             switch (a.lgN) { MLB_ROWS_TMA(8) MLB_ROWS_TMA(9) MLB_ROWS_TMA(10) MLB_ROWS_TMA(11) }
 #undef MLB_ROWS_TMA
+#undef MLB_ROWS_TMA_RING
         }
     }
     MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs the TMA-fed kernel (256..2048 points, "
@@ -1195,7 +1238,8 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
 // column tile width of the fused column+power pass for a length-N transform (0: not supported)
 static int cols_power_tile(int N) {
     if (!mlb::is_pow2(N) || N < 256 || N > 2048) return 0;
-    return (mlb::g_cols_power_wide ? 4096 : 2048) / N;
+    const bool wide = mlb::g_cols_power_wide < 0 ? (N >= 1024) : (mlb::g_cols_power_wide != 0);
+    return (wide ? 4096 : 2048) / N;
 }
 
 extern "C" int mlb_fft_cols_power_blocks(int N, int n_cols) {
@@ -1246,7 +1290,7 @@ extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, 
         }                                                                                                             \
         mlb::fft_cols_power_kernel<LG, CL, T><<<grid, T, smem, st>>>(a);                                              \
     } while (0)
-    if (!mlb::g_cols_power_wide) {                       // 2048-point tiles, 512 threads, 4 points per thread and field
+    if (cl * N == 2048) {                                // 2048-point tiles, 512 threads, 4 points per thread and field
         switch (lgN) {
             case 8: MLB_CP_LAUNCH(8, 8, 512); break;
             case 9: MLB_CP_LAUNCH(9, 4, 512); break;

@@ -114,7 +114,7 @@ def workload(M, s, n_items, tag):
             us_per_item=us / n_items)
     except Exception as e:                                  # noqa: BLE001
         out(tag=tag, variant="graph", error=repr(e))
-    opt(rows_ctas_per_sm=0, rows_l2_evict_first=1, cols_power_wide=0)
+    opt(rows_ctas_per_sm=0, rows_l2_evict_first=1, cols_power_wide=-1)
     del fields, sh_u, sh_f
     torch.cuda.empty_cache()
 

@@ -571,7 +571,7 @@ def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
         assert np.abs(Pa[fin] - 2 * P2[fin]).max() <= 4e-6 * P2[fin].max()
         assert abs(ta.item() - 2 * t2.item()) <= 4e-6 * abs(t2.item())
     finally:
-        lib.mlb_set_option(b"cols_power_wide", 0)
+        lib.mlb_set_option(b"cols_power_wide", -1)
 
 
 @pytest.mark.parametrize("name,stride", [("lens256_seed1", 1), ("lens256_seed1_rot", 1)])
@@ -596,7 +596,10 @@ def test_options_api():
     assert b"unknown option" in lib.mlb_last_error()
     assert lib.mlb_set_option(b"rows_ctas_per_sm", 7) != 0
     assert lib.mlb_fft_cols_power_blocks(1000, 64) == 0 and lib.mlb_fft_cols_power_blocks(4096, 64) == 0
+    lib.mlb_set_option(b"cols_power_wide", 0)
     assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 512
+    lib.mlb_set_option(b"cols_power_wide", -1)
+    assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 256 and lib.mlb_fft_cols_power_blocks(512, 512) == 128
 
 
 @pytest.mark.parametrize("evict,per_sm", [(0, 0), (1, 1), (1, 2)])
@@ -661,3 +664,35 @@ def test_pipelined_tiles_equal_sequential(M, stride, method):
         P_g2, _t = sh.replay()
     torch.cuda.synchronize()
     assert _same(P_g2, P_g)
+
+
+def test_radix16_row_kernels_match_numpy():
+    """fft16_rows_kernel (register-resident radix-16 butterflies, csrc/fft16.cuh) against numpy.fft for every
+    supported length 256..8192: fftshift rolls, ragged row counts (several rows per CTA), aperture fold."""
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(16)
+    lib.mlb_set_option(b"rows_engine", 1)
+    try:
+        for N, n_rows, s1, s2 in ((256, 37, 1, 1), (512, 9, 1, 1), (1024, 5, 1, 1), (2048, 3, 1, 1), (4096, 3, 1, 1),
+                                  (8192, 2, 1, 1), (256, 7, 2, 3), (1024, 6, 4, 4), (4096, 2, 2, 1), (8192, 1, 1, 2)):
+            big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
+            ldi = N * s2 + 2
+            dbig = [torch.zeros(n_rows * s1, ldi, dtype=torch.complex64).cuda() for _ in range(2)]
+            dbig[0][:, :N * s2].copy_(torch.from_numpy(big))
+            dbig[1][:, :N * s2].copy_(torch.from_numpy(2 * big))
+            tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
+            _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
+            folded = big.astype(complex).reshape(s1, n_rows, s2, N).sum(axis=(0, 2))
+            rr, rc, ro = n_rows // 2, (N // 2 + 5) % N, N // 2 + 3
+            ref = np.roll(np.fft.fft(np.roll(folded, (rr, rc), axis=(0, 1)), axis=1), ro, axis=1)
+            dres = [torch.zeros(n_rows, N + 4, dtype=torch.complex64).cuda() for _ in range(2)]
+            pi_, k1 = _lib.ptr_array(dbig)
+            po, k2 = _lib.ptr_array(dres)
+            _lib.check(lib.mlb_fft_rows(pi_, ldi, po, N + 4, n_rows, N, s1, s2, tw.data_ptr(), rr, rc, ro, 0, 2, None), "r16 rows")
+            torch.cuda.synchronize()
+            assert field_error(dres[0][:, :N].cpu().numpy(), ref) < 3e-6, (N, s1, s2)
+            assert field_error(dres[1][:, :N].cpu().numpy(), 2 * ref) < 3e-6, (N, s1, s2)
+            assert float(dres[0][:, N:].abs().max()) == 0.0                     # pitch padding untouched
+    finally:
+        lib.mlb_set_option(b"rows_engine", 0)
