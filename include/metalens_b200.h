@@ -146,8 +146,10 @@ int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, i
  * P[(q + out_roll) % N][c] of mlb_ff_epilogue (nearfield_farfield.py:135-189; ux has N entries in the
  * OUTPUT row order, uy n_cols entries).  The 4 x N x n_cols aperture sums never go to memory unless h_Fhat
  * (4 device pointers, pitch ldf) is given.  block_sums receives mlb_fft_cols_power_blocks(N, n_cols) partial
- * sums of the finite P values (query it after any mlb_set_option call).  Powers of two 256..2048 only:
- * mlb_fft_cols_power_blocks returns 0 for every other length and the caller uses mlb_fft_cols + mlb_ff_epilogue.
+ * sums of the finite P values (query it after any mlb_set_option call).  Powers of two 256..8192 with the
+ * radix-16 column engine (cols_engine = 1; lengths >= 4096 run a first pass in place on in_f, which is therefore
+ * scratch; h_Fhat must be NULL), 256..2048 with the radix-4 one: mlb_fft_cols_power_blocks returns 0 for every other
+ * length and the caller uses mlb_fft_cols + mlb_ff_epilogue.
  */
 int mlb_fft_cols_power_blocks(int N, int n_cols);
 int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw, int out_roll,
@@ -159,6 +161,12 @@ int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols,
  *   rows_l2_evict_first  1 (default) = stream the aperture through L2 with an evict-first policy
  *   cols_power_wide      fused pass tile: 1 = 4096-point column tiles / 1024 threads, 0 = 2048 / 512,
  *                        -1 (default) = by length: wide from 1024 points up
+ *   rows_ring_kb         shared-memory ring of the TMA-fed row pass per CTA: 64 (default) or 128
+ *   rows_engine          0 = radix-4 shared-memory row kernels everywhere, 1 = radix-16 register kernels (256..8192
+ *                        points) everywhere, 2 (default) = radix-16 without a fold, TMA-fed fold+FFT kernel with one
+ *   cols_engine          0 = radix-4 column kernels, 1 (default) = radix-16 register kernels (256..8192 points; 4096 and
+ *                        8192 as 16 x 256/512 in two passes, the first in place on the INPUT buffer)
+ *   r16_occupancy        resident CTAs per SM the radix-16 kernels are compiled for: 0 (default: rows 4, columns 3), 2..4
  * mlb_get_option returns -1 for an unknown name. */
 int mlb_set_option(const char *name, int value);
 int mlb_get_option(const char *name);

@@ -129,6 +129,69 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
     }
 }
 
+// Two adjacent far-field points per thread (16-byte loads of the four aperture sums, 8-byte store of P): the
+// float32-output flavour for even row lengths.  Same arithmetic as ff_epilogue_kernel<true> except that
+// sin(theta) and the final quotient are formed in fp32 (relative error ~1e-7); the evanescent mask, the DC test
+// and the unit-system dependent scale stay in float64.  128 threads x 2 points keeps the block count (and the
+// block_sums layout) of mlb_ff_epilogue_blocks().
+__global__ void __launch_bounds__(EPI_THREADS / 2) ff_epilogue_x2_kernel(EpiArgs a) {
+    const long long n = ((long long)blockIdx.x * (EPI_THREADS / 2) + threadIdx.x) * 2;
+    const long long total = (long long)a.Kx * a.Ky;
+    double sum = 0.0;
+    if (n < total) {
+        const int i = (int)(n / a.Ky), j = (int)(n % a.Ky);
+        const double ux = a.ux[i];
+        const double2 uy2v = *reinterpret_cast<const double2 *>(a.uy + j);
+        const size_t off = (size_t)i * a.ldf + j;
+        const float4 fex = *reinterpret_cast<const float4 *>(a.F[0] + off), fey = *reinterpret_cast<const float4 *>(a.F[1] + off);
+        const float4 fhx = *reinterpret_cast<const float4 *>(a.F[2] + off), fhy = *reinterpret_cast<const float4 *>(a.F[3] + off);
+        const double ux2 = __dmul_rn(ux, ux);
+        const float Zf = (float)a.Z;
+        const double scale = a.pref * a.amp_scale * a.amp_scale * 2.0;
+        float *dst = reinterpret_cast<float *>(a.P) + (size_t)i * a.ldp + j;
+        float pf[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double uy = q ? uy2v.y : uy2v.x;
+            const cfl ex = q ? cfl{fex.z, fex.w} : cfl{fex.x, fex.y}, ey = q ? cfl{fey.z, fey.w} : cfl{fey.x, fey.y};
+            const cfl hx = q ? cfl{fhx.z, fhx.w} : cfl{fhx.x, fhx.y}, hy = q ? cfl{fhy.z, fhy.w} : cfl{fhy.x, fhy.y};
+            const double uyy = __dmul_rn(uy, uy);
+            const double uz2 = __dsub_rn(__dsub_rn(1.0, ux2), uyy);              // as numpy: bit-identical NaN mask
+            const float uzf = (uz2 < 0.0) ? CUDART_NAN_F : sqrtf((float)uz2);
+            float px = 1.f, py = 0.f;                                            // DC bin: Cartesian components (:161-169)
+            if (!(ux == 0.0 && uy == 0.0)) {
+                const float inv = 1.0f / (sqrtf((float)__dadd_rn(ux2, uyy)) + 1e-9f);
+                px = (float)ux * inv; py = (float)uy * inv;
+            }
+            const float cx = px * uzf, cy = py * uzf;
+            // t1 = L_phi + Z N_theta, t2 = L_theta - Z N_phi with N = (-Fhy, Fhx), L = (Fey, -Fex)
+            const cfl t1 = {-px * ex.re - py * ey.re + Zf * (cy * hx.re - cx * hy.re),
+                            -px * ex.im - py * ey.im + Zf * (cy * hx.im - cx * hy.im)};
+            const cfl t2 = {cx * ey.re - cy * ex.re - Zf * (px * hx.re + py * hy.re),
+                            cx * ey.im - cy * ex.im - Zf * (px * hx.im + py * hy.im)};
+            const float qf = (fabs2(t1) + fabs2(t2)) / (uzf + 1e-5f);
+            const double p = scale * (double)qf;
+            pf[q] = (float)p;
+            if (a.accumulate) pf[q] += dst[q];
+            if (isfinite(pf[q])) sum += p;
+        }
+        *reinterpret_cast<float2 *>(dst) = make_float2(pf[0], pf[1]);
+    }
+    if (a.block_sums) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __shared__ double ws[EPI_THREADS / 64];
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < EPI_THREADS / 64; ++w) s += ws[w];
+            a.block_sums[blockIdx.x] = s;
+        }
+    }
+}
+
 // Figure-of-merit reduction: per-block sums of P over (a) all finite bins and
 // (b) the finite bins inside a cone (ux-ux0)^2 + (uy-uy0)^2 <= radius^2 around a target direction.
 template <typename T>
@@ -209,7 +272,11 @@ extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const doub
     a.pref = k * k / (32 * pi * pi * a.Z);                                  // :184
     a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double & 1; a.accumulate = (p_is_double >> 1) & 1;
     p_is_double &= 1;
+    bool x2 = !p_is_double && Ky % 2 == 0 && ldf % 2 == 0 && ldp % 2 == 0 && (reinterpret_cast<uintptr_t>(P) & 7u) == 0 &&
+              mlb::aligned16(uy);
+    for (int f = 0; f < 4; ++f) x2 = x2 && mlb::aligned16(a.F[f]);
     if (p_is_double) mlb::ff_epilogue_kernel<false><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
+    else if (x2) mlb::ff_epilogue_x2_kernel<<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS / 2, 0, (cudaStream_t)stream>>>(a);
     else mlb::ff_epilogue_kernel<true><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_ff_epilogue");
 }

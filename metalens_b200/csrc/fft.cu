@@ -905,8 +905,11 @@ __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
 
 // tuning knobs (mlb_fft_tune): rows-pass loader variant, lanes and threads; defaults chosen on B200
 static int g_rows_per_sm = 0;          // TMA row pass: resident CTAs per SM (0 = as many as fit, at most 3)
-static int g_rows_engine = 0;          // row pass: 0 = radix-4 shared-memory kernels (TMA-fed where possible), 1 = radix-16
-                                       // register kernels (256..8192 points), 2 = radix-16 only without a fold
+static int g_rows_engine = 2;          // row pass: 0 = radix-4 shared-memory kernels (TMA-fed where possible), 1 = radix-16
+                                       // register kernels (256..8192 points), 2 = radix-16 only without a fold (default:
+                                       // the TMA-fed fold+FFT kernel stays the choice when the aperture is folded)
+static int g_r16_occ = 0;              // radix-16 kernels: resident CTAs per SM they are compiled for (0 = default, 2..4)
+static int g_cols_engine = 1;          // column pass: 0 = radix-4 shared-memory kernels, 1 = radix-16 register kernels (256..8192; default)
 static int g_rows_ring_kb = 64;        // TMA row pass: bytes of shared memory in the slot ring per CTA (64 or 128 KB)
 static int g_rows_evict_first = 1;     // TMA row pass: stream the aperture through L2 with an evict-first policy
 static int g_cols_power_wide = -1;     // fused column+power pass: 1 = 4096-point tiles / 1024 threads, 0 = 2048 / 512,
@@ -973,6 +976,8 @@ extern "C" int mlb_set_option(const char *name, int value) {
     if (n == "rows_ctas_per_sm") { MLB_REQUIRE(value >= 0 && value <= 3, "rows_ctas_per_sm: 0..3"); mlb::g_rows_per_sm = value; }
     else if (n == "rows_l2_evict_first") mlb::g_rows_evict_first = value ? 1 : 0;
     else if (n == "rows_engine") { MLB_REQUIRE(value >= 0 && value <= 2, "rows_engine: 0..2"); mlb::g_rows_engine = value; }
+    else if (n == "r16_occupancy") { MLB_REQUIRE(value == 0 || (value >= 2 && value <= 4), "r16_occupancy: 0, 2..4"); mlb::g_r16_occ = value; }
+    else if (n == "cols_engine") { MLB_REQUIRE(value >= 0 && value <= 1, "cols_engine: 0..1"); mlb::g_cols_engine = value; }
     else if (n == "rows_ring_kb") { MLB_REQUIRE(value == 64 || value == 128, "rows_ring_kb: 64 or 128"); mlb::g_rows_ring_kb = value; }
     else if (n == "cols_power_wide") mlb::g_cols_power_wide = value < 0 ? -1 : (value ? 1 : 0);
     else MLB_REQUIRE(false, "mlb_set_option: unknown option '%s'", name);
@@ -986,6 +991,8 @@ extern "C" int mlb_get_option(const char *name) {
     if (n == "rows_l2_evict_first") return mlb::g_rows_evict_first;
     if (n == "rows_ring_kb") return mlb::g_rows_ring_kb;
     if (n == "rows_engine") return mlb::g_rows_engine;
+    if (n == "cols_engine") return mlb::g_cols_engine;
+    if (n == "r16_occupancy") return mlb::g_r16_occ;
     if (n == "cols_power_wide") return mlb::g_cols_power_wide;
     return -1;
 }
@@ -1066,7 +1073,25 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
             set_ = true;                                                                                             \
         }                                                                                                            \
         dim3 g16((n_rows + L - 1) / L, batch);                                                                       \
-        mlb::fft16_rows_kernel<LG><<<g16, T, smem16, st>>>(r);                                                       \
+        static bool set3_ = false, set4_ = false;                                                                    \
+        if (mlb::g_r16_occ == 3 || ((mlb::g_r16_occ == 2 || mlb::g_r16_occ == 0) && LG == 13)) {                                              \
+            constexpr int MB = (LG == 13) ? 2 : 3;                                                                   \
+            if (!set3_) {                                                                                            \
+                MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_rows_kernel<LG, MB>,                                        \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
+                set3_ = true;                                                                                        \
+            }                                                                                                        \
+            mlb::fft16_rows_kernel<LG, MB><<<g16, T, smem16, st>>>(r);                                               \
+        } else if ((mlb::g_r16_occ == 4 || mlb::g_r16_occ == 0) && LG < 13) {                                                                 \
+            if (!set4_) {                                                                                            \
+                MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_rows_kernel<LG, 4>,                                         \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
+                set4_ = true;                                                                                        \
+            }                                                                                                        \
+            mlb::fft16_rows_kernel<LG, 4><<<g16, T, smem16, st>>>(r);                                                \
+        } else {                                                                                                     \
+            mlb::fft16_rows_kernel<LG><<<g16, T, smem16, st>>>(r);                                                   \
+        }                                                                                                            \
         return mlb::check_launch("mlb_fft_rows(radix 16)");                                                          \
     }
         switch (a.lgN) { MLB_R16_ROWS(8) MLB_R16_ROWS(9) MLB_R16_ROWS(10) MLB_R16_ROWS(11) MLB_R16_ROWS(12) MLB_R16_ROWS(13) }
@@ -1178,6 +1203,63 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1; a.evict_first = 0;
+    if (mlb::g_cols_engine == 1 && a.lgN >= 8 && a.lgN <= 13) {
+        // radix-16 register kernels: direct up to 2048 points; 4096 / 8192 = 16 x (256 / 512) in two passes, the
+        // first of them in place on the INPUT buffer (which is therefore scratch, as with the radix-4 four-step)
+        cudaStream_t st = (cudaStream_t)stream;
+        mlb::R16ColArgs r;
+        for (int b = 0; b < 4; ++b) { r.in[b] = a.in[b]; r.out[b] = a.out[b]; }
+        r.ld_in = ld_in; r.ld_out = ld_out; r.n_cols = n_cols; r.lgNtot = a.lgN; r.roll = out_roll;
+        int lgSub = a.lgN, groups = 1;
+        if (a.lgN >= 12) {
+            for (int b = 0; b < batch; ++b)
+                MLB_REQUIRE(a.in[b] != a.out[b], "mlb_fft_cols: N >= 4096 needs out != in (the input is used as scratch)");
+            lgSub = a.lgN - 4; groups = 16;
+            mlb::R16FirstArgs f;
+            for (int b = 0; b < 4; ++b) f.data[b] = const_cast<float2 *>(a.in[b]);
+            f.tw = a.tw; f.ld = ld_in; f.n_cols = n_cols; f.B = 1 << lgSub;
+            dim3 gf((n_cols + 31) / 32, (f.B + 7) / 8, batch);
+            mlb::fft16_cols_first_kernel<<<gf, 256, 0, st>>>(f);
+            if (int rc = mlb::check_launch("mlb_fft_cols(radix-16 first pass)")) return rc;
+            r.in_gs = 1 << lgSub; r.in_rs = 1; r.out_gs = 1; r.out_rs = 16;
+        } else {
+            r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+        }
+        r.tw = a.tw;
+#define MLB_R16_COLS(LG, CL)                                                                                          \
+    case LG: {                                                                                                       \
+        constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);                     \
+        const size_t smem16 = (size_t)CL * PITCH * sizeof(float2);                                                   \
+        static bool set_ = false;                                                                                    \
+        if (!set_) {                                                                                                 \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem16));                                                             \
+            set_ = true;                                                                                             \
+        }                                                                                                            \
+        dim3 gc((n_cols + CL - 1) / CL, groups, batch);                                                              \
+        static bool set3_ = false, set4_ = false;                                                                    \
+        if ((mlb::g_r16_occ == 3 || mlb::g_r16_occ == 0) && T <= 256) {                                                                       \
+            if (!set3_) {                                                                                            \
+                MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_kernel<LG, CL, 3>,                                     \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
+                set3_ = true;                                                                                        \
+            }                                                                                                        \
+            mlb::fft16_cols_kernel<LG, CL, 3><<<gc, T, smem16, st>>>(r);                                             \
+        } else if (mlb::g_r16_occ == 4 && T <= 256) {                                                                \
+            if (!set4_) {                                                                                            \
+                MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_kernel<LG, CL, 4>,                                     \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
+                set4_ = true;                                                                                        \
+            }                                                                                                        \
+            mlb::fft16_cols_kernel<LG, CL, 4><<<gc, T, smem16, st>>>(r);                                             \
+        } else {                                                                                                     \
+            mlb::fft16_cols_kernel<LG, CL><<<gc, T, smem16, st>>>(r);                                                \
+        }                                                                                                            \
+        return mlb::check_launch("mlb_fft_cols(radix 16)");                                                          \
+    }
+        switch (lgSub) { MLB_R16_COLS(8, 16) MLB_R16_COLS(9, 8) MLB_R16_COLS(10, 4) MLB_R16_COLS(11, 4) }
+#undef MLB_R16_COLS
+    }
     if (a.lgN >= 12) {
         for (int b = 0; b < batch; ++b)
             MLB_REQUIRE(a.in[b] != a.out[b], "mlb_fft_cols: N >= 4096 needs out != in (the input is used as scratch)");
@@ -1241,19 +1323,80 @@ static int cols_power_tile(int N) {
     const bool wide = mlb::g_cols_power_wide < 0 ? (N >= 1024) : (mlb::g_cols_power_wide != 0);
     return (wide ? 4096 : 2048) / N;
 }
+// radix-16 engine: sub-transform length (N itself up to 2048, N/16 above), its column tile and group count
+static bool r16_power_shape(int N, int *lgSub, int *cl, int *groups) {
+    if (!mlb::is_pow2(N) || N < 256 || N > 8192) return false;
+    const int lg = mlb::ilog2(N);
+    *lgSub = lg >= 12 ? lg - 4 : lg;
+    *groups = lg >= 12 ? 16 : 1;
+    *cl = 4096 >> *lgSub;                       // 256 threads per CTA: 16, 8, 4, 2 columns
+    return true;
+}
 
 extern "C" int mlb_fft_cols_power_blocks(int N, int n_cols) {
+    if (n_cols <= 0) return 0;
+    if (mlb::g_cols_engine == 1) {
+        int lgSub, cl, groups;
+        if (!r16_power_shape(N, &lgSub, &cl, &groups)) return 0;
+        return groups * ((n_cols + cl - 1) / cl);
+    }
     const int cl = cols_power_tile(N);
-    return (cl && n_cols > 0) ? (n_cols + cl - 1) / cl : 0;
+    return cl ? (n_cols + cl - 1) / cl : 0;
 }
 
 extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw,
                                   int out_roll, const double *ux, const double *uy, double amp_scale,
                                   double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
                                   double *block_sums, mlb_c64 *const *h_Fhat, int ldf, void *stream) {
+    MLB_REQUIRE(h_in && tw && ux && uy && P, "mlb_fft_cols_power: NULL pointer");
+    if (mlb::g_cols_engine == 1 && !h_Fhat) {
+        int lgSub, cl16, groups;
+        MLB_REQUIRE(r16_power_shape(N, &lgSub, &cl16, &groups), "mlb_fft_cols_power: length %d must be a power of two in 256..8192", N);
+        MLB_REQUIRE(n_cols > 0 && ld_in >= n_cols && ldp >= n_cols && out_roll >= 0 && out_roll < N, "mlb_fft_cols_power: bad sizes");
+        MLB_REQUIRE(wavelength > 0 && n_glass > 0 && Z0 > 0, "mlb_fft_cols_power: bad physical constants");
+        cudaStream_t st16 = (cudaStream_t)stream;
+        mlb::R16PowerArgs r;
+        for (int f = 0; f < 4; ++f) {
+            MLB_REQUIRE(h_in[f] != nullptr, "mlb_fft_cols_power: field %d is NULL", f);
+            r.in[f] = reinterpret_cast<const float2 *>(h_in[f]);
+        }
+        r.tw = reinterpret_cast<const float2 *>(tw);
+        r.ux = ux; r.uy = uy; r.P = P; r.block_sums = block_sums;
+        const double pi16 = 3.14159265358979323846, Zd16 = Z0 / n_glass, k16 = 2 * pi16 * n_glass / wavelength;
+        r.scale = k16 * k16 / (32 * pi16 * pi16 * Zd16) * amp_scale * amp_scale * 2.0;
+        r.Z = (float)Zd16;
+        r.ld_in = ld_in; r.ldp = ldp; r.n_cols = n_cols; r.lgNtot = mlb::ilog2(N); r.accumulate = accumulate ? 1 : 0;
+        r.roll = out_roll;
+        if (groups > 1) {               // first pass of the 16 x B decomposition, in place on the inputs
+            mlb::R16FirstArgs f1;
+            for (int f = 0; f < 4; ++f) f1.data[f] = const_cast<float2 *>(r.in[f]);
+            f1.tw = r.tw; f1.ld = ld_in; f1.n_cols = n_cols; f1.B = 1 << lgSub;
+            dim3 gf((n_cols + 31) / 32, (f1.B + 7) / 8, 4);
+            mlb::fft16_cols_first_kernel<<<gf, 256, 0, st16>>>(f1);
+            if (int rc = mlb::check_launch("mlb_fft_cols_power(radix-16 first pass)")) return rc;
+            r.in_gs = 1 << lgSub; r.in_rs = 1; r.out_gs = 1; r.out_rs = 16;
+        } else {
+            r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+        }
+#define MLB_R16_CP(LG, CL)                                                                                            \
+    case LG: {                                                                                                       \
+        constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);                     \
+        const size_t smem16 = (size_t)CL * PITCH * sizeof(float2) + (size_t)16 * T * (sizeof(float2) + sizeof(float)); \
+        static bool set_ = false;                                                                                    \
+        if (!set_) {                                                                                                 \
+            MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_power_kernel<LG, CL>,                                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));                \
+            set_ = true;                                                                                             \
+        }                                                                                                            \
+        dim3 gc((n_cols + CL - 1) / CL, groups);                                                                     \
+        mlb::fft16_cols_power_kernel<LG, CL><<<gc, T, smem16, st16>>>(r);                                            \
+        return mlb::check_launch("mlb_fft_cols_power(radix 16)");                                                    \
+    }
+        switch (lgSub) { MLB_R16_CP(8, 16) MLB_R16_CP(9, 8) MLB_R16_CP(10, 4) MLB_R16_CP(11, 2) }
+#undef MLB_R16_CP
+    }
     const int cl = cols_power_tile(N);
     MLB_REQUIRE(cl > 0, "mlb_fft_cols_power: length %d must be a power of two in 256..2048", N);
-    MLB_REQUIRE(h_in && tw && ux && uy && P, "mlb_fft_cols_power: NULL pointer");
     MLB_REQUIRE(n_cols > 0 && ld_in >= n_cols && ldp >= n_cols && out_roll >= 0 && out_roll < N,
                 "mlb_fft_cols_power: bad sizes");
     MLB_REQUIRE(wavelength > 0 && n_glass > 0 && Z0 > 0, "mlb_fft_cols_power: bad physical constants");

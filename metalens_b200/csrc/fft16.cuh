@@ -21,6 +21,7 @@
 // 8192 = 16.16.16.2.  Stage twiddles are powers of one table entry W_N^(k N/(Ns R)) (float64-built table),
 // multiplied up along the binary expansion of r (at most 3 products deep).
 #pragma once
+#include <math_constants.h>
 
 namespace mlb {
 
@@ -127,17 +128,17 @@ __device__ __forceinline__ void apply_twiddle_powers(float2 (&v)[R], float2 w1) 
 // radix of stage S of a 2^LGN-point transform (see the table in the header comment) and stage count
 template <int LGN, int S>
 struct R16Radix {
-    static constexpr int rem = LGN - 8;
-    static constexpr int value = (S < 2) ? 16 : (S == 2 ? (rem >= 4 ? 16 : (1 << rem)) : (1 << (rem - 4)));
+    static constexpr int bits = LGN - 4 * S;              // bits left before stage S: radix 16 while >= 4 remain
+    static constexpr int value = (bits >= 4) ? 16 : (1 << bits);
 };
 template <int LGN>
-struct R16Stages { static constexpr int value = (LGN == 8) ? 2 : (LGN <= 12 ? 3 : 4); };
+struct R16Stages { static constexpr int value = (LGN + 3) / 4; };
 
 template <int R> struct Lg2 { static constexpr int value = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1; };
 
 // the butterflies of one stage on the thread's 16 register slots; t = thread index within the transform
 template <int LGN, int LGNS, int R>
-__device__ __forceinline__ void r16_butterflies(float2 (&a)[16], int t, const float2 *__restrict__ tw) {
+__device__ __forceinline__ void r16_butterflies(float2 (&a)[16], int t, const float2 *__restrict__ tw, int tws) {
     constexpr int TR = 1 << (LGN - 4), B = 16 / R, Ns = 1 << LGNS;
 #pragma unroll
     for (int b = 0; b < B; ++b) {
@@ -146,7 +147,8 @@ __device__ __forceinline__ void r16_butterflies(float2 (&a)[16], int t, const fl
         for (int r = 0; r < R; ++r) v[r] = a[b + B * r];
         if constexpr (LGNS > 0) {
             const int k = (t + b * TR) & (Ns - 1);
-            apply_twiddle_powers<R>(v, __ldg(tw + (k << (LGN - LGNS - Lg2<R>::value))));   // W_{Ns R}^k
+            // W_{Ns R}^k from the table W_{N 2^tws}^t (tws > 0: table of a longer transform this one is part of)
+            apply_twiddle_powers<R>(v, __ldg(tw + ((k << (LGN - LGNS - Lg2<R>::value)) << tws)));
         }
         dft_reg<R>(v);
 #pragma unroll
@@ -165,9 +167,10 @@ __device__ __forceinline__ int r16_out_index(int t, int b, int q) {
 // runs stages S.. on the thread's registers, exchanging through `sm` (this transform's padded buffer);
 // on return `a` holds the outputs of the LAST stage (slot b + B q = output q of butterfly b)
 template <int LGN, int S, int LGNS, typename Sync>
-__device__ __forceinline__ void r16_stages(float2 (&a)[16], int t, float2 *sm, const float2 *__restrict__ tw, Sync sync) {
+__device__ __forceinline__ void r16_stages(float2 (&a)[16], int t, float2 *sm, const float2 *__restrict__ tw, int tws,
+                                           Sync sync) {
     constexpr int R = R16Radix<LGN, S>::value, B = 16 / R, TR = 1 << (LGN - 4);
-    r16_butterflies<LGN, LGNS, R>(a, t, tw);
+    r16_butterflies<LGN, LGNS, R>(a, t, tw, tws);
     if constexpr (S + 1 < R16Stages<LGN>::value) {
         if constexpr (S > 0) sync();                      // everyone has read the previous contents
 #pragma unroll
@@ -177,7 +180,7 @@ __device__ __forceinline__ void r16_stages(float2 (&a)[16], int t, float2 *sm, c
         sync();
 #pragma unroll
         for (int m = 0; m < 16; ++m) a[m] = sm[pad16(t + m * TR)];
-        r16_stages<LGN, S + 1, LGNS + Lg2<R>::value>(a, t, sm, tw, sync);
+        r16_stages<LGN, S + 1, LGNS + Lg2<R>::value>(a, t, sm, tw, tws, sync);
     }
 }
 
@@ -201,8 +204,8 @@ struct R16Args {
 
 // rows: transform along the contiguous axis; L = threads / (N/16) rows per CTA.  The loader sums the s1 x s2
 // aliased copies (aperture fold) and applies the input fftshift; the output fftshift is a roll at store time.
-template <int LGN>
-__global__ void __launch_bounds__(R16Threads<LGN>::value, (LGN >= 13) ? 1 : 2) fft16_rows_kernel(const R16Args a) {
+template <int LGN, int MINB = ((LGN >= 13) ? 1 : 2)>
+__global__ void __launch_bounds__(R16Threads<LGN>::value, MINB) fft16_rows_kernel(const R16Args a) {
     constexpr int N = 1 << LGN, TR = N >> 4, T = R16Threads<LGN>::value, L = T / TR, PITCH = N + (N >> 4) + 1;
     extern __shared__ __align__(16) float2 fsm16[];
     const int tid = threadIdx.x, lane = tid / TR, t = tid - lane * TR;
@@ -237,12 +240,179 @@ __global__ void __launch_bounds__(R16Threads<LGN>::value, (LGN >= 13) ? 1 : 2) f
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m] = make_float2(0.f, 0.f);
     }
-    r16_stages<LGN, 0, 0>(v, t, sm, a.tw, [] { __syncthreads(); });
+    r16_stages<LGN, 0, 0>(v, t, sm, a.tw, 0, [] { __syncthreads(); });
     if (live) {
         float2 *dst = out + (size_t)r * a.ld_out;
 #pragma unroll
         for (int m = 0; m < 16; ++m) dst[(r16_final_index<LGN>(t, m) + a.out_roll) & (N - 1)] = v[m];
     }
+}
+
+// columns: transform along the strided axis, CL adjacent columns per CTA (8*CL-byte row segments), each column
+// with its own padded shared-memory buffer.  Serves the direct column pass (g = 0) and the second pass of the
+// long-transform decomposition below: sub-transform g reads rows g*in_gs + n*in_rs and stores output q at row
+// (g*out_gs + q*out_rs + roll) mod Ntot.
+struct R16ColArgs {
+    const float2 *in[4];
+    float2 *out[4];
+    const float2 *tw;                 // plain table W_Ntot^t of the FULL length (sub-transforms index it with a stride)
+    int ld_in, ld_out, n_cols, lgNtot;
+    int in_gs, in_rs, out_gs, out_rs, roll;
+};
+
+template <int LGN, int CL, int MINB = ((CL * (1 << (LGN - 4)) <= 256) ? 2 : 1)>
+__global__ void __launch_bounds__(CL * (1 << (LGN - 4)), MINB) fft16_cols_kernel(const R16ColArgs a) {
+    constexpr int N = 1 << LGN, TR = N >> 4, PITCH = N + (N >> 4) + 32 / CL;
+    extern __shared__ __align__(16) float2 fsm16[];
+    const int tid = threadIdx.x, lane = tid % CL, t = tid / CL;
+    const int c = blockIdx.x * CL + lane, g = blockIdx.y;
+    const bool live = c < a.n_cols;
+    const float2 *__restrict__ in = pick4(a.in, blockIdx.z);
+    float2 *__restrict__ out = pick4(a.out, blockIdx.z);
+    float2 *sm = fsm16 + lane * PITCH;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+        v[m] = live ? in[(size_t)(g * a.in_gs + (t + m * TR) * a.in_rs) * a.ld_in + c] : make_float2(0.f, 0.f);
+    r16_stages<LGN, 0, 0>(v, t, sm, a.tw, a.lgNtot - LGN, [] { __syncthreads(); });
+    if (live) {
+        const int mask = (1 << a.lgNtot) - 1;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int orow = (g * a.out_gs + r16_final_index<LGN>(t, m) * a.out_rs + a.roll) & mask;
+            out[(size_t)orow * a.ld_out + c] = v[m];
+        }
+    }
+}
+
+// Fused column pass + radiated power on the radix-16 engine: the CTA transforms its CL columns of ALL FOUR
+// fields one after the other and accumulates, per far-field point, only
+//     t1 = L_phi + Z N_theta = -px Fex - py Fey + Z cy Fhx - Z cx Fhy
+//     t2 = L_theta - Z N_phi = -cy Fex + cx Fey - Z px Fhx - Z py Fhy      (nearfield_farfield.py:158-167, :184)
+// ((px,py) = (ux,uy)/(sin(theta)+1e-9), (cx,cy) = (px,py) uz; DC bin (:161-169): (1,0,1,0)); then
+// P = k^2/(32 pi^2 Z)(|t1|^2+|t2|^2)/(uz+1e-5) * 2 (:184-189) goes straight from registers to memory, so the
+// aperture sums are never stored.  The projection coefficients of the thread's 16 points are computed once
+// (float64 evanescent mask / DC test as in ff_epilogue_kernel) and parked in thread-private shared memory.
+struct R16PowerArgs {
+    const float2 *in[4];
+    const float2 *tw;
+    const double *ux, *uy;
+    float *P;
+    double *block_sums;
+    double scale;                     // pref * amp_scale^2 * 2
+    float Z;
+    int ld_in, ldp, n_cols, lgNtot, accumulate;
+    int in_gs, in_rs, out_gs, out_rs, roll;
+};
+
+template <int LGN, int CL>
+__global__ void __launch_bounds__(CL * (1 << (LGN - 4)), 2) fft16_cols_power_kernel(const R16PowerArgs a) {
+    constexpr int N = 1 << LGN, TR = N >> 4, T = CL * TR, PITCH = N + (N >> 4) + 32 / CL;
+    extern __shared__ __align__(16) float2 fsm16[];
+    float2 *cP = fsm16 + CL * PITCH;                               // [16][T] (px, py) of the thread's points
+    float *cZ = reinterpret_cast<float *>(cP + 16 * T);            // [16][T] uz
+    const int tid = threadIdx.x, lane = tid % CL, t = tid / CL;
+    const int c = blockIdx.x * CL + lane, g = blockIdx.y;
+    const bool live = c < a.n_cols;
+    float2 *sm = fsm16 + lane * PITCH;
+    const int mask = (1 << a.lgNtot) - 1;
+    const double uy = live ? a.uy[c] : 0.0;
+    const double uy2 = __dmul_rn(uy, uy);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int orow = (g * a.out_gs + r16_final_index<LGN>(t, m) * a.out_rs + a.roll) & mask;
+        const double ux = a.ux[orow];
+        // uz^2 exactly as numpy evaluates (1 - ux**2 - uy**2): bit-identical evanescent mask (:153-155)
+        const double ux2 = __dmul_rn(ux, ux);
+        const double uz2 = __dsub_rn(__dsub_rn(1.0, ux2), uy2);
+        float px = 1.f, py = 0.f;
+        if (!(ux == 0.0 && uy == 0.0)) {
+            const float inv = 1.0f / ((float)sqrt(__dadd_rn(ux2, uy2)) + 1e-9f);
+            px = (float)ux * inv; py = (float)uy * inv;
+        }
+        cP[m * T + tid] = make_float2(px, py);
+        cZ[m * T + tid] = (uz2 < 0.0) ? CUDART_NAN_F : sqrtf((float)uz2);
+    }
+    float2 t1[16], t2[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) t1[m] = t2[m] = make_float2(0.f, 0.f);
+    const float Z = a.Z;
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        const float2 *__restrict__ in = pick4(a.in, f);
+        float2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            v[m] = live ? in[(size_t)(g * a.in_gs + (t + m * TR) * a.in_rs) * a.ld_in + c] : make_float2(0.f, 0.f);
+        if (f > 0) __syncthreads();                                // the previous field's exchange buffer is free
+        r16_stages<LGN, 0, 0>(v, t, sm, a.tw, a.lgNtot - LGN, [] { __syncthreads(); });
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const float2 p = cP[m * T + tid];
+            const float uz = cZ[m * T + tid];
+            const float cx = p.x * uz, cy = p.y * uz;
+            float k1, k2;
+            if (f == 0) { k1 = -p.x; k2 = -cy; }                   // Ex:  L_y = -Fex
+            else if (f == 1) { k1 = -p.y; k2 = cx; }               // Ey:  L_x =  Fey
+            else if (f == 2) { k1 = Z * cy; k2 = -(Z * p.x); }     // Hx:  N_y =  Fhx
+            else { k1 = -(Z * cx); k2 = -(Z * p.y); }              // Hy:  N_x = -Fhy
+            t1[m].x = fmaf(k1, v[m].x, t1[m].x); t1[m].y = fmaf(k1, v[m].y, t1[m].y);
+            t2[m].x = fmaf(k2, v[m].x, t2[m].x); t2[m].y = fmaf(k2, v[m].y, t2[m].y);
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int orow = (g * a.out_gs + r16_final_index<LGN>(t, m) * a.out_rs + a.roll) & mask;
+        const float mag = t1[m].x * t1[m].x + t1[m].y * t1[m].y + t2[m].x * t2[m].x + t2[m].y * t2[m].y;
+        const double p = a.scale * (double)mag / ((double)cZ[m * T + tid] + 1e-5);
+        if (live) {
+            float pf = (float)p;
+            float *dst = a.P + (size_t)orow * a.ldp + c;
+            if (a.accumulate) pf += *dst;                          // incoherent sum over sources
+            *dst = pf;
+            if (isfinite(pf)) sum += p;
+        }
+    }
+    if (a.block_sums) {                                            // :74 total_P over finite bins
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __shared__ double ws[T / 32];
+        if ((tid & 31) == 0) ws[tid >> 5] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < T / 32; ++w) s += ws[w];
+            a.block_sums[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// Long column transforms (N = 16 B, B = 256 or 512), first pass: for every n2 < B a 16-point DFT over rows
+// n2 + n1 B entirely in registers, times W_N^(n2 k1), stored IN PLACE at row k1 B + n2.  No shared memory:
+// a warp is 32 adjacent columns, so every access is a 256-byte row segment.  The second pass
+// (fft16_cols_kernel with in_gs = B, out_rs = 16) transforms the B contiguous rows of each k1:
+//     X[k1 + 16 k2] = sum_n2 W_B^(n2 k2) [ W_N^(n2 k1) sum_n1 x[B n1 + n2] W_16^(n1 k1) ]
+struct R16FirstArgs {
+    float2 *data[4];
+    const float2 *tw;                 // plain table W_N^t of the FULL length N
+    int ld, n_cols, B;
+};
+
+__global__ void __launch_bounds__(256) fft16_cols_first_kernel(const R16FirstArgs a) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int n2 = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (c >= a.n_cols || n2 >= a.B) return;
+    float2 *__restrict__ d = pick4(a.data, blockIdx.z) + (size_t)n2 * a.ld + c;
+    const size_t step = (size_t)a.B * a.ld;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = d[m * step];
+    dft_reg<16>(v);
+    apply_twiddle_powers<16>(v, __ldg(a.tw + n2));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) d[m * step] = v[m];
 }
 
 }  // namespace mlb

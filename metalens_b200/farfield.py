@@ -88,9 +88,10 @@ class FarfieldPlan:
     rows : optional (row0, row1): compute only that slab of far-field rows (ux indices) -- the
         multi-GPU tile of metalens_b200/sharding.py.  Supported by 'dense' and 'fold', whose work
         scales with the slab; the FFT passes produce all rows at once.
-    fuse_power : with method 'fft', float32 P and power-of-two column lengths 256..2048, run() uses the
+    fuse_power : with method 'fft', float32 P and power-of-two column lengths 256..1024, run() uses the
         fused column-pass + power kernel (mlb_fft_cols_power): the 4 x Kx x Ky aperture sums then stay in
-        registers; amplitudes() re-runs the unfused passes when asked.  False = always separate kernels.
+        registers; amplitudes() re-runs the unfused passes when asked.  False = always separate kernels,
+        'always' = fused for every length the kernel supports (up to 8192).
     """
 
     def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride=None, ux=None, uy=None,
@@ -104,7 +105,7 @@ class FarfieldPlan:
         self.wavelength, self.n_glass = float(wavelength), float(n_glass)
         assert p_dtype in (torch.float32, torch.float64)
         self.p_dtype = p_dtype
-        self._want_fused = bool(fuse_power)
+        self._want_fused = fuse_power if fuse_power == "always" else bool(fuse_power)
 
         if ux is None and uy is None:
             stride = 1 if stride is None else stride
@@ -199,8 +200,11 @@ class FarfieldPlan:
             for t, n in ((self.tw1, K1), (self.tw2, K2)):
                 _lib.check(self.lib.mlb_fft_twiddle(n, t.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
             self.AxT = self.Ay = None
+            # fused column pass + power: measured faster than column pass + epilogue up to 1024-point columns
+            # (above that the fused kernel's register footprint costs more than the saved round trip)
             self.fused = bool(self._want_fused and not self.two_pass_t and self.p_dtype == torch.float32
-                              and self.lib.mlb_fft_cols_power_blocks(K1, K2) > 0)
+                              and self.lib.mlb_fft_cols_power_blocks(K1, K2) > 0
+                              and (K1 <= 1024 or self._want_fused == "always"))
         else:
             # folded aperture (K1 x K2) and exact integer DFT twiddles exp(-2 pi i p q / K)
             K1, K2 = Mx // self.sx, My // self.sy
@@ -222,7 +226,7 @@ class FarfieldPlan:
         self._staged = False
         self.P = torch.empty((Kx, Ky), dtype=self.p_dtype, device=dev)
         self.nblocks = self.lib.mlb_ff_epilogue_blocks(Kx, Ky)
-        self.block_sums = torch.empty(max(self.nblocks, Ky), dtype=torch.float64, device=dev)
+        self.block_sums = torch.empty(max(self.nblocks, 2 * Ky + 16), dtype=torch.float64, device=dev)
         self.total = torch.zeros(1, dtype=torch.float64, device=dev)
         self.d_ux = torch.from_numpy(self.ux).to(dev)
         self.d_uy = torch.from_numpy(self.uy).to(dev)

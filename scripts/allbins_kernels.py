@@ -9,7 +9,11 @@ from metalens_b200.farfield import FarfieldPlan
 lib = _lib.load()
 engine = int(os.environ.get("ROWS_ENGINE", "0"))
 lib.mlb_set_option(b"rows_engine", engine)
-print("rows_engine", engine)
+cengine = int(os.environ.get("COLS_ENGINE", "0"))
+lib.mlb_set_option(b"cols_engine", cengine)
+occ = int(os.environ.get("R16_OCC", "0"))
+lib.mlb_set_option(b"r16_occupancy", occ)
+print("rows_engine", engine, "cols_engine", cengine, "r16_occupancy", occ)
 sizes = [int(a) for a in sys.argv[1:]] or [1024, 2048, 3375, 3600, 4096, 8192]
 wl, ng = 580e-9, 1.459
 d = wl / 2.2

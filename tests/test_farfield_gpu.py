@@ -199,9 +199,24 @@ def test_fold_matches_numpy():
             assert field_error(d[:, :K2].cpu().numpy(), ref) < 1e-6
 
 
-def test_fft_passes_match_numpy():
+@pytest.fixture
+def fft_engines(request):
+    """(rows_engine, cols_engine) for one test; the library defaults (2, 1) are restored afterwards."""
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    rows, cols = request.param
+    lib.mlb_set_option(b"rows_engine", rows)
+    lib.mlb_set_option(b"cols_engine", cols)
+    yield request.param
+    lib.mlb_set_option(b"rows_engine", 2)
+    lib.mlb_set_option(b"cols_engine", 1)
+
+
+@pytest.mark.parametrize("fft_engines", [(0, 0), (2, 1)], indirect=True, ids=["radix4", "radix16"])
+def test_fft_passes_match_numpy(fft_engines):
     """mlb_fft_rows / mlb_fft_cols against numpy.fft for every power of two up to the limit,
-    including the fftshift rolls."""
+    including the fftshift rolls; once with the radix-4 shared-memory kernels everywhere and once with the
+    default engines (radix-16 register kernels from 256 points up)."""
     from metalens_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(9)
@@ -535,22 +550,32 @@ def _same(a, b):
     return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
 
 
-@pytest.mark.parametrize("wide", [0, 1])
+@pytest.mark.parametrize("wide", [0, 1, 16])
 @pytest.mark.parametrize("shape,stride", [((256, 256), 1), ((1024, 1024), 4), ((1024, 2048), (4, 4)),
-                                          ((2048, 512), (2, 2)), ((2048, 1024), (1, 4)), ((512, 300), (1, 1))])
+                                          ((2048, 512), (2, 2)), ((2048, 1024), (1, 4)), ((512, 300), (1, 1)),
+                                          ((4096, 300), (1, 1)), ((8192, 150), (1, 1))])
 def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
-    """fft_cols_power_kernel (column pass + radiated power in one kernel, aperture sums never stored) against
-    the separate column pass + epilogue on the same plan geometry: same NaN mask, P and total_P to fp32
-    rounding; column lengths 256..2048, square and rectangular, ragged column counts, both tile widths."""
+    """Column pass + radiated power in one kernel (aperture sums never stored) against the separate column
+    pass + epilogue on the same plan geometry: same NaN mask, P and total_P to fp32 rounding; column lengths
+    256..2048 with the radix-4 kernel (fft_cols_power_kernel, both tile widths) and 256..8192 with the
+    radix-16 engine (fft16_cols_power_kernel, wide == 16); square and rectangular, ragged column counts."""
     from metalens_b200 import _lib
     from metalens_b200.farfield import FarfieldPlan
     lib = _lib.load()
     Mx, My = shape
+    if wide != 16 and Mx // (stride if np.isscalar(stride) else stride[0]) > 2048:
+        pytest.skip("the radix-4 fused kernel stops at 2048 points")
     Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(Mx, 71, WL, My=My)
     dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
-    lib.mlb_set_option(b"cols_power_wide", wide)
+    if wide == 16:
+        lib.mlb_set_option(b"cols_engine", 1)
+        lib.mlb_set_option(b"rows_engine", 2)
+    else:
+        lib.mlb_set_option(b"cols_engine", 0)
+        lib.mlb_set_option(b"rows_engine", 0)
+        lib.mlb_set_option(b"cols_power_wide", wide)
     try:
-        fused = FarfieldPlan((Mx, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=stride)
+        fused = FarfieldPlan((Mx, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=stride, fuse_power="always")
         plain = FarfieldPlan((Mx, My), x[1] - x[0], y[1] - y[0], WL, NG, stride=stride, fuse_power=False)
         assert fused.method == "fft" and fused.fused and not plain.fused
         assert [s[0] for s in fused.steps(dev)][-1] == "fft_cols_power"
@@ -572,6 +597,8 @@ def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
         assert abs(ta.item() - 2 * t2.item()) <= 4e-6 * abs(t2.item())
     finally:
         lib.mlb_set_option(b"cols_power_wide", -1)
+        lib.mlb_set_option(b"cols_engine", 1)
+        lib.mlb_set_option(b"rows_engine", 2)
 
 
 @pytest.mark.parametrize("name,stride", [("lens256_seed1", 1), ("lens256_seed1_rot", 1)])
@@ -595,11 +622,18 @@ def test_options_api():
     assert lib.mlb_set_option(b"no_such_option", 1) != 0
     assert b"unknown option" in lib.mlb_last_error()
     assert lib.mlb_set_option(b"rows_ctas_per_sm", 7) != 0
-    assert lib.mlb_fft_cols_power_blocks(1000, 64) == 0 and lib.mlb_fft_cols_power_blocks(4096, 64) == 0
-    lib.mlb_set_option(b"cols_power_wide", 0)
-    assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 512
-    lib.mlb_set_option(b"cols_power_wide", -1)
-    assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 256 and lib.mlb_fft_cols_power_blocks(512, 512) == 128
+    assert lib.mlb_fft_cols_power_blocks(1000, 64) == 0 and lib.mlb_fft_cols_power_blocks(16384, 64) == 0
+    assert lib.mlb_get_option(b"cols_engine") == 1 and lib.mlb_get_option(b"rows_engine") == 2
+    assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 256 and lib.mlb_fft_cols_power_blocks(8192, 64) == 16 * 8
+    lib.mlb_set_option(b"cols_engine", 0)
+    try:
+        assert lib.mlb_fft_cols_power_blocks(4096, 64) == 0
+        lib.mlb_set_option(b"cols_power_wide", 0)
+        assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 512
+        lib.mlb_set_option(b"cols_power_wide", -1)
+        assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 256 and lib.mlb_fft_cols_power_blocks(512, 512) == 128
+    finally:
+        lib.mlb_set_option(b"cols_engine", 1)
 
 
 @pytest.mark.parametrize("evict,per_sm", [(0, 0), (1, 1), (1, 2)])
@@ -695,4 +729,41 @@ def test_radix16_row_kernels_match_numpy():
             assert field_error(dres[1][:, :N].cpu().numpy(), 2 * ref) < 3e-6, (N, s1, s2)
             assert float(dres[0][:, N:].abs().max()) == 0.0                     # pitch padding untouched
     finally:
-        lib.mlb_set_option(b"rows_engine", 0)
+        lib.mlb_set_option(b"rows_engine", 2)
+
+
+def test_radix16_column_kernels_match_numpy():
+    """fft16_cols_kernel (direct, 256..2048 points) and the two-pass 16 x B decomposition for 4096 / 8192 points
+    (fft16_cols_first_kernel in place on the input + fft16_cols_kernel) against numpy.fft: output roll, ragged
+    column counts (partial column tiles), two fields per launch."""
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    lib.mlb_set_option(b"cols_engine", 1)
+    try:
+        for N, n_cols in ((256, 45), (512, 17), (1024, 9), (2048, 6), (4096, 37), (8192, 33), (1024, 64)):
+            a = [(rng.standard_normal((N, n_cols)) + 1j * rng.standard_normal((N, n_cols))).astype(np.complex64) for _ in range(2)]
+            tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
+            _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
+            ldc = n_cols + (n_cols & 1) + 2
+            din = [torch.zeros(N, ldc, dtype=torch.complex64).cuda() for _ in a]
+            for d, v in zip(din, a):
+                d[:, :n_cols].copy_(torch.from_numpy(v))
+            dout = [torch.zeros(N, ldc, dtype=torch.complex64).cuda() for _ in a]
+            ro = (N // 2 + 1) % N
+            pc, k3 = _lib.ptr_array(din)
+            po, k4 = _lib.ptr_array(dout)
+            if N >= 4096:
+                assert lib.mlb_fft_cols(pc, ldc, pc, ldc, N, n_cols, tw.data_ptr(), ro, 2, None) != 0   # needs out != in
+            _lib.check(lib.mlb_fft_cols(pc, ldc, po, ldc, N, n_cols, tw.data_ptr(), ro, 2, None), "r16 cols")
+            torch.cuda.synchronize()
+            for v, d in zip(a, dout):
+                ref = np.roll(np.fft.fft(v.astype(complex), axis=0), ro, axis=0)
+                assert field_error(d[:, :n_cols].cpu().numpy(), ref) < 3e-6, ("cols", N)
+                assert float(d[:, n_cols:].abs().max()) == 0.0
+            if N <= 2048:                                                   # in place is allowed for the direct pass
+                _lib.check(lib.mlb_fft_cols(pc, ldc, pc, ldc, N, n_cols, tw.data_ptr(), ro, 2, None), "r16 cols in place")
+                torch.cuda.synchronize()
+                assert torch.equal(din[0], dout[0]) and torch.equal(din[1], dout[1])
+    finally:
+        lib.mlb_set_option(b"cols_engine", 1)
