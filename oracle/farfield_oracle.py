@@ -119,6 +119,43 @@ def farfield_reference_path(Ex, Ey, Hx, Hy, xp_list, yp_list, wavelength, n_glas
     return farfield_from_fft(f[0], f[1], f[2], f[3], xp_list, yp_list, wavelength, n_glass)
 
 
+def farfield_reference_path_threads(Ex, Ey, Hx, Hy, xp_list, yp_list, wavelength, n_glass, workers,
+                                    points_at_a_time=1e7):
+    """farfield_reference_path() with its independent pieces spread over `workers` threads -- the
+    "all host cores" flavour of the CPU baseline.  Two things are independent in the reference itself:
+    the four caller-side fft2(fftshift(.)) calls (nearfield_farfield.py:18-20) and the uy-chunk loop of
+    farfield_from_nearfield (:45-66, chunks of `points_at_a_time`/num_x columns; here the chunk width is
+    additionally capped so that every worker has work).  numpy's pocketfft and ufunc loops release the
+    GIL, so plain threads scale.  Elementwise arithmetic is chunk-invariant and total_P is summed over the
+    assembled map exactly as at :74, so the result is bit-identical to farfield_reference_path()."""
+    from concurrent.futures import ThreadPoolExecutor
+    dxp = xp_list[1] - xp_list[0]
+    dyp = yp_list[1] - yp_list[0]
+    nx, ny = len(xp_list), len(yp_list)
+    assert Ex.shape == Ey.shape == Hx.shape == Hy.shape == (nx, ny)               # :26
+    check_uniform_axis(xp_list, wavelength)
+    check_uniform_axis(yp_list, wavelength)
+    ux = fft_bin_direction_cosines(nx, dxp, wavelength, n_glass)
+    uy = fft_bin_direction_cosines(ny, dyp, wavelength, n_glass)
+    cols = max(1, min(int(points_at_a_time / nx), -(-ny // max(1, workers))))     # :46, capped
+    starts = list(range(0, ny, cols))                                             # :47-49
+    with ThreadPoolExecutor(max(1, workers)) as pool:
+        f = list(pool.map(lambda a: np.fft.fft2(np.fft.fftshift(np.asarray(a, dtype=complex))), (Ex, Ey, Hx, Hy)))
+
+        def chunk(j0):                                                            # body of the loop, :50-66
+            sl = slice(j0, min(ny, j0 + cols))
+            return radiated_power(f[0][:, sl], f[1][:, sl], f[2][:, sl], f[3][:, sl], ux, uy[sl], dxp, dyp,
+                                  wavelength, n_glass)
+        P = np.concatenate(list(pool.map(chunk, starts)), axis=1)
+    P = np.fft.fftshift(P)                # :68
+    ux = np.fft.fftshift(ux)              # :69
+    uy = np.fft.fftshift(uy)              # :70
+    dux = ux[1] - ux[0]                   # :71
+    duy = uy[1] - uy[0]                   # :72
+    total_P = (P * dux * duy)[np.isfinite(P)].sum()    # :74
+    return P, total_P, ux.reshape(-1, 1), uy.reshape(1, -1), dux, duy
+
+
 def fftshift_origin_index(num):
     """Index of the aperture sample that fftshift() moves to position 0, i.e. the
     phase origin x'=0 of the reference transform (nearfield_farfield.py:106-110;

@@ -69,3 +69,15 @@ def test_grid_validation():
     bad = x.copy(); bad[3] += 1e-9
     with pytest.raises(AssertionError):
         fo.check_uniform_axis(bad, WL)             # non-uniform
+
+
+@pytest.mark.parametrize("workers", [1, 3, 8])
+def test_threaded_reference_path_is_bit_identical(workers):
+    """The all-cores flavour of the CPU baseline (bench.py) is the same arithmetic as the single-thread path:
+    chunking the uy loop (nearfield_farfield.py:45-66) must not change a single bit, NaN mask included."""
+    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(96, 11, WL, My=70)
+    a = fo.farfield_reference_path(Ex, Ey, Hx, Hy, x, y, WL, NG)
+    b = fo.farfield_reference_path_threads(Ex, Ey, Hx, Hy, x, y, WL, NG, workers, points_at_a_time=96 * 13)
+    assert np.array_equal(a[0], b[0], equal_nan=True) and a[1] == b[1]
+    for u, v in zip(a[2:], b[2:]):
+        assert np.array_equal(u, v)
