@@ -42,6 +42,9 @@ const char *mlb_last_error(void);
 int mlb_device_caps(int device, int *out4);
 /* number of kernels this library has launched since load (bench "gpu_launches") */
 long long mlb_launch_count(void);
+/* sizeof(mlb_table_pack), sizeof(mlb_lens_desc) as compiled into the library: a binding checks its own struct
+ * layout against these before passing descriptors */
+int mlb_struct_sizes(int *out2);
 
 /* ---- A1/A4: separable aperture sum --------------------------------------- */
 /*
@@ -250,6 +253,22 @@ typedef struct mlb_lens_desc {
     double source_x, source_y, source_z;
     int plane_wave, source_pol;           /* pol: 0='x' 1='y' 2='z'                         */
     double wavelength, n_glass, dipole_moment, c0, Z0;
+    /* Per-lens derived data: caller-allocated device buffers that mlb_nearfield_prepare() fills once per lens and
+     * wavelength (they do not depend on the source or the sample grid); mlb_nearfield_assemble() reads them.
+     *   ring_aux     n_rings x 64 bytes: { r_center, grating_period, angle_per_grating = 2 pi / num_around (:161),
+     *                lateral_period (:165), 2 pi / grating_period, 2 pi / lateral_period, t2 (float64 each),
+     *                gc index, i2 (int32 each) } -- (i2, t2) = interpolation cell and weight of the ring's
+     *                grating_period on the third table axis (scipy RGI find_indices), one 64-byte record per ring
+     *   ring_aux_f32 n_rings x 32 bytes: float32 screens for the order box and the grating-copy index
+     *   ring_lut     n_lut + 1 ints: ring_lut[b] = number of ring boundaries < b * lut_r_max / n_lut (last entry
+     *                n_rings + 1), so that searchsorted(boundaries, r) (:125) only looks at a 3-bin bracket;
+     *                n_lut >= 1, about 4 * n_rings recommended
+     *   lut_r_max    host copy of ring_boundary[n_rings] (lens_max_r, :94) */
+    void *ring_aux;
+    void *ring_aux_f32;
+    int *ring_lut;
+    int n_lut, _pad2;
+    double lut_r_max;
 } mlb_lens_desc;
 
 #define MLB_STATS_PER_ORDER 8   /* count, min/max ux, min/max uy, min/max third, pad (int64 each) */
@@ -261,12 +280,15 @@ typedef struct mlb_lens_desc {
  * nearest-cell search (:359-466); all in float64.  Output fields are written as complex64
  * (out_is_double=0) or complex128 (1), row pitch `ld` elements.  power_block_sums receives
  * mlb_nearfield_blocks() partial sums of Ex_inc*Hy_inc - Ey_inc*Hx_inc over lens points
- * (:474-477).  violation[0] is set non-zero if any interpolation point lies outside a pack's
+ * (:474-477; one partial sum per warp).  violation[0] is set non-zero if any interpolation point lies outside a pack's
  * bounds (the ValueErrors of :294-305, :412-419); with want_stats=1 the per-(pack,order)
  * count / min / max needed for the reference's messages are accumulated in `stats`
  * (int64, order-preserving encoding of doubles; see metalens_b200/nearfield.py).
  */
 int mlb_nearfield_blocks(int nx, int ny);
+/* Fills ring_aux / ring_aux_f32 / ring_lut of the descriptor (device buffers owned by the caller) from its ring
+ * arrays and table axes; once per lens and wavelength, before the first mlb_nearfield_assemble(). */
+int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream);
 /* tuning knob: register budget variant of the complex64 kernel (min resident blocks/SM: 1, 5 or 6) */
 int mlb_nearfield_tune(int min_blocks);
 int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,

@@ -55,8 +55,10 @@ SIGNATURES = {
     "mlb_cone_power": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
                                  C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mlb_sum_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "mlb_struct_sizes": (C.c_int, [C.c_void_p]),
     "mlb_nearfield_blocks": (C.c_int, [C.c_int, C.c_int]),
     "mlb_nearfield_tune": (C.c_int, [C.c_int]),
+    "mlb_nearfield_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlb_nearfield_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_table_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -24,6 +24,13 @@ const char *mlb_last_error(void) { return mlb::g_err; }
 
 long long mlb_launch_count(void) { return mlb::g_launches.load(); }
 
+int mlb_struct_sizes(int *out2) {
+    MLB_REQUIRE(out2 != nullptr, "mlb_struct_sizes: out2 is NULL");
+    out2[0] = (int)sizeof(mlb_table_pack);
+    out2[1] = (int)sizeof(mlb_lens_desc);
+    return MLB_OK;
+}
+
 int mlb_device_caps(int device, int *out4) {
     MLB_REQUIRE(out4 != nullptr, "mlb_device_caps: out4 is NULL");
     cudaDeviceProp p;

@@ -8,6 +8,8 @@
 // neighbouring threads hit the same interpolation cell, so the gathers are mostly broadcasts.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mlb {
@@ -41,16 +43,37 @@ struct Interp3 {
     double t0, t1, t2;
 };
 
-__device__ __forceinline__ Interp3 locate(const mlb_table_pack &p, double u0, double u1, double u2) {
-    Interp3 q;
-    const double *a0 = p.axes, *a1 = p.axes + p.n_ux, *a2 = p.axes + p.n_ux + p.n_uy;
+// Per-ring record written by nearfield_prepare_kernel (layout documented at mlb_lens_desc.ring_aux): everything
+// a periphery sample needs about its ring in ONE 64-byte line, all values formed with the reference's own float64
+// expressions (so reading them is bit-identical to recomputing them per sample).
+struct __align__(16) RingAux {
+    double rc, gp, apg, lat, qx, qy, t2;
+    int gc, i2;
+};
+// float32 screens: order-box extent (units of kvac) and the grating-copy index guard
+struct __align__(16) RingAuxF {
+    float fqx, fqy, inv_fqx, inv_fqy, inv_apg, guard, pad0, pad1;
+};
+static_assert(sizeof(RingAux) == 64 && sizeof(RingAuxF) == 32, "ring records");
+
+// launch-uniform scalars, computed once on the host (IEEE float64, same expressions as nearfield.py:213, :262)
+struct NfUniform {
+    double kvac, kg, inv_kvac, inv_kg_n, Hcoef, lut_scale;
+    float ng2, cf;
+};
+
+// first two axes of the table (third: precomputed per ring, or located by the caller)
+__device__ __forceinline__ void locate2(const mlb_table_pack &p, double u0, double u1, Interp3 &q) {
+    const double *a0 = p.axes, *a1 = p.axes + p.n_ux;
     q.i0 = find_interval(a0, p.n_ux, u0);
     q.i1 = find_interval(a1, p.n_uy, u1);
-    q.i2 = find_interval(a2, p.n_g, u2);
     q.t0 = (u0 - a0[q.i0]) / (a0[q.i0 + 1] - a0[q.i0]);
     q.t1 = (u1 - a1[q.i1]) / (a1[q.i1 + 1] - a1[q.i1]);
+}
+__device__ __forceinline__ void locate3(const mlb_table_pack &p, double u2, Interp3 &q) {
+    const double *a2 = p.axes + p.n_ux + p.n_uy;
+    q.i2 = find_interval(a2, p.n_g, u2);
     q.t2 = (u2 - a2[q.i2]) / (a2[q.i2 + 1] - a2[q.i2]);
-    return q;
 }
 
 // trilinear gather of the 4 slots (x/ampfy, x/ampfx, y/ampfy, y/ampfx) of one order
@@ -82,101 +105,91 @@ __device__ __forceinline__ void gather4(const mlb_table_pack &p, int order, cons
 }
 
 // e^{i x}: float64 sincos for the complex128 output; for the complex64 output the argument is reduced
-// to [-pi, pi] in float64 (exact to ~1e-16 turns) and the sine/cosine taken in fp32 (abs. error
+// to [-1/2, 1/2] turns in float64 (exact to ~1e-16 turns) and the sine/cosine taken in fp32 (abs. error
 // ~1e-7, below the output's own rounding).
-template <bool FAST>
-__device__ __forceinline__ cplx expi(double x) {
-    if (FAST) {
-        const double t = x * 0.15915494309189535;                 // x / 2 pi
-        const float f = (float)((t - rint(t)) * 6.283185307179586);
-        float s, c;
-        sincosf(f, &s, &c);
-        return {(double)c, (double)s};
-    }
-    double s, c;
-    sincos(x, &s, &c);
-    return {c, s};
-}
-
-// fp32 versions for the complex64 output path: tables read from the float2 copy of the pack, the
-// order's contribution formed in fp32 (relative error ~1e-7, below the output rounding) and added
-// to the float64 per-sample accumulators.
 struct cf { float re, im; };
 __device__ __forceinline__ cf operator+(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
 __device__ __forceinline__ cf operator*(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 __device__ __forceinline__ cf operator*(cf a, float s) { return {a.re * s, a.im * s}; }
 __device__ __forceinline__ cf operator*(float s, cf a) { return {a.re * s, a.im * s}; }
 
-__device__ __forceinline__ void gather4f(const mlb_table_pack &p, int order, const Interp3 &q, cf (&amp)[4]) {
-#pragma unroll
-    for (int s = 0; s < 4; ++s) amp[s] = {0.f, 0.f};
-    const size_t per_order = (size_t)p.n_ux * p.n_uy * p.n_g;
-    const float4 *__restrict__ base = reinterpret_cast<const float4 *>(p.values_f32) + (size_t)order * per_order * 2;
+__device__ __forceinline__ cplx expi(double x) {
+    double s, c;
+    sincos(x, &s, &c);
+    return {c, s};
+}
+__device__ __forceinline__ cf expi_fast(double x) {
+    const double t = x * 0.15915494309189535;                 // x / 2 pi
+    const double fr = t - rint(t);                            // [-1/2, 1/2] turns
+    float s, c;
+    sincospif((float)(fr + fr), &s, &c);                      // angle = pi * (2 fr)
+    return {c, s};
+}
+
+// The interpolation cell of one sample in the float32 copy of a pack: every diffraction order of the sample
+// reads the SAME cell (the interpolation point (ux', uy', period) does not depend on the order, nearfield.py:293),
+// so corner offsets and the 8 trilinear weights are formed once per sample, not once per order.
+struct CellF {
+    int base, sA, sB;         // float4 offsets: first corner, stride of the ux axis, stride of the uy axis
+    float w[8];               // weight of corner (a, b, c) at index 4a + 2b + c
+};
+__device__ __forceinline__ CellF make_cell(const mlb_table_pack &p, const Interp3 &q) {
+    CellF cell;
+    cell.sB = p.n_g * 2;
+    cell.sA = p.n_uy * cell.sB;
+    cell.base = q.i0 * cell.sA + q.i1 * cell.sB + q.i2 * 2;
     const float t0 = (float)q.t0, t1 = (float)q.t1, t2 = (float)q.t2;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const float wa = a ? t0 : 1.f - t0;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-            const float wb = b ? t1 : 1.f - t1;
+            const float wab = (a ? t0 : 1.f - t0) * (b ? t1 : 1.f - t1);
+            cell.w[4 * a + 2 * b] = wab * (1.f - t2);
+            cell.w[4 * a + 2 * b + 1] = wab * t2;
+        }
+    return cell;
+}
+
+// One diffraction order in fp32 (complex64-output path): gather the 4 slots of the cell, form
+//   E_a += Z0 [ S_fy kx ky + S_fx (ky^2+kz^2) ] / (k_g kz n) * phase      (nearfield.py:312-327 / :426-441)
+//   E_b += Z0 [ S_fy (-kx^2-kz^2) - S_fx kx ky ] / (k_g kz n) * phase
+//   H_a += S_fy * phase ;  H_b += S_fx * phase        with S_f* = Hw_x a_x,f* + Hw_y a_y,f*
+// nx, ny = k / kvac (so the products stay well inside the fp32 range); cfac = Z0 kvac / (k_g n).
+__device__ __forceinline__ void order_fast(const float4 *__restrict__ tbl, int per_order2, int o, const CellF &cell,
+                                           float Hw_x, float Hw_y, float nx, float ny, float ng2, float cfac, cf phase,
+                                           cf &Ea, cf &Eb, cf &Ha, cf &Hb) {
+    const float4 *__restrict__ v = tbl + ((size_t)o * per_order2 + cell.base);
+    cf amp[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) amp[s] = {0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const float4 *c0 = v + (a ? cell.sA : 0) + (b ? cell.sB : 0);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const float w = wa * wb * (c ? t2 : 1.f - t2);
-                const float4 *v = base + (((size_t)(q.i0 + a) * p.n_uy + (q.i1 + b)) * p.n_g + (q.i2 + c)) * 2;
-                const float4 x0 = __ldg(v), x1 = __ldg(v + 1);          // slots (0,1) and (2,3)
+                const float w = cell.w[4 * a + 2 * b + c];
+                const float4 x0 = __ldg(c0 + 2 * c), x1 = __ldg(c0 + 2 * c + 1);   // slots (0,1) and (2,3)
                 amp[0].re = fmaf(x0.x, w, amp[0].re); amp[0].im = fmaf(x0.y, w, amp[0].im);
                 amp[1].re = fmaf(x0.z, w, amp[1].re); amp[1].im = fmaf(x0.w, w, amp[1].im);
                 amp[2].re = fmaf(x1.x, w, amp[2].re); amp[2].im = fmaf(x1.y, w, amp[2].im);
                 amp[3].re = fmaf(x1.z, w, amp[3].re); amp[3].im = fmaf(x1.w, w, amp[3].im);
             }
         }
-    }
-}
-
-__device__ __forceinline__ void add_order_f(const cf (&amp)[4], float Hw_x, float Hw_y, float kx, float ky, float kz,
-                                            float f, cf phase, cplx &Ea, cplx &Eb, cplx &Ha, cplx &Hb) {
+    const float nz2 = ng2 - nx * nx - ny * ny;                // > 0: the order propagates in air, n_glass > 1
+    const float rs = rsqrtf(nz2);
+    const float f = cfac * rs;                                // Z0 / (k_g kz n) in units of 1/kvac
     const cf Sfy = Hw_x * amp[0] + Hw_y * amp[2];
     const cf Sfx = Hw_x * amp[1] + Hw_y * amp[3];
-    const cf ea = ((Sfy * (kx * ky) + Sfx * (ky * ky + kz * kz)) * f) * phase;
-    const cf eb = ((Sfy * (-kx * kx - kz * kz) + Sfx * (-kx * ky)) * f) * phase;
-    const cf ha = Sfy * phase, hb = Sfx * phase;
-    Ea.re += ea.re; Ea.im += ea.im; Eb.re += eb.re; Eb.im += eb.im;
-    Ha.re += ha.re; Ha.im += ha.im; Hb.re += hb.re; Hb.im += hb.im;
+    const cf ea = ((Sfy * (nx * ny) + Sfx * (ny * ny + nz2)) * f) * phase;
+    const cf eb = ((Sfy * (-nx * nx - nz2) + Sfx * (-nx * ny)) * f) * phase;
+    Ea = Ea + ea; Eb = Eb + eb;
+    Ha = Ha + Sfy * phase; Hb = Hb + Sfx * phase;
 }
 
-__device__ __forceinline__ void add_order(const cplx (&amp)[4], double Hw_x, double Hw_y, double kx, double ky,
-                                          double kz, double inv_kg_n, double Z0, cplx phase, cplx &Ea, cplx &Eb,
-                                          cplx &Ha, cplx &Hb);
-
-// one diffraction order, either precision.  kx, ky are in units of kvac in the fp32 path so that the
-// products stay well inside the fp32 range; the common factor Z0 kvac / (k_g n) is applied via `f`.
-template <bool FAST>
-__device__ __forceinline__ void order_term(const mlb_table_pack &p, int o, const Interp3 &q, double Hw_x, double Hw_y,
-                                           double kx, double ky, double kg, double kvac, double inv_kg_n, double Z0,
-                                           double phase_arg, cplx &Ea, cplx &Eb, cplx &Ha, cplx &Hb) {
-    if (FAST) {
-        const float nx = (float)(kx / kvac), ny = (float)(ky / kvac);
-        const float ng2 = (float)((kg / kvac) * (kg / kvac));
-        const float nz = sqrtf(ng2 - nx * nx - ny * ny);
-        const cplx ph = expi<true>(phase_arg);
-        cf amp[4];
-        gather4f(p, o, q, amp);
-        const float f = (float)(Z0 * inv_kg_n * kvac) / nz;
-        add_order_f(amp, (float)Hw_x, (float)Hw_y, nx, ny, nz, f, {(float)ph.re, (float)ph.im}, Ea, Eb, Ha, Hb);
-    } else {
-        const double kz = sqrt(kg * kg - kx * kx - ky * ky);
-        const cplx ph = expi<false>(phase_arg);
-        cplx amp[4];
-        gather4(p, o, q, amp);
-        add_order(amp, Hw_x, Hw_y, kx, ky, kz, inv_kg_n, Z0, ph, Ea, Eb, Ha, Hb);
-    }
-}
-
-// one diffraction order's contribution (nearfield.py:306-327 / :420-441), both incident
-// polarisations and both amplitudes at once:
-//   E_a += Z0 [ S_fy kx ky + S_fx (ky^2+kz^2) ] / (k_g kz n) * phase
-//   E_b += Z0 [ S_fy (-kx^2-kz^2) - S_fx kx ky ] / (k_g kz n) * phase
-//   H_a += S_fy * phase ;  H_b += S_fx * phase        with S_f* = Hw_x a_x,f* + Hw_y a_y,f*
+// one diffraction order's contribution in float64 (nearfield.py:306-327 / :420-441), both incident
+// polarisations and both amplitudes at once (same formulas as order_fast)
 __device__ __forceinline__ void add_order(const cplx (&amp)[4], double Hw_x, double Hw_y, double kx, double ky,
                                           double kz, double inv_kg_n, double Z0, cplx phase, cplx &Ea, cplx &Eb,
                                           cplx &Ha, cplx &Hb) {
@@ -191,30 +204,84 @@ __device__ __forceinline__ void add_order(const cplx (&amp)[4], double Hw_x, dou
     Hb = Hb + Sfx * phase;
 }
 
-template <bool STATS>
-__device__ __forceinline__ void record(const mlb_table_pack &p, int order, double u0, double u1, double u2, bool check2,
-                                       long long *stats, int *violation) {
-    const bool bad = (u0 < p.bounds[0]) | (u0 > p.bounds[1]) | (u1 < p.bounds[2]) | (u1 > p.bounds[3]) |
-                     (check2 & ((u2 < p.bounds[4]) | (u2 > p.bounds[5])));
-    if (bad) atomicOr(violation, 1);
-    if (STATS) {
-        long long *s = stats + (size_t)(p.stats_slot + order) * MLB_STATS_PER_ORDER;
-        atomicAdd(reinterpret_cast<unsigned long long *>(s), 1ULL);
-        atomicMin(s + 1, enc_f64(u0)); atomicMax(s + 2, enc_f64(u0));
-        atomicMin(s + 3, enc_f64(u1)); atomicMax(s + 4, enc_f64(u1));
-        atomicMin(s + 5, enc_f64(u2)); atomicMax(s + 6, enc_f64(u2));
-    }
+__device__ __forceinline__ bool out_of_bounds(const mlb_table_pack &p, double u0, double u1, double u2, bool check2) {
+    return (u0 < p.bounds[0]) | (u0 > p.bounds[1]) | (u1 < p.bounds[2]) | (u1 > p.bounds[3]) |
+           (check2 & ((u2 < p.bounds[4]) | (u2 > p.bounds[5])));
+}
+
+// per-(pack, order) count / min / max for the reference's error messages (slow path, want_stats)
+__device__ __forceinline__ void record_stats(const mlb_table_pack &p, int order, double u0, double u1, double u2,
+                                             long long *stats) {
+    long long *s = stats + (size_t)(p.stats_slot + order) * MLB_STATS_PER_ORDER;
+    atomicAdd(reinterpret_cast<unsigned long long *>(s), 1ULL);
+    atomicMin(s + 1, enc_f64(u0)); atomicMax(s + 2, enc_f64(u0));
+    atomicMin(s + 3, enc_f64(u1)); atomicMax(s + 4, enc_f64(u1));
+    atomicMin(s + 5, enc_f64(u2)); atomicMax(s + 6, enc_f64(u2));
 }
 
 constexpr int NF_THREADS = 128;
 
 struct NfOut {
     void *F[4];
-    double *power_block_sums;
+    double *power_warp_sums;
     long long *stats;
     int *violation;
     int ld, out_is_double;
 };
+
+// The diffraction-order loop of one sample (periphery: primed grating frame, nearfield.py:263-327; centre:
+// lab frame about the hex cell, :389-441).  u0, u1 = incident direction cosines in that frame, (X, Y) = sample
+// position relative to the grating / cell centre, qx, qy = reciprocal-lattice steps, u2 = third table coordinate.
+// Orders that can propagate in air satisfy |u0 + ox qx/kvac| <= 1 and |u1 + oy qy/kvac| <= 1: only that (small)
+// index box is visited, through the pack's dense (ox,oy) -> order map; an fp32 screen with margin picks the box,
+// the exact float64 test of :279 / :398 decides.  FAST: fp32 order terms into fp32 accumulators (E, H of the
+// complex64 output), in units where the incident weights Hw carry no dipole scale.
+template <bool STATS, bool FAST, typename Acc, typename W>
+__device__ __forceinline__ void order_loop(const mlb_table_pack &p, const NfUniform &U, double Z0, double u0, double u1,
+                                           double u2, bool check2, bool have_q3, Interp3 q, double X, double Y,
+                                           double qx, double qy, float fqx, float fqy, float inv_fqx, float inv_fqy,
+                                           W Hw_x, W Hw_y, const NfOut &out, Acc &Ea, Acc &Eb, Acc &Ha, Acc &Hb) {
+    const float fu0 = (float)u0, fu1 = (float)u1;
+    const int R = p.order_radius, Wd = 2 * R + 1;
+    const int ox_lo = max(-R, (int)ceilf((-1.001f - fu0) * inv_fqx)), ox_hi = min(R, (int)floorf((1.001f - fu0) * inv_fqx));
+    const int oy_lo = max(-R, (int)ceilf((-1.001f - fu1) * inv_fqy)), oy_hi = min(R, (int)floorf((1.001f - fu1) * inv_fqy));
+    (void)fqx; (void)fqy;
+    const double k0 = U.kvac * u0, k1 = U.kvac * u1, kv2 = U.kvac * U.kvac;
+    bool located = false;
+    CellF cell;
+    const float4 *tbl = reinterpret_cast<const float4 *>(p.values_f32);
+    const int per_order2 = p.n_ux * p.n_uy * p.n_g * 2;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const double kx = k0 + ox * qx;                                                // :268 / :395
+        const int *__restrict__ map_row = p.order_map + (ox + R) * Wd + R;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            const int o = map_row[oy];
+            if (o < 0) continue;                                                       // order not in the tables
+            const double ky = k1 + oy * qy;                                            // :269 / :396
+            if (kx * kx + ky * ky <= kv2) {                                            // :279 / :398
+                if (STATS) record_stats(p, o, u0, u1, u2, out.stats);
+                if (!located) {
+                    located = true;
+                    if (out_of_bounds(p, u0, u1, u2, check2)) atomicOr(out.violation, 1);   // :294-305 / :412-419
+                    locate2(p, u0, u1, q);
+                    if (!have_q3) locate3(p, u2, q);
+                    if constexpr (FAST) cell = make_cell(p, q);
+                }
+                // kz (:287), phase about the grating / cell centre (:291, :408-409), table gathers, accumulation
+                const double phase_arg = kx * X + ky * Y;
+                if constexpr (FAST) {
+                    order_fast(tbl, per_order2, o, cell, Hw_x, Hw_y, (float)(kx * U.inv_kvac), (float)(ky * U.inv_kvac),
+                               U.ng2, U.cf, expi_fast(phase_arg), Ea, Eb, Ha, Hb);
+                } else {
+                    const double kz = sqrt(U.kg * U.kg - kx * kx - ky * ky);
+                    cplx amp[4];
+                    gather4(p, o, q, amp);
+                    add_order(amp, Hw_x, Hw_y, kx, ky, kz, U.inv_kg_n, Z0, expi(phase_arg), Ea, Eb, Ha, Hb);
+                }
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ void store_c(void *base, size_t off, cplx v, int is_double) {
     if (is_double) reinterpret_cast<double2 *>(base)[off] = make_double2(v.re, v.im);
@@ -222,7 +289,10 @@ __device__ __forceinline__ void store_c(void *base, size_t off, cplx v, int is_d
 }
 
 template <bool STATS, bool FAST, int MINB>
-__global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __grid_constant__ mlb_lens_desc L, const NfOut out) {
+__global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __grid_constant__ mlb_lens_desc L,
+                                                                      const __grid_constant__ NfUniform U, const NfOut out) {
+    using Acc = typename std::conditional<FAST, cf, cplx>::type;      // per-sample field accumulators
+    using W = typename std::conditional<FAST, float, double>::type;   // incident weights
     const int j = blockIdx.x * NF_THREADS + threadIdx.x;   // y index (fast)
     const int i = blockIdx.y;                              // x index
     const double PI = 3.14159265358979323846;
@@ -230,8 +300,11 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
     if (j < L.ny) {
         const double x = L.x_pts[i], y = L.y_pts[j];
         const double r = sqrt(x * x + y * y);                                  // nearfield.py:118
-        // which_ring = searchsorted(boundaries, r) - 1  (left-biased)          :125-128
-        int lo = 0, hi = L.n_rings + 1;
+        // which_ring = searchsorted(boundaries, r) - 1  (left-biased, :125-128): the bin table brackets the
+        // answer to the boundaries of three bins, the same bisection as before finishes it
+        int b = (int)(r * U.lut_scale);
+        b = min(max(b, 0), L.n_lut - 1);
+        int lo = L.ring_lut[max(b - 1, 0)], hi = L.ring_lut[min(b + 2, L.n_lut)];
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (L.ring_boundary[mid] < r) lo = mid + 1; else hi = mid;
@@ -240,21 +313,30 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
         const bool in_center = (ring == -1);
         if (ring == L.n_rings) ring = -1;
 
-        const double kvac = 2.0 * PI / L.wavelength, kg = 2.0 * PI * L.n_glass / L.wavelength;
-        const double inv_kg_n = 1.0 / (kg * L.n_glass);
-        // incident direction and dipole field (:172-228)
-        double ux = 0.0, uy = 0.0, uz = 1.0, dHx, dHy, dEx, dEy;
+        // incident direction and dipole field (:172-228).  FAST: one float64 reciprocal instead of four
+        // divisions (<= 1 ulp each); the incident weights then leave out the dipole scale Hcoef, which multiplies
+        // the float64 power term and the final fields instead, so fp32 never sees the unit system.
+        double ux = 0.0, uy = 0.0, uz = 1.0, dHx, dHy, dEx, dEy, scale;
         if (L.plane_wave) {
             const double px = L.source_pol == 0 ? 1.0 : 0.0, py = L.source_pol == 1 ? 1.0 : 0.0;
-            dEx = px * L.dipole_moment; dEy = py * L.dipole_moment;
-            dHx = -py * L.dipole_moment / L.Z0; dHy = px * L.dipole_moment / L.Z0;
+            scale = FAST ? L.dipole_moment : 1.0;
+            const double dm = FAST ? 1.0 : L.dipole_moment;
+            dEx = px * dm; dEy = py * dm;
+            dHx = -py * dm / L.Z0; dHy = px * dm / L.Z0;
         } else {
             const double dx = x - L.source_x, dy = y - L.source_y, dz = 0.0 - L.source_z;
             const double dist = sqrt(dx * dx + dy * dy + dz * dz);
-            ux = dx / dist; uy = dy / dist; uz = dz / dist;
-            const double kv = 2.0 * PI / L.wavelength;
-            const double Hcoef = L.c0 * (kv * kv) * L.dipole_moment / (4.0 * PI);   // :213
-            const double a = Hcoef * sqrt(uz) / dist;
+            double a;
+            if (FAST) {
+                const double inv = 1.0 / dist;
+                ux = dx * inv; uy = dy * inv; uz = dz * inv;
+                a = sqrt(uz) * inv;
+                scale = U.Hcoef;
+            } else {
+                ux = dx / dist; uy = dy / dist; uz = dz / dist;
+                a = U.Hcoef * sqrt(uz) / dist;                                      // :213-219
+                scale = 1.0;
+            }
             const double px = L.source_pol == 0, py = L.source_pol == 1, pz = L.source_pol == 2;
             dHx = (uy * pz - uz * py) * a;
             dHy = (uz * px - ux * pz) * a;
@@ -262,66 +344,61 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             dEx = (dHy * uz - dHz * uy) * L.Z0;                                     // :221
             dEy = (dHz * ux - dHx * uz) * L.Z0;                                     // :222
         }
-        cplx Ex = {0, 0}, Ey = {0, 0}, Hx = {0, 0}, Hy = {0, 0};
+        Acc Ex = {0, 0}, Ey = {0, 0}, Hx = {0, 0}, Hy = {0, 0};
         if (ring >= 0) {
             // ---------------- periphery (:148-354)
-            const int gc = L.gc_index[ring];
-            const double gp = L.grating_period[ring];
-            const double apg = 2.0 * PI / L.num_around[ring];                       // :161
-            const double rc = L.r_center[ring];
-            const double lat = rc * apg;                                            // :165
-            const double phi = atan2(y, x);
-            const double rot = rint(phi / apg) * apg;                               // :167 (half to even)
+            const RingAux &ra = reinterpret_cast<const RingAux *>(L.ring_aux)[ring];
+            const RingAuxF &rf = reinterpret_cast<const RingAuxF *>(L.ring_aux_f32)[ring];
+            const int gc = ra.gc;
+            const double apg = ra.apg, rc = ra.rc;                                  // :161
+            // grating copy: rot = round(phi / angle_per_grating) * angle_per_grating (:167, half to even)
+            double kd;
+            bool have_k = false;
+            if (FAST) {
+                // fp32 screen: |error of phi_f / apg| < guard (atan2f <= 2 ulp, float inputs), so unless the
+                // quotient is within `guard` of a half-integer the rounded index equals the float64 one
+                const float yf = (float)y;
+                const float kf = atan2f(yf, (float)x) * rf.inv_apg;
+                const float kr = rintf(kf);
+                if (fabsf(kf - kr) < 0.5f - rf.guard && fabsf(yf) > 1e-30f) { kd = (double)kr; have_k = true; }
+            }
+            if (!have_k) kd = rint(atan2(y, x) / apg);
+            const double rot = kd * apg;
             double s, c;
             sincos(rot, &s, &c);
             const double uxp = ux * c + uy * s, uyp = -ux * s + uy * c;             // :195-196
             const double xp = x * c + y * s - rc, yp = -x * s + y * c;              // :200-201
             const double Hxp_w = dHx * c + dHy * s, Hyp_w = -dHx * s + dHy * c;     // :231-234
-            const double Hw_x = Hyp_w, Hw_y = Hxp_w;                                // :246-247
-            cplx Exp = {0, 0}, Eyp = {0, 0}, Hxp = {0, 0}, Hyp = {0, 0};
+            Acc Exp = {0, 0}, Eyp = {0, 0}, Hxp = {0, 0}, Hyp = {0, 0};
             if (gc >= 0 && gc < L.n_packs) {
-                const mlb_table_pack &p = L.packs[gc];
                 Interp3 q;
-                bool located = false;
-                const double qx = 2.0 * PI / gp, qy = 2.0 * PI / lat;
-                // Orders that can propagate in air satisfy |ux + ox*lambda/gp| <= 1 and |uy + oy*lambda/lat| <= 1:
-                // only that (small) index box is visited, through the pack's dense (ox,oy) -> order map; an
-                // fp32 screen with margin picks the box, the exact float64 test of :279 decides.
-                const float fux = (float)uxp, fuy = (float)uyp, fqx = (float)(qx / kvac), fqy = (float)(qy / kvac);
-                const int R = p.order_radius, W = 2 * R + 1;
-                const int ox_lo = max(-R, (int)ceilf((-1.001f - fux) / fqx)), ox_hi = min(R, (int)floorf((1.001f - fux) / fqx));
-                const int oy_lo = max(-R, (int)ceilf((-1.001f - fuy) / fqy)), oy_hi = min(R, (int)floorf((1.001f - fuy) / fqy));
-                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                    const double kxp = kvac * uxp + ox * qx;                               // :268
-                    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-                        const int o = p.order_map[(ox + R) * W + (oy + R)];
-                        if (o < 0) continue;                                               // order not in the tables
-                        const double kyp = kvac * uyp + oy * qy;                           // :269
-                        if (kxp * kxp + kyp * kyp <= kvac * kvac) {                        // :279
-                            record<STATS>(p, o, uxp, uyp, gp, true, out.stats, out.violation);
-                            if (!located) { q = locate(p, uxp, uyp, gp); located = true; }
-                            // kzp (:287), phase about the grating centre (:291), table gathers, accumulation
-                            order_term<FAST>(p, o, q, Hw_x, Hw_y, kxp, kyp, kg, kvac, inv_kg_n, L.Z0, kxp * xp + kyp * yp,
-                                             Exp, Eyp, Hxp, Hyp);
-                        }
-                    }
-                }
+                q.i2 = ra.i2; q.t2 = ra.t2;
+                // weights: H_xp_weight = Hyp, H_yp_weight = Hxp (:246-247)
+                order_loop<STATS, FAST, Acc, W>(L.packs[gc], U, L.Z0, uxp, uyp, ra.gp, true, true, q, xp, yp, ra.qx, ra.qy,
+                                                rf.fqx, rf.fqy, rf.inv_fqx, rf.inv_fqy, (W)Hyp_w, (W)Hxp_w, out,
+                                                Exp, Eyp, Hxp, Hyp);
             }
             if (!L.plane_wave) {                                                    // :337-346
                 const double gx = rc * c, gy = rc * s;                              // :170-171
                 const double path = sqrt((gx - L.source_x) * (gx - L.source_x) + (gy - L.source_y) * (gy - L.source_y) +
                                          L.source_z * L.source_z);
-                const cplx e = expi<FAST>(kvac * path);
-                Exp = Exp * e; Eyp = Eyp * e; Hxp = Hxp * e; Hyp = Hyp * e;
+                if constexpr (FAST) {
+                    const cf e = expi_fast(U.kvac * path);
+                    Exp = Exp * e; Eyp = Eyp * e; Hxp = Hxp * e; Hyp = Hyp * e;
+                } else {
+                    const cplx e = expi(U.kvac * path);
+                    Exp = Exp * e; Eyp = Eyp * e; Hxp = Hxp * e; Hyp = Hyp * e;
+                }
             }
-            Ex = {Exp.re * c - Eyp.re * s, Exp.im * c - Eyp.im * s};               // :351-354
-            Ey = {Exp.re * s + Eyp.re * c, Exp.im * s + Eyp.im * c};
-            Hx = {Hxp.re * c - Hyp.re * s, Hxp.im * c - Hyp.im * s};
-            Hy = {Hxp.re * s + Hyp.re * c, Hxp.im * s + Hyp.im * c};
-            local_power = dEx * dHy - dEy * dHx;                                    // :474
+            const W cw = (W)c, sw = (W)s;
+            Ex = {Exp.re * cw - Eyp.re * sw, Exp.im * cw - Eyp.im * sw};           // :351-354
+            Ey = {Exp.re * sw + Eyp.re * cw, Exp.im * sw + Eyp.im * cw};
+            Hx = {Hxp.re * cw - Hyp.re * sw, Hxp.im * cw - Hyp.im * sw};
+            Hy = {Hxp.re * sw + Hyp.re * cw, Hxp.im * sw + Hyp.im * cw};
+            local_power = (dEx * dHy - dEy * dHx) * (scale * scale);                // :474
         } else if (in_center) {
             // ---------------- centre (:359-466): nearest cell through the bin grid
-            local_power = dEx * dHy - dEy * dHx;
+            local_power = (dEx * dHy - dEy * dHx) * (scale * scale);
             int best = -1, best_orig = -1;
             double best_d2 = CUDART_INF;
             if (L.n_cells > 0) {
@@ -336,8 +413,8 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                         const int step = edge_row ? 1 : 2 * k;          // interior rows: only the two end bins
                         for (int ix = bx - k; ix <= bx + k; ix += (step > 0 ? step : 1)) {
                             if (ix < 0 || ix >= L.nbx) continue;
-                            const int b = iy * L.nbx + ix;
-                            for (int cidx = L.bin_start[b]; cidx < L.bin_start[b + 1]; ++cidx) {
+                            const int bb = iy * L.nbx + ix;
+                            for (int cidx = L.bin_start[bb]; cidx < L.bin_start[bb + 1]; ++cidx) {
                                 const double ddx = L.cell_x[cidx] - x, ddy = L.cell_y[cidx] - y;
                                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                                 const int orig = L.cell_orig[cidx];
@@ -354,56 +431,89 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             if (best >= 0) {
                 const double cx = L.cell_x[best], cy = L.cell_y[best];
                 const double which = (double)L.cell_which[best];                    // :367
-                const double Hw_x = dHy, Hw_y = dHx;                                // :375-376
-                const mlb_table_pack &p = L.hex;
-                Interp3 q;
-                bool located = false;
                 const double qx = 2.0 * PI / L.hex_x_period, qy = 2.0 * PI / L.hex_y_period;
-                const float fux = (float)ux, fuy = (float)uy, fqx = (float)(qx / kvac), fqy = (float)(qy / kvac);
-                const int R = p.order_radius, W = 2 * R + 1;
-                const int ox_lo = max(-R, (int)ceilf((-1.001f - fux) / fqx)), ox_hi = min(R, (int)floorf((1.001f - fux) / fqx));
-                const int oy_lo = max(-R, (int)ceilf((-1.001f - fuy) / fqy)), oy_hi = min(R, (int)floorf((1.001f - fuy) / fqy));
-                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                    const double kx = kvac * ux + ox * qx;                                         // :395
-                    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-                        const int o = p.order_map[(ox + R) * W + (oy + R)];
-                        if (o < 0) continue;
-                        const double ky = kvac * uy + oy * qy;                                     // :396
-                        if (kx * kx + ky * ky <= kvac * kvac) {                                    // :398
-                            record<STATS>(p, o, ux, uy, which, false, out.stats, out.violation);
-                            if (!located) { q = locate(p, ux, uy, which); located = true; }
-                            // kz (:404), phase about the cell centre (:408-409), gathers, accumulation
-                            order_term<FAST>(p, o, q, Hw_x, Hw_y, kx, ky, kg, kvac, inv_kg_n, L.Z0,
-                                             kx * (x - cx) + ky * (y - cy), Ex, Ey, Hx, Hy);
-                        }
-                    }
-                }
+                const float fqx = (float)(qx * U.inv_kvac), fqy = (float)(qy * U.inv_kvac);
+                Interp3 q;
+                q.i2 = 0; q.t2 = 0.0;
+                // weights un-rotated: H_x_weight = Hy, H_y_weight = Hx (:375-376)
+                order_loop<STATS, FAST, Acc, W>(L.hex, U, L.Z0, ux, uy, which, false, false, q, x - cx, y - cy, qx, qy, fqx, fqy,
+                                                1.0f / fqx, 1.0f / fqy, (W)dHy, (W)dHx, out, Ex, Ey, Hx, Hy);
                 if (!L.plane_wave) {                                                // :453-461
                     const double path = sqrt((cx - L.source_x) * (cx - L.source_x) + (cy - L.source_y) * (cy - L.source_y) +
                                              L.source_z * L.source_z);
-                    const cplx e = expi<FAST>(kvac * path);
-                    Ex = Ex * e; Ey = Ey * e; Hx = Hx * e; Hy = Hy * e;
+                    if constexpr (FAST) {
+                        const cf e = expi_fast(U.kvac * path);
+                        Ex = Ex * e; Ey = Ey * e; Hx = Hx * e; Hy = Hy * e;
+                    } else {
+                        const cplx e = expi(U.kvac * path);
+                        Ex = Ex * e; Ey = Ey * e; Hx = Hx * e; Hy = Hy * e;
+                    }
                 }
             }
         }
         const size_t off = (size_t)i * out.ld + j;
-        store_c(out.F[0], off, Ex, out.out_is_double);
-        store_c(out.F[1], off, Ey, out.out_is_double);
-        store_c(out.F[2], off, Hx, out.out_is_double);
-        store_c(out.F[3], off, Hy, out.out_is_double);
+        if constexpr (FAST) {
+            // the dipole scale left out of the fp32 weights, applied in float64
+            reinterpret_cast<float2 *>(out.F[0])[off] = make_float2((float)(Ex.re * scale), (float)(Ex.im * scale));
+            reinterpret_cast<float2 *>(out.F[1])[off] = make_float2((float)(Ey.re * scale), (float)(Ey.im * scale));
+            reinterpret_cast<float2 *>(out.F[2])[off] = make_float2((float)(Hx.re * scale), (float)(Hx.im * scale));
+            reinterpret_cast<float2 *>(out.F[3])[off] = make_float2((float)(Hy.re * scale), (float)(Hy.im * scale));
+        } else {
+            store_c(out.F[0], off, Ex, out.out_is_double);
+            store_c(out.F[1], off, Ey, out.out_is_double);
+            store_c(out.F[2], off, Hx, out.out_is_double);
+            store_c(out.F[3], off, Hy, out.out_is_double);
+        }
     }
-    // incident power through the lens (:474-477), deterministic per-block partial sums
+    // incident power through the lens (:474-477), deterministic per-warp partial sums (no block barrier: the
+    // warps of a block finish at very different times)
     double v = local_power;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __shared__ double ws[NF_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NF_THREADS / 32; ++w) s += ws[w];
-        out.power_block_sums[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    if ((threadIdx.x & 31) == 0)
+        out.power_warp_sums[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NF_THREADS / 32) + (threadIdx.x >> 5)] = v;
+}
+
+// Per-lens derived data (mlb_nearfield_prepare): ring records and the ring bin table.
+__global__ void nearfield_prepare_kernel(const __grid_constant__ mlb_lens_desc L, double kvac) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double PI = 3.14159265358979323846;
+    if (t < L.n_rings) {
+        RingAux ra;
+        ra.rc = L.r_center[t];
+        ra.gp = L.grating_period[t];
+        ra.apg = 2.0 * PI / L.num_around[t];                                       // :161
+        ra.lat = ra.rc * ra.apg;                                                   // :165
+        ra.qx = 2.0 * PI / ra.gp;
+        ra.qy = 2.0 * PI / ra.lat;
+        ra.gc = L.gc_index[t];
+        ra.i2 = 0; ra.t2 = 0.0;
+        if (ra.gc >= 0 && ra.gc < L.n_packs) {
+            Interp3 q;
+            locate3(L.packs[ra.gc], ra.gp, q);
+            ra.i2 = q.i2; ra.t2 = q.t2;
+        }
+        reinterpret_cast<RingAux *>(L.ring_aux)[t] = ra;
+        RingAuxF rf;
+        rf.fqx = (float)(ra.qx / kvac); rf.fqy = (float)(ra.qy / kvac);
+        rf.inv_fqx = 1.0f / rf.fqx; rf.inv_fqy = 1.0f / rf.fqy;
+        rf.inv_apg = (float)(1.0 / ra.apg);
+        rf.guard = fminf(0.5f, 4e-6f * rf.inv_apg + 1e-6f);
+        rf.pad0 = rf.pad1 = 0.f;
+        reinterpret_cast<RingAuxF *>(L.ring_aux_f32)[t] = rf;
+    }
+    if (t <= L.n_lut) {
+        int cnt = L.n_rings + 1;
+        if (t < L.n_lut) {
+            const double edge = t * (L.lut_r_max / L.n_lut);
+            int lo = 0, hi = L.n_rings + 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (L.ring_boundary[mid] < edge) lo = mid + 1; else hi = mid;
+            }
+            cnt = lo;
+        }
+        L.ring_lut[t] = cnt;
     }
 }
 
@@ -435,15 +545,19 @@ __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n
 
 }  // namespace mlb
 
-static int g_nf_minblocks = 5;   // 96 registers, 5 blocks/SM: fastest on B200 (scripts/tune_nearfield.py)
-/* tuning knob: minimum resident blocks per SM the complex64 kernel is compiled for (1, 5 or 6) */
+static int g_nf_minblocks = 6;   // 80 registers, 6 blocks/SM: fastest on B200 (scripts/tune_nearfield.py)
+/* tuning knob: minimum resident blocks per SM the complex64 kernel is compiled for (1, 5, 6 or 8) */
 extern "C" int mlb_nearfield_tune(int min_blocks) {
-    MLB_REQUIRE(min_blocks == 1 || min_blocks == 5 || min_blocks == 6, "mlb_nearfield_tune: min_blocks must be 1, 5 or 6");
+    MLB_REQUIRE(min_blocks == 1 || min_blocks == 5 || min_blocks == 6 || min_blocks == 8,
+                "mlb_nearfield_tune: min_blocks must be 1, 5, 6 or 8");
     g_nf_minblocks = min_blocks;
     return MLB_OK;
 }
 
-extern "C" int mlb_nearfield_blocks(int nx, int ny) { return nx * ((ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS); }
+/* one incident-power partial sum per warp */
+extern "C" int mlb_nearfield_blocks(int nx, int ny) {
+    return nx * ((ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS) * (mlb::NF_THREADS / 32);
+}
 
 static int check_pack(const mlb_table_pack &p, const char *what) {
     MLB_REQUIRE(p.axes && p.values && p.values_f32 && p.orders, "mlb_nearfield_assemble: %s pack has NULL arrays", what);
@@ -455,6 +569,29 @@ static int check_pack(const mlb_table_pack &p, const char *what) {
     return MLB_OK;
 }
 
+static int check_desc(const mlb_lens_desc &L, const char *who) {
+    MLB_REQUIRE(L.n_rings >= 1 && L.ring_boundary && L.r_center && L.grating_period && L.num_around && L.gc_index,
+                "%s: the periphery needs >= 1 ring (nearfield.py:87-93 dereferences it)", who);
+    MLB_REQUIRE(L.n_packs >= 1 && L.n_packs <= MLB_MAX_PACKS, "%s: %d collections (max %d)", who, L.n_packs, MLB_MAX_PACKS);
+    for (int g = 0; g < L.n_packs; ++g)
+        if (int rc = check_pack(L.packs[g], "collection")) return rc;
+    MLB_REQUIRE(L.ring_aux && L.ring_aux_f32 && L.ring_lut && L.n_lut >= 1 && L.lut_r_max > 0,
+                "%s: ring_aux / ring_aux_f32 / ring_lut buffers missing (see mlb_nearfield_prepare)", who);
+    MLB_REQUIRE(mlb::aligned16(L.ring_aux) && mlb::aligned16(L.ring_aux_f32), "%s: ring_aux buffers not 16-byte aligned", who);
+    MLB_REQUIRE(L.wavelength > 0 && L.n_glass > 0, "%s: bad wavelength / n_glass", who);
+    return MLB_OK;
+}
+
+extern "C" int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream) {
+    MLB_REQUIRE(h_desc, "mlb_nearfield_prepare: NULL descriptor");
+    const mlb_lens_desc &L = *h_desc;
+    if (int rc = check_desc(L, "mlb_nearfield_prepare")) return rc;
+    const double kvac = 2.0 * 3.14159265358979323846 / L.wavelength;
+    const int n = (L.n_rings > L.n_lut + 1) ? L.n_rings : L.n_lut + 1;
+    mlb::nearfield_prepare_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, kvac);
+    return mlb::check_launch("mlb_nearfield_prepare");
+}
+
 extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
                                       int out_is_double, double *power_block_sums, long long *stats, int want_stats,
                                       int *violation, void *stream) {
@@ -462,12 +599,7 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     const mlb_lens_desc &L = *h_desc;
     MLB_REQUIRE(L.nx > 0 && L.ny > 0 && ld >= L.ny, "mlb_nearfield_assemble: bad grid (%d,%d,ld=%d)", L.nx, L.ny, ld);
     MLB_REQUIRE(L.x_pts && L.y_pts, "mlb_nearfield_assemble: NULL sample coordinates");
-    MLB_REQUIRE(L.n_rings >= 1 && L.ring_boundary && L.r_center && L.grating_period && L.num_around && L.gc_index,
-                "mlb_nearfield_assemble: the periphery needs >= 1 ring (nearfield.py:87-93 dereferences it)");
-    MLB_REQUIRE(L.n_packs >= 1 && L.n_packs <= MLB_MAX_PACKS, "mlb_nearfield_assemble: %d collections (max %d)",
-                L.n_packs, MLB_MAX_PACKS);
-    for (int g = 0; g < L.n_packs; ++g)
-        if (int rc = check_pack(L.packs[g], "collection")) return rc;
+    if (int rc = check_desc(L, "mlb_nearfield_assemble")) return rc;
     if (L.n_cells > 0) {
         if (int rc = check_pack(L.hex, "hexgridset")) return rc;
         MLB_REQUIRE(L.cell_x && L.cell_y && L.cell_which && L.cell_orig && L.bin_start && L.nbx > 0 && L.nby > 0 &&
@@ -481,18 +613,30 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     MLB_REQUIRE((size_t)L.ny <= 65535u * mlb::NF_THREADS * 32u && L.nx <= 65535, "mlb_nearfield_assemble: grid too large");
     mlb::NfOut out;
     out.F[0] = Ex; out.F[1] = Ey; out.F[2] = Hx; out.F[3] = Hy;
-    out.power_block_sums = power_block_sums; out.stats = stats; out.violation = violation;
+    out.power_warp_sums = power_block_sums; out.stats = stats; out.violation = violation;
     out.ld = ld; out.out_is_double = out_is_double;
+    // launch-uniform scalars in IEEE float64, the expressions of nearfield.py:213 / :262 / :287
+    const double PI = 3.14159265358979323846;
+    mlb::NfUniform U;
+    U.kvac = 2.0 * PI / L.wavelength;
+    U.kg = 2.0 * PI * L.n_glass / L.wavelength;
+    U.inv_kvac = 1.0 / U.kvac;
+    U.inv_kg_n = 1.0 / (U.kg * L.n_glass);
+    U.Hcoef = L.c0 * (U.kvac * U.kvac) * L.dipole_moment / (4.0 * PI);
+    U.lut_scale = L.n_lut / L.lut_r_max;
+    U.ng2 = (float)((U.kg / U.kvac) * (U.kg / U.kvac));
+    U.cf = (float)(L.Z0 * U.inv_kg_n * U.kvac);
     dim3 grid((L.ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS, L.nx);
     const cudaStream_t st = (cudaStream_t)stream;
     if (want_stats) {
-        if (out_is_double) mlb::nearfield_kernel<true, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
-        else mlb::nearfield_kernel<true, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        if (out_is_double) mlb::nearfield_kernel<true, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        else mlb::nearfield_kernel<true, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
     } else {
-        if (out_is_double) mlb::nearfield_kernel<false, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
-        else if (g_nf_minblocks == 5) mlb::nearfield_kernel<false, true, 5><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
-        else if (g_nf_minblocks == 6) mlb::nearfield_kernel<false, true, 6><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
-        else mlb::nearfield_kernel<false, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, out);
+        if (out_is_double) mlb::nearfield_kernel<false, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        else if (g_nf_minblocks == 5) mlb::nearfield_kernel<false, true, 5><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        else if (g_nf_minblocks == 6) mlb::nearfield_kernel<false, true, 6><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        else if (g_nf_minblocks == 8) mlb::nearfield_kernel<false, true, 8><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        else mlb::nearfield_kernel<false, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
     }
     return mlb::check_launch("mlb_nearfield_assemble");
 }

@@ -44,7 +44,9 @@ class _LensC(C.Structure):
                 ("source_x", C.c_double), ("source_y", C.c_double), ("source_z", C.c_double),
                 ("plane_wave", C.c_int), ("source_pol", C.c_int),
                 ("wavelength", C.c_double), ("n_glass", C.c_double), ("dipole_moment", C.c_double),
-                ("c0", C.c_double), ("Z0", C.c_double)]
+                ("c0", C.c_double), ("Z0", C.c_double),
+                ("ring_aux", C.c_void_p), ("ring_aux_f32", C.c_void_p), ("ring_lut", C.c_void_p),
+                ("n_lut", C.c_int), ("_pad2", C.c_int), ("lut_r_max", C.c_double)]
 
 
 def good_fft_number(goal):
@@ -166,6 +168,15 @@ class NearfieldPlan:
             self.bin_size = 1.0
             self.nbx = self.nby = 1
 
+        # per-lens derived data, filled on the device by mlb_nearfield_prepare (ring records, ring bin table)
+        self.n_lut = max(16, 4 * self.n_rings)
+        self._keep.update(
+            ring_aux=torch.zeros(self.n_rings * 8, dtype=torch.float64, device=dev),
+            ring_aux_f32=torch.zeros(self.n_rings * 8, dtype=torch.float32, device=dev),
+            ring_lut=torch.zeros(self.n_lut + 1, dtype=torch.int32, device=dev))
+        L = self._desc(self._keep['ring_boundary'], self._keep['ring_boundary'], 0.0, 0.0, -1.0, 'x', 1.0)
+        _lib.check(self.lib.mlb_nearfield_prepare(C.byref(L), _stream_ptr()), "mlb_nearfield_prepare")
+
     # ------------------------------------------------------------------
     def _pack_struct(self, pack, dev_arrays):
         s = _PackC()
@@ -202,6 +213,8 @@ class NearfieldPlan:
         L.source_pol = {'x': 0, 'y': 1, 'z': 2}[source_pol]
         L.wavelength, L.n_glass, L.dipole_moment = self.wavelength, float(self.n_glass), float(dipole_moment)
         L.c0, L.Z0 = c0, Z0
+        L.ring_aux, L.ring_aux_f32 = k['ring_aux'].data_ptr(), k['ring_aux_f32'].data_ptr()
+        L.ring_lut, L.n_lut, L.lut_r_max = k['ring_lut'].data_ptr(), self.n_lut, self.lens_max_r
         return L
 
     def default_grid(self):

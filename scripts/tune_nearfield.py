@@ -15,7 +15,7 @@ periph, center, _ = make_design(collections, f, spec["radius"], hgs)
 plan = NearfieldPlan(wl, periph, center, hgs)
 x = np.linspace(-R, R, M)
 ref = None
-for variant, dtype in ((1, torch.complex64), (5, torch.complex64), (6, torch.complex64), (1, torch.complex128)):
+for variant, dtype in ((1, torch.complex64), (5, torch.complex64), (6, torch.complex64), (8, torch.complex64), (1, torch.complex128)):
     _lib.check(lib.mlb_nearfield_tune(variant), "tune")
     out = torch.zeros((4, M, M), dtype=dtype, device="cuda")
     for _ in range(2): plan.run(0.0, 0.0, -f, "x", x, x, out=out)

@@ -36,6 +36,14 @@ def test_ctypes_table_matches_header():
     assert lib.mlb_launch_count() >= 0
 
 
+def test_descriptor_structs_match_the_library():
+    """The ctypes mirrors of mlb_table_pack / mlb_lens_desc have the size the library was compiled with."""
+    from metalens_b200 import _lib, nearfield
+    out = (ctypes.c_int * 2)()
+    assert _lib.load().mlb_struct_sizes(out) == 0
+    assert out[0] == ctypes.sizeof(nearfield._PackC) and out[1] == ctypes.sizeof(nearfield._LensC)
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from metalens_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
