@@ -138,8 +138,9 @@ int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, i
                  int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
                  int batch, void *stream);
 /* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}.  In-place allowed
- * for N <= 2048; for N >= 4096 the transform is a four-step decomposition that uses the INPUT buffer as
- * scratch (it is overwritten) and needs out != in. */
+ * for power-of-two N <= 2048 and every other length; for power-of-two N >= 4096 the transform is a two-pass
+ * decomposition that uses the INPUT buffer as scratch (it is overwritten) and needs out != in; for other lengths
+ * the two-pass form is chosen when out != in and >= 8 columns (INPUT overwritten), the direct one otherwise. */
 int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N, int n_cols,
                  const mlb_c64 *tw, int out_roll, int batch, void *stream);
 
@@ -169,6 +170,14 @@ int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols,
  *                        points) everywhere, 2 (default) = radix-16 without a fold, TMA-fed fold+FFT kernel with one
  *   cols_engine          0 = radix-4 column kernels, 1 (default) = radix-16 register kernels (256..8192 points; 4096 and
  *                        8192 as 16 x 256/512 in two passes, the first in place on the INPUT buffer)
+ *   mixed_engine         non-power-of-two lengths (the good_fft_number() sizes): 1 (default) = big-radix engine (radices
+ *                        up to 16 in registers, long columns as A x B in two passes, the first in place on the INPUT
+ *                        buffer unless the call is in place), 0 = radix 2..5 shared-memory kernels
+ *   mixed_registers      1 (default) = one-butterfly-per-thread register kernels of that engine where they pay (long
+ *                        transforms that keep >= 80 % of a CTA's threads busy), 2 = wherever they apply, 0 = never
+ *   mixed_occupancy      resident CTAs per SM those kernels are compiled for: 0 (default: rows 2, columns 4), 2..4
+ *   cols_strip_mb        two-pass (>= 4096-point) column transforms run strip by strip, strips of this many MB of all
+ *                        fields (intermediate stays in L2); 0 (default) = one strip
  *   r16_occupancy        resident CTAs per SM the radix-16 kernels are compiled for: 0 (default: rows 4, columns 3), 2..4
  * mlb_get_option returns -1 for an unknown name. */
 int mlb_set_option(const char *name, int value);

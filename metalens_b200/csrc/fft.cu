@@ -875,6 +875,10 @@ __global__ void __launch_bounds__(256) fft_cols_mixed_kernel(const MixArgs a) {
     }
 }
 
+}  // namespace mlb
+#include "fftmix.cuh"
+namespace mlb {
+
 __global__ void fft_twiddle_kernel(int N, float2 *__restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
@@ -912,6 +916,13 @@ static int g_r16_occ = 0;              // radix-16 kernels: resident CTAs per SM
 static int g_cols_engine = 1;          // column pass: 0 = radix-4 shared-memory kernels, 1 = radix-16 register kernels (256..8192; default)
 static int g_rows_ring_kb = 64;        // TMA row pass: bytes of shared memory in the slot ring per CTA (64 or 128 KB)
 static int g_rows_evict_first = 1;     // TMA row pass: stream the aperture through L2 with an evict-first policy
+static int g_cols_strip_mb = 0;        // two-pass column transforms (>= 4096 points): run them strip by strip, strips of this many MB (so the
+                                       // intermediate stays in L2); 0 = one strip (default: measured faster on B200, the per-strip launches cost
+                                       // more than the saved HBM round trip)
+static int g_mixed_occ = 0;            // register kernels of the big-radix engine: resident CTAs per SM they are compiled for
+                                       // (2..4; 0 = default: rows 2, columns 4 -- measured on B200, scripts/allbins_kernels.py)
+static int g_mixed_reg = 1;            // big-radix engine: use the one-butterfly-per-thread register kernels where they apply
+static int g_mixed_engine = 1;         // non-power-of-two lengths: 0 = radix 2..5 shared-memory kernels, 1 = big-radix engine (fftmix.cuh; default)
 static int g_cols_power_wide = -1;     // fused column+power pass: 1 = 4096-point tiles / 1024 threads, 0 = 2048 / 512,
                                        // -1 = by length (wide from 1024 points up: measured faster on B200)
 static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
@@ -980,6 +991,10 @@ extern "C" int mlb_set_option(const char *name, int value) {
     else if (n == "cols_engine") { MLB_REQUIRE(value >= 0 && value <= 1, "cols_engine: 0..1"); mlb::g_cols_engine = value; }
     else if (n == "rows_ring_kb") { MLB_REQUIRE(value == 64 || value == 128, "rows_ring_kb: 64 or 128"); mlb::g_rows_ring_kb = value; }
     else if (n == "cols_power_wide") mlb::g_cols_power_wide = value < 0 ? -1 : (value ? 1 : 0);
+    else if (n == "mixed_registers") { MLB_REQUIRE(value >= 0 && value <= 2, "mixed_registers: 0..2"); mlb::g_mixed_reg = value; }
+    else if (n == "mixed_occupancy") { MLB_REQUIRE(value == 0 || (value >= 2 && value <= 4), "mixed_occupancy: 0, 2..4"); mlb::g_mixed_occ = value; }
+    else if (n == "mixed_engine") { MLB_REQUIRE(value >= 0 && value <= 1, "mixed_engine: 0..1"); mlb::g_mixed_engine = value; }
+    else if (n == "cols_strip_mb") { MLB_REQUIRE(value >= 0 && value <= 4096, "cols_strip_mb: 0..4096"); mlb::g_cols_strip_mb = value; }
     else MLB_REQUIRE(false, "mlb_set_option: unknown option '%s'", name);
     return MLB_OK;
 }
@@ -994,8 +1009,99 @@ extern "C" int mlb_get_option(const char *name) {
     if (n == "cols_engine") return mlb::g_cols_engine;
     if (n == "r16_occupancy") return mlb::g_r16_occ;
     if (n == "cols_power_wide") return mlb::g_cols_power_wide;
+    if (n == "cols_strip_mb") return mlb::g_cols_strip_mb;
+    if (n == "mixed_engine") return mlb::g_mixed_engine;
+    if (n == "mixed_registers") return mlb::g_mixed_reg;
+    if (n == "mixed_occupancy") return mlb::g_mixed_occ;
     return -1;
 }
+
+namespace mlb {
+// ---- host side of the big-radix mixed engine (fftmix.cuh)
+static unsigned mix2_magic(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ULL + (unsigned long long)d - 1) / (unsigned long long)d); }
+
+// radix sequence of a 5-smooth length: odd radices first (their stride-R first-stage writes are conflict-free),
+// then the even ones; fills radix / magic tables; returns the stage count or 0
+static int mix2_plan(Mix2Args &m, int N) {
+    int a = 0, b = 0, c = 0, n = N;
+    while (n % 2 == 0) { ++a; n /= 2; }
+    while (n % 3 == 0) { ++b; n /= 3; }
+    while (n % 5 == 0) { ++c; n /= 5; }
+    if (n != 1 || N < 2) return 0;
+    int r[32], ns = 0;
+    while (b >= 1 && c >= 1) { r[ns++] = 15; --b; --c; }
+    while (b >= 2) { r[ns++] = 9; b -= 2; }
+    int five_even = 0, three_even = 0;                    // odd primes to be paired with factors of two
+    while (c >= 1) { if (a >= 1 + 0 && five_even < a) { ++five_even; } else { r[ns++] = 5; } --c; }
+    // pair each deferred 5 with one factor 2 (radix 10)
+    int tens = five_even; a -= tens;
+    if (b == 1) { if (a >= 2) { three_even = 12; a -= 2; } else if (a >= 1) { three_even = 6; a -= 1; } else { r[ns++] = 3; } b = 0; }
+    if (three_even) r[ns++] = three_even;
+    for (int t = 0; t < tens; ++t) r[ns++] = 10;
+    while (a >= 4) { r[ns++] = 16; a -= 4; }
+    if (a == 3) r[ns++] = 8; else if (a == 2) r[ns++] = 4; else if (a == 1) r[ns++] = 2;
+    if (ns > MIX2_MAX_STAGES) return 0;
+    int Ns = 1;
+    for (int s = 0; s < ns; ++s) {
+        m.radix[s] = r[s];
+        m.magic_ns[s] = mix2_magic(Ns);
+        m.magic_per[s] = mix2_magic(N / r[s]);
+        Ns *= r[s];
+    }
+    m.nstage = ns; m.N = N;
+    m.pad_sh = (r[0] & 1) ? 30 : 4;
+    return ns;
+}
+static size_t mix2_smem(int N, int lanes) { return 2 * (size_t)lanes * (mixpad(N, 4) + 1) * sizeof(float2); }
+constexpr size_t MIX2_SMEM_MAX = 2 * (size_t)(FFT_MAX_N + (FFT_MAX_N >> 4) + 1) * sizeof(float2);   // one 8192-point transform
+static int mix2_set_smem() {
+    static bool set_ = false;
+    if (!set_) {
+        MLB_CUDA(cudaFuncSetAttribute(mix2_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
+        MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
+        set_ = true;
+    }
+    return MLB_OK;
+}
+// power-of-two column lanes per CTA for sub-length n: as many as fit in ~72 KB, at most 32
+static int mix2_col_lanes(int n, int n_cols) {
+    int lanes = 1;
+    while (lanes < 32 && mix2_smem(n, lanes * 2) <= 72 * 1024 && lanes < n_cols) lanes *= 2;
+    return lanes;
+}
+// butterflies of the busiest stage of one transform (the register variant needs lanes * this <= 256)
+static int mix2_max_per(const Mix2Args &m) {
+    int mx = 0;
+    for (int s = 0; s < m.nstage; ++s) mx = (m.N / m.radix[s] > mx) ? m.N / m.radix[s] : mx;
+    return mx;
+}
+template <int A>
+static void mix2_launch_first(const Mix2FirstArgs &f, dim3 grid, cudaStream_t st) { mix2_cols_first_kernel<A><<<grid, 256, 0, st>>>(f); }
+static int mix2_first(int A, const Mix2FirstArgs &f, int batch, cudaStream_t st) {
+    dim3 grid((f.n_cols + 31) / 32, (f.B + 7) / 8, batch);
+    switch (A) {
+        case 16: mix2_launch_first<16>(f, grid, st); break;
+        case 15: mix2_launch_first<15>(f, grid, st); break;
+        case 12: mix2_launch_first<12>(f, grid, st); break;
+        case 10: mix2_launch_first<10>(f, grid, st); break;
+        case 9: mix2_launch_first<9>(f, grid, st); break;
+        case 8: mix2_launch_first<8>(f, grid, st); break;
+        case 6: mix2_launch_first<6>(f, grid, st); break;
+        case 5: mix2_launch_first<5>(f, grid, st); break;
+        case 4: mix2_launch_first<4>(f, grid, st); break;
+        case 3: mix2_launch_first<3>(f, grid, st); break;
+        case 2: mix2_launch_first<2>(f, grid, st); break;
+        default: set_error("mixed column pass: no first-pass radix %d", A); return MLB_ERR_ARG;
+    }
+    return check_launch("mlb_fft_cols(mixed radix, first pass)");
+}
+}  // namespace mlb
 
 extern "C" int mlb_fft_max_length(void) { return mlb::FFT_MAX_N; }
 
@@ -1022,6 +1128,35 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.tw = reinterpret_cast<const float2 *>(tw);
     if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
         MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs a power-of-two length");
+        if (mlb::g_mixed_engine == 1) {
+            mlb::Mix2Args m2;
+            MLB_REQUIRE(mlb::mix2_plan(m2, N) > 0, "mlb_fft_rows: cannot factor %d", N);
+            for (int b = 0; b < 4; ++b) { m2.in[b] = a.in[b]; m2.out[b] = a.out[b]; }
+            m2.tw = a.tw; m2.ld_in = ld_in; m2.ld_out = ld_out; m2.other = n_rows; m2.tw_mul = 1; m2.Ntot = N;
+            m2.in_roll_r = in_roll_r; m2.in_roll_c = in_roll_c; m2.out_roll = out_roll; m2.s1 = s1; m2.s2 = s2;
+            m2.in_gs = m2.in_rs = m2.out_gs = m2.out_rs = m2.roll = 0;
+            int lanes = 1;                           // rows per CTA: ~one butterfly per thread and stage, <= 64 KB
+            while (lanes < 16 && mlb::mix2_smem(N, lanes * 2) <= 64 * 1024 && lanes * 2 <= n_rows && lanes * N < 4096) lanes *= 2;
+            if (int rc = mlb::mix2_set_smem()) return rc;
+            const int mp = mlb::mix2_max_per(m2);
+            int rl = mp <= 256 ? 256 / mp : 0;
+            if (rl > 16) rl = 16;
+            if (rl > n_rows) rl = n_rows;
+            // one butterfly per thread and stage (register variant): long rows that keep >= 80 % of the threads busy
+            if (mlb::g_mixed_reg && rl >= 1 && (mlb::g_mixed_reg == 2 || (N >= 2048 && rl * mp >= 205))) {
+                m2.lanes = rl; m2.lg_lanes = 0;
+                dim3 grid((n_rows + rl - 1) / rl, batch);
+                const size_t sm2 = mlb::mix2_smem(N, rl) / 2;
+                if (mlb::g_mixed_occ == 4) mlb::mix2_reg_kernel<false, 4><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+                else if (mlb::g_mixed_occ == 3) mlb::mix2_reg_kernel<false, 3><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+                else mlb::mix2_reg_kernel<false, 2><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+                return mlb::check_launch("mlb_fft_rows(mixed radix, registers)");
+            }
+            m2.lanes = lanes; m2.lg_lanes = 0;
+            dim3 grid((n_rows + lanes - 1) / lanes, batch);
+            mlb::mix2_rows_kernel<<<grid, 256, mlb::mix2_smem(N, lanes), (cudaStream_t)stream>>>(m2);
+            return mlb::check_launch("mlb_fft_rows(mixed radix)");
+        }
         mlb::MixArgs m;
         mlb::fill_mixed(m, a, N);
         m.tw = a.tw; m.ld_in = ld_in; m.ld_out = ld_out; m.other = n_rows;
@@ -1173,6 +1308,79 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     return mlb::check_launch("mlb_fft_rows");
 }
 
+namespace mlb {
+template <int LG, int CL>
+static int launch_r16_cols(const R16ColArgs &r, int groups, int batch, cudaStream_t st) {
+    constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);
+    const size_t smem16 = (size_t)CL * PITCH * sizeof(float2);
+    static bool set_ = false, set3_ = false, set4_ = false;
+    dim3 gc((r.n_cols + CL - 1) / CL, groups, batch);
+    if ((g_r16_occ == 3 || g_r16_occ == 0) && T <= 256) {
+        if (!set3_) {
+            MLB_CUDA(cudaFuncSetAttribute(fft16_cols_kernel<LG, CL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            set3_ = true;
+        }
+        fft16_cols_kernel<LG, CL, 3><<<gc, T, smem16, st>>>(r);
+    } else if (g_r16_occ == 4 && T <= 256) {
+        if (!set4_) {
+            MLB_CUDA(cudaFuncSetAttribute(fft16_cols_kernel<LG, CL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            set4_ = true;
+        }
+        fft16_cols_kernel<LG, CL, 4><<<gc, T, smem16, st>>>(r);
+    } else {
+        if (!set_) {
+            MLB_CUDA(cudaFuncSetAttribute(fft16_cols_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+            set_ = true;
+        }
+        fft16_cols_kernel<LG, CL><<<gc, T, smem16, st>>>(r);
+    }
+    return check_launch("mlb_fft_cols(radix 16)");
+}
+static int r16_cols_dispatch(int lgSub, const R16ColArgs &r, int groups, int batch, cudaStream_t st) {
+    switch (lgSub) {
+        case 8: return launch_r16_cols<8, 16>(r, groups, batch, st);
+        case 9: return launch_r16_cols<9, 8>(r, groups, batch, st);
+        case 10: return launch_r16_cols<10, 4>(r, groups, batch, st);
+        case 11: return launch_r16_cols<11, 4>(r, groups, batch, st);
+    }
+    set_error("radix-16 column pass: unsupported sub-length 2^%d", lgSub);
+    return MLB_ERR_ARG;
+}
+// column strip of the two-pass (>= 4096-point) column transforms: all `fields` fields of a strip stay in L2
+// between the passes (multiple of 32 columns = 256-byte row segments)
+static int r16_strip_cols(int N, int n_cols, int fields) {
+    if (g_cols_strip_mb <= 0) return n_cols;
+    long long w = (long long)g_cols_strip_mb * (1 << 20) / ((long long)fields * N * 8);
+    w = w / 32 * 32;
+    if (w < 32) w = 32;
+    return w < n_cols ? (int)w : n_cols;
+}
+
+template <int LG, int CL>
+static int launch_r16_cols_power(const R16PowerArgs &r, int groups, cudaStream_t st) {
+    constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);
+    const size_t smem16 = (size_t)CL * PITCH * sizeof(float2) + (size_t)16 * T * (sizeof(float2) + sizeof(float));
+    static bool set_ = false;
+    if (!set_) {
+        MLB_CUDA(cudaFuncSetAttribute(fft16_cols_power_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+        set_ = true;
+    }
+    dim3 gc((r.n_cols + CL - 1) / CL, groups);
+    fft16_cols_power_kernel<LG, CL><<<gc, T, smem16, st>>>(r);
+    return check_launch("mlb_fft_cols_power(radix 16)");
+}
+static int r16_cols_power_dispatch(int lgSub, const R16PowerArgs &r, int groups, cudaStream_t st) {
+    switch (lgSub) {
+        case 8: return launch_r16_cols_power<8, 16>(r, groups, st);
+        case 9: return launch_r16_cols_power<9, 8>(r, groups, st);
+        case 10: return launch_r16_cols_power<10, 4>(r, groups, st);
+        case 11: return launch_r16_cols_power<11, 2>(r, groups, st);
+    }
+    set_error("radix-16 column+power pass: unsupported sub-length 2^%d", lgSub);
+    return MLB_ERR_ARG;
+}
+}  // namespace mlb
+
 extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int N,
                             int n_cols, const mlb_c64 *tw, int out_roll, int batch, void *stream) {
     mlb::FftArgs a;
@@ -1183,6 +1391,52 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     MLB_REQUIRE(tw && n_cols > 0 && ld_in >= n_cols && ld_out >= n_cols, "mlb_fft_cols: bad sizes");
     MLB_REQUIRE(out_roll >= 0 && out_roll < N, "mlb_fft_cols: roll out of range");
     a.tw = reinterpret_cast<const float2 *>(tw);
+    if (!mlb::is_pow2(N) && mlb::g_mixed_engine == 1) {
+        // big-radix engine: direct while >= 16 columns per CTA fit, else N = A x B in two passes (the first in place
+        // on the INPUT buffer, which is then scratch; in-place calls fall back to the direct pass)
+        cudaStream_t st = (cudaStream_t)stream;
+        bool inplace = false;
+        for (int b = 0; b < batch; ++b) inplace = inplace || (a.in[b] == a.out[b]);
+        int A = 1;
+        if (!inplace && mlb::mix2_col_lanes(N, n_cols) < 16 && n_cols >= 8) {
+            static const int cand[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
+            for (int c : cand)
+                if (N % c == 0 && N / c >= 2) { A = c; break; }
+        }
+        const int B = N / A;
+        mlb::Mix2Args m2;
+        MLB_REQUIRE(mlb::mix2_plan(m2, B) > 0, "mlb_fft_cols: cannot factor %d", B);
+        for (int b = 0; b < 4; ++b) { m2.in[b] = a.in[b]; m2.out[b] = a.out[b]; }
+        m2.tw = a.tw; m2.ld_in = ld_in; m2.ld_out = ld_out; m2.other = n_cols; m2.tw_mul = A; m2.Ntot = N;
+        m2.in_roll_r = m2.in_roll_c = m2.out_roll = 0; m2.s1 = m2.s2 = 1; m2.roll = out_roll;
+        if (A > 1) {
+            mlb::Mix2FirstArgs f;
+            for (int b = 0; b < 4; ++b) { f.in[b] = a.in[b]; f.out[b] = const_cast<float2 *>(a.in[b]); }
+            f.tw = a.tw; f.ld = ld_in; f.n_cols = n_cols; f.B = B;
+            if (int rc = mlb::mix2_first(A, f, batch, st)) return rc;
+            m2.in_gs = B; m2.in_rs = 1; m2.out_gs = 1; m2.out_rs = A;
+        } else {
+            m2.in_gs = 0; m2.in_rs = 1; m2.out_gs = 0; m2.out_rs = 1;
+        }
+        if (int rc = mlb::mix2_set_smem()) return rc;
+        const int mp = mlb::mix2_max_per(m2);
+        int rl = 1;
+        while (rl < 32 && rl * 2 * mp <= 256) rl *= 2;
+        if (mlb::g_mixed_reg && rl * mp <= 256 && rl >= 8 && (mlb::g_mixed_reg == 2 || rl * mp >= 205)) {
+            m2.lanes = rl; m2.lg_lanes = mlb::ilog2(rl);   // one butterfly per thread and stage: register variant
+            dim3 gr((n_cols + rl - 1) / rl, A, batch);
+            const size_t sm2 = mlb::mix2_smem(B, rl) / 2;
+            if (mlb::g_mixed_occ == 2) mlb::mix2_reg_kernel<true, 2><<<gr, 256, sm2, st>>>(m2);
+            else if (mlb::g_mixed_occ == 3) mlb::mix2_reg_kernel<true, 3><<<gr, 256, sm2, st>>>(m2);
+            else mlb::mix2_reg_kernel<true, 4><<<gr, 256, sm2, st>>>(m2);
+            return mlb::check_launch("mlb_fft_cols(mixed radix, registers)");
+        }
+        const int lanes = mlb::mix2_col_lanes(B, n_cols);
+        m2.lanes = lanes; m2.lg_lanes = mlb::ilog2(lanes);
+        dim3 grid((n_cols + lanes - 1) / lanes, A, batch);
+        mlb::mix2_cols_kernel<<<grid, 256, mlb::mix2_smem(B, lanes), st>>>(m2);
+        return mlb::check_launch("mlb_fft_cols(mixed radix)");
+    }
     if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
         mlb::MixArgs m;
         mlb::fill_mixed(m, a, N);
@@ -1204,61 +1458,35 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1; a.evict_first = 0;
     if (mlb::g_cols_engine == 1 && a.lgN >= 8 && a.lgN <= 13) {
-        // radix-16 register kernels: direct up to 2048 points; 4096 / 8192 = 16 x (256 / 512) in two passes, the
-        // first of them in place on the INPUT buffer (which is therefore scratch, as with the radix-4 four-step)
+        // radix-16 register kernels: direct up to 2048 points; 4096 / 8192 = 16 x (256 / 512) in two passes run
+        // strip by strip, the first of them writing into the first strip of the INPUT buffer (which is therefore
+        // scratch, as with the radix-4 four-step)
         cudaStream_t st = (cudaStream_t)stream;
         mlb::R16ColArgs r;
         for (int b = 0; b < 4; ++b) { r.in[b] = a.in[b]; r.out[b] = a.out[b]; }
         r.ld_in = ld_in; r.ld_out = ld_out; r.n_cols = n_cols; r.lgNtot = a.lgN; r.roll = out_roll;
-        int lgSub = a.lgN, groups = 1;
-        if (a.lgN >= 12) {
-            for (int b = 0; b < batch; ++b)
-                MLB_REQUIRE(a.in[b] != a.out[b], "mlb_fft_cols: N >= 4096 needs out != in (the input is used as scratch)");
-            lgSub = a.lgN - 4; groups = 16;
+        r.tw = a.tw;
+        if (a.lgN < 12) {
+            r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+            return mlb::r16_cols_dispatch(a.lgN, r, 1, batch, st);
+        }
+        for (int b = 0; b < batch; ++b)
+            MLB_REQUIRE(a.in[b] != a.out[b], "mlb_fft_cols: N >= 4096 needs out != in (the input is used as scratch)");
+        const int lgSub = a.lgN - 4;
+        r.in_gs = 1 << lgSub; r.in_rs = 1; r.out_gs = 1; r.out_rs = 16;
+        const int strip = mlb::r16_strip_cols(N, n_cols, batch);
+        for (int c0 = 0; c0 < n_cols; c0 += strip) {
+            const int w = (n_cols - c0 < strip) ? n_cols - c0 : strip;
             mlb::R16FirstArgs f;
-            for (int b = 0; b < 4; ++b) f.data[b] = const_cast<float2 *>(a.in[b]);
-            f.tw = a.tw; f.ld = ld_in; f.n_cols = n_cols; f.B = 1 << lgSub;
-            dim3 gf((n_cols + 31) / 32, (f.B + 7) / 8, batch);
+            for (int b = 0; b < 4; ++b) { f.in[b] = a.in[b] + c0; f.out[b] = const_cast<float2 *>(a.in[b]); r.out[b] = a.out[b] + c0; }
+            f.tw = a.tw; f.ld = ld_in; f.n_cols = w; f.B = 1 << lgSub;
+            dim3 gf((w + 31) / 32, (f.B + 7) / 8, batch);
             mlb::fft16_cols_first_kernel<<<gf, 256, 0, st>>>(f);
             if (int rc = mlb::check_launch("mlb_fft_cols(radix-16 first pass)")) return rc;
-            r.in_gs = 1 << lgSub; r.in_rs = 1; r.out_gs = 1; r.out_rs = 16;
-        } else {
-            r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+            r.n_cols = w;
+            if (int rc = mlb::r16_cols_dispatch(lgSub, r, 16, batch, st)) return rc;
         }
-        r.tw = a.tw;
-#define MLB_R16_COLS(LG, CL)                                                                                          \
-    case LG: {                                                                                                       \
-        constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);                     \
-        const size_t smem16 = (size_t)CL * PITCH * sizeof(float2);                                                   \
-        static bool set_ = false;                                                                                    \
-        if (!set_) {                                                                                                 \
-            MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem16));                                                             \
-            set_ = true;                                                                                             \
-        }                                                                                                            \
-        dim3 gc((n_cols + CL - 1) / CL, groups, batch);                                                              \
-        static bool set3_ = false, set4_ = false;                                                                    \
-        if ((mlb::g_r16_occ == 3 || mlb::g_r16_occ == 0) && T <= 256) {                                                                       \
-            if (!set3_) {                                                                                            \
-                MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_kernel<LG, CL, 3>,                                     \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
-                set3_ = true;                                                                                        \
-            }                                                                                                        \
-            mlb::fft16_cols_kernel<LG, CL, 3><<<gc, T, smem16, st>>>(r);                                             \
-        } else if (mlb::g_r16_occ == 4 && T <= 256) {                                                                \
-            if (!set4_) {                                                                                            \
-                MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_kernel<LG, CL, 4>,                                     \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
-                set4_ = true;                                                                                        \
-            }                                                                                                        \
-            mlb::fft16_cols_kernel<LG, CL, 4><<<gc, T, smem16, st>>>(r);                                             \
-        } else {                                                                                                     \
-            mlb::fft16_cols_kernel<LG, CL><<<gc, T, smem16, st>>>(r);                                                \
-        }                                                                                                            \
-        return mlb::check_launch("mlb_fft_cols(radix 16)");                                                          \
-    }
-        switch (lgSub) { MLB_R16_COLS(8, 16) MLB_R16_COLS(9, 8) MLB_R16_COLS(10, 4) MLB_R16_COLS(11, 4) }
-#undef MLB_R16_COLS
+        return MLB_OK;
     }
     if (a.lgN >= 12) {
         for (int b = 0; b < batch; ++b)
@@ -1367,33 +1595,29 @@ extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, 
         r.Z = (float)Zd16;
         r.ld_in = ld_in; r.ldp = ldp; r.n_cols = n_cols; r.lgNtot = mlb::ilog2(N); r.accumulate = accumulate ? 1 : 0;
         r.roll = out_roll;
-        if (groups > 1) {               // first pass of the 16 x B decomposition, in place on the inputs
+        const int xblocks = (n_cols + cl16 - 1) / cl16;
+        r.bs_stride = xblocks; r.bs_off = 0;
+        if (groups == 1) {
+            r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+            return mlb::r16_cols_power_dispatch(lgSub, r, 1, st16);
+        }
+        // 16 x B decomposition, strip by strip: the first pass of every strip writes into the first strip of the
+        // inputs (scratch), the fused second pass reads it back from L2
+        r.in_gs = 1 << lgSub; r.in_rs = 1; r.out_gs = 1; r.out_rs = 16;
+        const int strip = mlb::r16_strip_cols(N, n_cols, 4);
+        for (int c0 = 0; c0 < n_cols; c0 += strip) {
+            const int w = (n_cols - c0 < strip) ? n_cols - c0 : strip;
             mlb::R16FirstArgs f1;
-            for (int f = 0; f < 4; ++f) f1.data[f] = const_cast<float2 *>(r.in[f]);
-            f1.tw = r.tw; f1.ld = ld_in; f1.n_cols = n_cols; f1.B = 1 << lgSub;
-            dim3 gf((n_cols + 31) / 32, (f1.B + 7) / 8, 4);
+            for (int f = 0; f < 4; ++f) { f1.in[f] = r.in[f] + c0; f1.out[f] = const_cast<float2 *>(r.in[f]); }
+            f1.tw = r.tw; f1.ld = ld_in; f1.n_cols = w; f1.B = 1 << lgSub;
+            dim3 gf((w + 31) / 32, (f1.B + 7) / 8, 4);
             mlb::fft16_cols_first_kernel<<<gf, 256, 0, st16>>>(f1);
             if (int rc = mlb::check_launch("mlb_fft_cols_power(radix-16 first pass)")) return rc;
-            r.in_gs = 1 << lgSub; r.in_rs = 1; r.out_gs = 1; r.out_rs = 16;
-        } else {
-            r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+            mlb::R16PowerArgs rs = r;
+            rs.n_cols = w; rs.uy = uy + c0; rs.P = P + c0; rs.bs_off = c0 / cl16;
+            if (int rc = mlb::r16_cols_power_dispatch(lgSub, rs, 16, st16)) return rc;
         }
-#define MLB_R16_CP(LG, CL)                                                                                            \
-    case LG: {                                                                                                       \
-        constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);                     \
-        const size_t smem16 = (size_t)CL * PITCH * sizeof(float2) + (size_t)16 * T * (sizeof(float2) + sizeof(float)); \
-        static bool set_ = false;                                                                                    \
-        if (!set_) {                                                                                                 \
-            MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_cols_power_kernel<LG, CL>,                                      \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));                \
-            set_ = true;                                                                                             \
-        }                                                                                                            \
-        dim3 gc((n_cols + CL - 1) / CL, groups);                                                                     \
-        mlb::fft16_cols_power_kernel<LG, CL><<<gc, T, smem16, st16>>>(r);                                            \
-        return mlb::check_launch("mlb_fft_cols_power(radix 16)");                                                    \
-    }
-        switch (lgSub) { MLB_R16_CP(8, 16) MLB_R16_CP(9, 8) MLB_R16_CP(10, 4) MLB_R16_CP(11, 2) }
-#undef MLB_R16_CP
+        return MLB_OK;
     }
     const int cl = cols_power_tile(N);
     MLB_REQUIRE(cl > 0, "mlb_fft_cols_power: length %d must be a power of two in 256..2048", N);

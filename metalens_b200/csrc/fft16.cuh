@@ -303,6 +303,7 @@ struct R16PowerArgs {
     float Z;
     int ld_in, ldp, n_cols, lgNtot, accumulate;
     int in_gs, in_rs, out_gs, out_rs, roll;
+    int bs_stride, bs_off;            // block_sums[blockIdx.y * bs_stride + bs_off + blockIdx.x] (column strips)
 };
 
 template <int LGN, int CL>
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(CL * (1 << (LGN - 4)), 2) fft16_cols_power_ker
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < T / 32; ++w) s += ws[w];
-            a.block_sums[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+            a.block_sums[(size_t)blockIdx.y * a.bs_stride + a.bs_off + blockIdx.x] = s;
         }
     }
 }
@@ -394,8 +395,12 @@ __global__ void __launch_bounds__(CL * (1 << (LGN - 4)), 2) fft16_cols_power_ker
 // a warp is 32 adjacent columns, so every access is a 256-byte row segment.  The second pass
 // (fft16_cols_kernel with in_gs = B, out_rs = 16) transforms the B contiguous rows of each k1:
 //     X[k1 + 16 k2] = sum_n2 W_B^(n2 k2) [ W_N^(n2 k1) sum_n1 x[B n1 + n2] W_16^(n1 k1) ]
+// The host runs the two passes strip by strip (a few hundred columns of all four fields, sized to stay in L2):
+// the first pass of every strip writes into the columns of the FIRST strip (dead by then), so the intermediate
+// is produced and consumed in L2 and only that one strip-sized region is ever dirty.
 struct R16FirstArgs {
-    float2 *data[4];
+    const float2 *in[4];
+    float2 *out[4];                   // == in for an in-place pass; same row pitch
     const float2 *tw;                 // plain table W_N^t of the FULL length N
     int ld, n_cols, B;
 };
@@ -404,15 +409,17 @@ __global__ void __launch_bounds__(256) fft16_cols_first_kernel(const R16FirstArg
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int n2 = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (c >= a.n_cols || n2 >= a.B) return;
-    float2 *__restrict__ d = pick4(a.data, blockIdx.z) + (size_t)n2 * a.ld + c;
+    const size_t off = (size_t)n2 * a.ld + c;
+    const float2 *__restrict__ src = pick4(a.in, blockIdx.z) + off;
+    float2 *__restrict__ dst = pick4(a.out, blockIdx.z) + off;
     const size_t step = (size_t)a.B * a.ld;
     float2 v[16];
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = d[m * step];
+    for (int m = 0; m < 16; ++m) v[m] = __ldcs(src + m * step);       // read once: stream through L2
     dft_reg<16>(v);
     apply_twiddle_powers<16>(v, __ldg(a.tw + n2));
 #pragma unroll
-    for (int m = 0; m < 16; ++m) d[m * step] = v[m];
+    for (int m = 0; m < 16; ++m) dst[m * step] = v[m];
 }
 
 }  // namespace mlb

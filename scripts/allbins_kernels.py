@@ -13,7 +13,13 @@ cengine = int(os.environ.get("COLS_ENGINE", "0"))
 lib.mlb_set_option(b"cols_engine", cengine)
 occ = int(os.environ.get("R16_OCC", "0"))
 lib.mlb_set_option(b"r16_occupancy", occ)
-print("rows_engine", engine, "cols_engine", cengine, "r16_occupancy", occ)
+strip = int(os.environ.get("COLS_STRIP_MB", "48"))
+lib.mlb_set_option(b"cols_strip_mb", strip)
+lib.mlb_set_option(b"mixed_registers", int(os.environ.get("MIXED_REG", "1")))
+lib.mlb_set_option(b"mixed_occupancy", int(os.environ.get("MIXED_OCC", "0")))
+print("mixed_registers", lib.mlb_get_option(b"mixed_registers"), "mixed_occupancy", lib.mlb_get_option(b"mixed_occupancy"))
+fuse_mode = os.environ.get("FUSE", "default")          # default | always | never
+print("rows_engine", engine, "cols_engine", cengine, "r16_occupancy", occ, "cols_strip_mb", strip, "fuse", fuse_mode)
 sizes = [int(a) for a in sys.argv[1:]] or [1024, 2048, 3375, 3600, 4096, 8192]
 wl, ng = 580e-9, 1.459
 d = wl / 2.2
@@ -34,7 +40,9 @@ for M in sizes:
     # two field sets so that consecutive launches never find their input in L2 (for M >= 2048)
     sets = [[torch.randn(M, M, dtype=torch.complex64, device="cuda", generator=g) for _ in range(4)] for _ in range(2)]
     for fuse in (True, False):
-        plan = FarfieldPlan((M, M), d, d, wl, ng, stride=1, fuse_power=fuse)
+        if (fuse_mode == "never" and fuse) or (fuse_mode == "always" and not fuse):
+            continue
+        plan = FarfieldPlan((M, M), d, d, wl, ng, stride=1, fuse_power=("always" if fuse_mode == "always" else fuse))
         if fuse and not plan.fused:
             continue
         rr = [0]

@@ -261,8 +261,16 @@ def test_fft_passes_match_numpy(fft_engines):
     pb, k4 = _lib.ptr_array([bad])
     assert lib.mlb_fft_rows(pb, 14, pb, 14, 4, 14, 1, 1, bad.data_ptr(), 0, 0, 0, 0, 1, None) != 0   # 14 = 2*7: not 5-smooth
     # mixed radix (good_fft_number sizes): rows with fold + rolls, and columns
-    for N, other, s1, s2 in ((6, 5, 1, 1), (12, 7, 2, 3), (45, 9, 1, 2), (100, 4, 3, 1), (675, 3, 1, 1), (720, 5, 2, 2),
-                             (1000, 2, 1, 1), (6000, 2, 1, 1)):
+    # engine 1 = big-radix kernels (fftmix.cuh; long columns in two passes when >= 8 columns), 0 = radix 2..5 kernels
+    cases = [(1, c) for c in ((6, 5, 1, 1), (12, 7, 2, 3), (45, 9, 1, 2), (100, 4, 3, 1), (675, 3, 1, 1), (720, 5, 2, 2),
+                              (1000, 2, 1, 1), (6000, 2, 1, 1), (3375, 37, 1, 1), (450, 20, 2, 1), (8100, 9, 1, 1),
+                              (2187, 12, 1, 1), (3125, 8, 1, 1), (1536, 16, 1, 2), (3600, 40, 1, 1), (20, 33, 1, 1))]
+    cases += [(0, c) for c in ((12, 7, 2, 3), (675, 3, 1, 1), (720, 5, 2, 2), (6000, 2, 1, 1))]
+    # engine 2 here = big-radix engine with the register (one butterfly per thread) kernels switched off
+    cases += [(2, c) for c in ((12, 7, 2, 3), (675, 3, 1, 1), (3375, 37, 1, 1), (450, 20, 2, 1), (3600, 40, 1, 1))]
+    for engine, (N, other, s1, s2) in cases:
+        lib.mlb_set_option(b"mixed_engine", min(engine, 1))
+        lib.mlb_set_option(b"mixed_registers", 0 if engine == 2 else 2)      # 2: register kernels wherever they apply
         big = (rng.standard_normal((other * s1, N * s2)) + 1j * rng.standard_normal((other * s1, N * s2))).astype(np.complex64)
         ldi = N * s2 + 3
         dbig = [torch.zeros(other * s1, ldi, dtype=torch.complex64).cuda()]
@@ -288,6 +296,9 @@ def test_fft_passes_match_numpy(fft_engines):
         torch.cuda.synchronize()
         refc = np.roll(np.fft.fft(folded.T.astype(np.complex64).astype(complex), axis=0), ro, axis=0)
         assert field_error(dco[0][:, :other].cpu().numpy(), refc) < 3e-6, ("mixed cols", N)
+        assert float(dco[0][:, other:].abs().max()) == 0.0                       # pitch padding untouched
+    lib.mlb_set_option(b"mixed_engine", 1)
+    lib.mlb_set_option(b"mixed_registers", 1)
     # fused fold: [n_rows*s1][N*s2] input, summed over the aliased copies while loading
     n_rows, N, s1, s2 = 6, 64, 3, 4
     big = (rng.standard_normal((n_rows * s1, N * s2)) + 1j * rng.standard_normal((n_rows * s1, N * s2))).astype(np.complex64)
@@ -570,6 +581,8 @@ def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
     if wide == 16:
         lib.mlb_set_option(b"cols_engine", 1)
         lib.mlb_set_option(b"rows_engine", 2)
+        if Mx >= 4096:
+            lib.mlb_set_option(b"cols_strip_mb", 1 if Mx == 4096 else 0)     # 4096: ten 32-column strips (ragged last)
     else:
         lib.mlb_set_option(b"cols_engine", 0)
         lib.mlb_set_option(b"rows_engine", 0)
@@ -599,6 +612,7 @@ def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
         lib.mlb_set_option(b"cols_power_wide", -1)
         lib.mlb_set_option(b"cols_engine", 1)
         lib.mlb_set_option(b"rows_engine", 2)
+        lib.mlb_set_option(b"cols_strip_mb", 0)
 
 
 @pytest.mark.parametrize("name,stride", [("lens256_seed1", 1), ("lens256_seed1_rot", 1)])
@@ -624,6 +638,7 @@ def test_options_api():
     assert lib.mlb_set_option(b"rows_ctas_per_sm", 7) != 0
     assert lib.mlb_fft_cols_power_blocks(1000, 64) == 0 and lib.mlb_fft_cols_power_blocks(16384, 64) == 0
     assert lib.mlb_get_option(b"cols_engine") == 1 and lib.mlb_get_option(b"rows_engine") == 2
+    assert lib.mlb_get_option(b"cols_strip_mb") == 0 and lib.mlb_set_option(b"cols_strip_mb", -1) != 0
     assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 256 and lib.mlb_fft_cols_power_blocks(8192, 64) == 16 * 8
     lib.mlb_set_option(b"cols_engine", 0)
     try:
@@ -741,7 +756,9 @@ def test_radix16_column_kernels_match_numpy():
     rng = np.random.default_rng(17)
     lib.mlb_set_option(b"cols_engine", 1)
     try:
-        for N, n_cols in ((256, 45), (512, 17), (1024, 9), (2048, 6), (4096, 37), (8192, 33), (1024, 64)):
+        for N, n_cols, strip_mb in ((256, 45, 0), (512, 17, 0), (1024, 9, 0), (2048, 6, 0), (4096, 37, 0),
+                                    (8192, 33, 0), (1024, 64, 0), (4096, 77, 1), (8192, 70, 48), (8192, 70, 2)):
+            lib.mlb_set_option(b"cols_strip_mb", strip_mb)     # 1-2 MB: several 32-column strips with a ragged tail
             a = [(rng.standard_normal((N, n_cols)) + 1j * rng.standard_normal((N, n_cols))).astype(np.complex64) for _ in range(2)]
             tw = torch.empty(2 * N, dtype=torch.complex64).cuda()
             _lib.check(lib.mlb_fft_twiddle(N, tw.data_ptr(), None), "tw")
@@ -767,3 +784,4 @@ def test_radix16_column_kernels_match_numpy():
                 assert torch.equal(din[0], dout[0]) and torch.equal(din[1], dout[1])
     finally:
         lib.mlb_set_option(b"cols_engine", 1)
+        lib.mlb_set_option(b"cols_strip_mb", 0)
