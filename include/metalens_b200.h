@@ -137,6 +137,14 @@ int mlb_fft_rows_can_transpose(int N);
 int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
                  int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
                  int batch, void *stream);
+/* mlb_fft_rows with an 8-byte device work area owned by the caller (two uint32 counters, zero before the FIRST call;
+ * the kernel leaves them zero again; one area per concurrently running call): the TMA-fed persistent kernel then
+ * hands rows to its CTAs dynamically instead of by a fixed stride, so CTAs that start late (SMs still busy with
+ * another stream's kernels) do not delay the pass.
+ * NULL, or a path other than the TMA-fed kernel, behaves exactly like mlb_fft_rows. */
+int mlb_fft_rows_ws(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
+                    int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
+                    int batch, void *work_counter, void *stream);
 /* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}.  In-place allowed
  * for power-of-two N <= 2048 and every other length; for power-of-two N >= 4096 the transform is a two-pass
  * decomposition that uses the INPUT buffer as scratch (it is overwritten) and needs out != in; for other lengths
@@ -178,6 +186,9 @@ int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols,
  *   mixed_occupancy      resident CTAs per SM those kernels are compiled for: 0 (default: rows 2, columns 4), 2..4
  *   cols_strip_mb        two-pass (>= 4096-point) column transforms run strip by strip, strips of this many MB of all
  *                        fields (intermediate stays in L2); 0 (default) = one strip
+ *   rows_dynamic         1 = mlb_fft_rows_ws uses its work counter (kernel alone +2.5 %, pipelined items -12 %: measured),
+ *                        0 (default) = fixed stride
+ *   r16_min_lg           the radix-16 kernels serve lengths from 2^this up (default 10; 8..13), the radix-4 ones below
  *   r16_occupancy        resident CTAs per SM the radix-16 kernels are compiled for: 0 (default: rows 4, columns 3), 2..4
  * mlb_get_option returns -1 for an unknown name. */
 int mlb_set_option(const char *name, int value);

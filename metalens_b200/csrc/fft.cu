@@ -100,6 +100,7 @@ struct FftArgs {
     float2 *out[4];
     const float2 *tw;
     int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader, transpose_out, evict_first;
+    unsigned int *work_counter;       // TMA-fed row pass: two zeroed device counters (next item, finished CTAs) or NULL
 };
 
 // folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
@@ -201,7 +202,10 @@ __device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *
 // mbarrier transaction counts); 256 consumer threads add the segments into registers as they land, then run
 // the row FFT and store the row.  The producer keeps prefetching the next rows while the consumers are in
 // their butterfly stages, so loads stay in flight all the time (the thread-issued loader loses ~20 % of the
-// HBM bandwidth to that phase alternation).  CTAs are persistent and stride over (field, row) work items.
+// HBM bandwidth to that phase alternation).  CTAs are persistent; the producer draws (field, row) work items
+// from a device counter when the caller provides one (a CTA that starts late -- its SM still busy with the
+// previous item's column pass on another stream -- then simply takes fewer rows), else strides over them; it
+// hands the item number to the consumers through the slot of the item's first segment (-1 = no more work).
 constexpr int TMA_CONSUMERS = 256;
 
 template <int LGN, int RING_KB = 64>
@@ -210,7 +214,8 @@ struct RowsTmaCfg {
     static constexpr int SLOT_BYTES = N * 8;
     static constexpr int SLOTS = (RING_KB * 1024 / SLOT_BYTES) > 32 ? 32 : ((RING_KB * 1024 / SLOT_BYTES) < 4 ? 4 : (RING_KB * 1024 / SLOT_BYTES));
     static constexpr int EPT = N / TMA_CONSUMERS;                       // complex elements per consumer thread
-    static constexpr size_t SMEM = (size_t)SLOTS * SLOT_BYTES + 3 * (size_t)N * 8 + 2 * SLOTS * sizeof(uint64_t) + 16;
+    static constexpr size_t SMEM = (size_t)SLOTS * SLOT_BYTES + 3 * (size_t)N * 8 + 2 * SLOTS * sizeof(uint64_t) +
+                                   SLOTS * sizeof(int) + 16;
 };
 
 template <int LGN, int RING_KB = 64>
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
     float2 *ring = reinterpret_cast<float2 *>(tsm);
     float2 *buf0 = ring + (size_t)S * N, *buf1 = buf0 + N, *stw = buf1 + N;
     uint64_t *full = reinterpret_cast<uint64_t *>(stw + N), *empty = full + S;
+    int *wq = reinterpret_cast<int *>(empty + S);                           // work item of the segment in each slot
     const int tid = threadIdx.x;
     const int nseg = a.s1 * a.s2;
     const int work = a.other * batch;
@@ -237,34 +243,49 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
         if (tid == TMA_CONSUMERS) {
             long long g = 0;
             const uint64_t pol = l2_evict_first_policy();
-            for (int w = blockIdx.x; w < work; w += gridDim.x) {
-                const int f = w / a.other, r = w - f * a.other;
+            for (int seq = 0;; ++seq) {
+                int w = a.work_counter ? (int)atomicAdd(a.work_counter, 1u) : blockIdx.x + seq * (int)gridDim.x;
+                if (w >= work) {
+                    w = -1;
+                    // every CTA draws exactly one number >= work; the last one to do so re-arms the two counters
+                    if (a.work_counter && atomicAdd(a.work_counter + 1, 1u) == gridDim.x - 1) {
+                        a.work_counter[0] = 0u;
+                        a.work_counter[1] = 0u;
+                    }
+                }
+                const int f = w < 0 ? 0 : w / a.other, r = w < 0 ? 0 : w - f * a.other;
                 int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
                 const float2 *src = pick4(a.in, f);
-                for (int t = 0; t < nseg; ++t, ++g) {
+                for (int t = 0; t < (w < 0 ? 1 : nseg); ++t, ++g) {
                     const int slot = (int)(g % S);
                     const long long use = g / S;
                     if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
+                    wq[slot] = w;                                           // released by the arrive below
+                    if (w < 0) { mbar_arrive(&full[slot]); break; }         // end marker: completes the phase, no data
                     const int t1 = t / a.s2, t2 = t - t1 * a.s2;
                     mbar_expect_tx(&full[slot], Cfg::SLOT_BYTES);
                     const float2 *seg = src + (size_t)(rs + t1 * a.other) * a.ld_in + ((size_t)t2 << LGN);
                     if (a.evict_first) bulk_g2s_hint(ring + (size_t)slot * N, seg, Cfg::SLOT_BYTES, &full[slot], pol);
                     else bulk_g2s(ring + (size_t)slot * N, seg, Cfg::SLOT_BYTES, &full[slot]);
                 }
+                if (w < 0) break;
             }
         }
         return;
     }
     // ---------------------------------------------------- consumers
     long long g = 0;
-    for (int w = blockIdx.x; w < work; w += gridDim.x) {
+    for (;;) {
+        mbar_wait(&full[(int)(g % S)], (uint32_t)((g / S) & 1));             // first segment of the next item (or the end marker)
+        const int w = wq[(int)(g % S)];
+        if (w < 0) break;
         const int f = w / a.other, r = w - f * a.other;
         float acc[2 * EPT];
 #pragma unroll
         for (int v = 0; v < 2 * EPT; ++v) acc[v] = 0.f;
         for (int t = 0; t < nseg; ++t, ++g) {
             const int slot = (int)(g % S);
-            mbar_wait(&full[slot], (uint32_t)((g / S) & 1));
+            if (t > 0) mbar_wait(&full[slot], (uint32_t)((g / S) & 1));
             const float2 *sl = ring + (size_t)slot * N;
             if (EPT >= 2) {
 #pragma unroll
@@ -919,6 +940,11 @@ static int g_rows_evict_first = 1;     // TMA row pass: stream the aperture thro
 static int g_cols_strip_mb = 0;        // two-pass column transforms (>= 4096 points): run them strip by strip, strips of this many MB (so the
                                        // intermediate stays in L2); 0 = one strip (default: measured faster on B200, the per-strip launches cost
                                        // more than the saved HBM round trip)
+static int g_rows_dynamic = 0;         // TMA row pass: 1 = draw rows from the caller's work counter (mlb_fft_rows_ws).  Measured on B200
+                                       // (scripts/ab_rows_dynamic.py): the kernel alone gains 2.5 % (90.4 vs 93.0 us at cfg3), but the two-stream
+                                       // item pipeline loses 12 % (371 vs 331 us per step) -- default off
+static int g_r16_min_lg = 10;          // radix-16 kernels from 2^this points up (8..13): below 1024 points the radix-4 kernels launch more
+                                       // CTAs and measure faster on B200 (cfg2 / the 256-point sweep of bench.py)
 static int g_mixed_occ = 0;            // register kernels of the big-radix engine: resident CTAs per SM they are compiled for
                                        // (2..4; 0 = default: rows 2, columns 4 -- measured on B200, scripts/allbins_kernels.py)
 static int g_mixed_reg = 1;            // big-radix engine: use the one-butterfly-per-thread register kernels where they apply
@@ -988,6 +1014,8 @@ extern "C" int mlb_set_option(const char *name, int value) {
     else if (n == "rows_l2_evict_first") mlb::g_rows_evict_first = value ? 1 : 0;
     else if (n == "rows_engine") { MLB_REQUIRE(value >= 0 && value <= 2, "rows_engine: 0..2"); mlb::g_rows_engine = value; }
     else if (n == "r16_occupancy") { MLB_REQUIRE(value == 0 || (value >= 2 && value <= 4), "r16_occupancy: 0, 2..4"); mlb::g_r16_occ = value; }
+    else if (n == "rows_dynamic") mlb::g_rows_dynamic = value ? 1 : 0;
+    else if (n == "r16_min_lg") { MLB_REQUIRE(value >= 8 && value <= 13, "r16_min_lg: 8..13"); mlb::g_r16_min_lg = value; }
     else if (n == "cols_engine") { MLB_REQUIRE(value >= 0 && value <= 1, "cols_engine: 0..1"); mlb::g_cols_engine = value; }
     else if (n == "rows_ring_kb") { MLB_REQUIRE(value == 64 || value == 128, "rows_ring_kb: 64 or 128"); mlb::g_rows_ring_kb = value; }
     else if (n == "cols_power_wide") mlb::g_cols_power_wide = value < 0 ? -1 : (value ? 1 : 0);
@@ -1007,6 +1035,8 @@ extern "C" int mlb_get_option(const char *name) {
     if (n == "rows_ring_kb") return mlb::g_rows_ring_kb;
     if (n == "rows_engine") return mlb::g_rows_engine;
     if (n == "cols_engine") return mlb::g_cols_engine;
+    if (n == "r16_min_lg") return mlb::g_r16_min_lg;
+    if (n == "rows_dynamic") return mlb::g_rows_dynamic;
     if (n == "r16_occupancy") return mlb::g_r16_occ;
     if (n == "cols_power_wide") return mlb::g_cols_power_wide;
     if (n == "cols_strip_mb") return mlb::g_cols_strip_mb;
@@ -1109,10 +1139,11 @@ extern "C" int mlb_fft_rows_can_transpose(int N) {
     return (mlb::g_rows_tma && mlb::is_pow2(N) && N >= 256 && N <= 2048) ? 1 : 0;
 }
 
-extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
-                            int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
-                            int transpose_out, int batch, void *stream) {
+static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
+                         int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
+                         int transpose_out, int batch, unsigned int *work_counter, void *stream) {
     mlb::FftArgs a;
+    a.work_counter = nullptr;
     if (int rc = mlb::fill_args(a, h_in, h_out, batch, "mlb_fft_rows")) return rc;
     int radix_probe[16];
     MLB_REQUIRE(N >= 2 && N <= mlb::FFT_MAX_N && mlb::factor_235(N, radix_probe) > 0,
@@ -1186,7 +1217,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
     // radix-16 register kernels (256..8192 points)
-    if (!transpose_out && a.lgN >= 8 && a.lgN <= 13 &&
+    if (!transpose_out && a.lgN >= mlb::g_r16_min_lg && a.lgN <= 13 &&
         (mlb::g_rows_engine == 1 || (mlb::g_rows_engine == 2 && s1 == 1 && s2 == 1))) {
         bool inplace = false;
         for (int b = 0; b < batch; ++b) inplace = inplace || (a.in[b] == a.out[b]);
@@ -1259,6 +1290,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
         if (per_sm < 1) per_sm = 1;                                                                                  \
         int grid = n_sm * per_sm;                                                                                    \
         if (grid > n_rows * batch) grid = n_rows * batch;                                                            \
+        a.work_counter = work_counter;                                                                               \
         mlb::fft_rows_tma_kernel<LG, KB><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch);                \
         return mlb::check_launch("mlb_fft_rows(tma)");                                                               \
     }
@@ -1306,6 +1338,20 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
 #undef MLB_ROWS_CASE
 #undef MLB_ROWS_LAUNCH
     return mlb::check_launch("mlb_fft_rows");
+}
+
+extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
+                            int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
+                            int transpose_out, int batch, void *stream) {
+    return fft_rows_impl(h_in, ld_in, h_out, ld_out, n_rows, N, s1, s2, tw, in_roll_r, in_roll_c, out_roll, transpose_out,
+                         batch, nullptr, stream);
+}
+
+extern "C" int mlb_fft_rows_ws(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
+                               int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
+                               int transpose_out, int batch, void *work_counter, void *stream) {
+    return fft_rows_impl(h_in, ld_in, h_out, ld_out, n_rows, N, s1, s2, tw, in_roll_r, in_roll_c, out_roll, transpose_out,
+                         batch, mlb::g_rows_dynamic ? reinterpret_cast<unsigned int *>(work_counter) : nullptr, stream);
 }
 
 namespace mlb {
@@ -1457,7 +1503,7 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
     a.in_roll_r = 0; a.in_roll_c = 0; a.out_roll = out_roll; a.s1 = a.s2 = 1; a.evict_first = 0;
-    if (mlb::g_cols_engine == 1 && a.lgN >= 8 && a.lgN <= 13) {
+    if (mlb::g_cols_engine == 1 && a.lgN >= mlb::g_r16_min_lg && a.lgN <= 13) {
         // radix-16 register kernels: direct up to 2048 points; 4096 / 8192 = 16 x (256 / 512) in two passes run
         // strip by strip, the first of them writing into the first strip of the INPUT buffer (which is therefore
         // scratch, as with the radix-4 four-step)
@@ -1563,7 +1609,7 @@ static bool r16_power_shape(int N, int *lgSub, int *cl, int *groups) {
 
 extern "C" int mlb_fft_cols_power_blocks(int N, int n_cols) {
     if (n_cols <= 0) return 0;
-    if (mlb::g_cols_engine == 1) {
+    if (mlb::g_cols_engine == 1 && N >= (1 << mlb::g_r16_min_lg)) {
         int lgSub, cl, groups;
         if (!r16_power_shape(N, &lgSub, &cl, &groups)) return 0;
         return groups * ((n_cols + cl - 1) / cl);
@@ -1577,7 +1623,7 @@ extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, 
                                   double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
                                   double *block_sums, mlb_c64 *const *h_Fhat, int ldf, void *stream) {
     MLB_REQUIRE(h_in && tw && ux && uy && P, "mlb_fft_cols_power: NULL pointer");
-    if (mlb::g_cols_engine == 1 && !h_Fhat) {
+    if (mlb::g_cols_engine == 1 && !h_Fhat && N >= (1 << mlb::g_r16_min_lg)) {
         int lgSub, cl16, groups;
         MLB_REQUIRE(r16_power_shape(N, &lgSub, &cl16, &groups), "mlb_fft_cols_power: length %d must be a power of two in 256..8192", N);
         MLB_REQUIRE(n_cols > 0 && ld_in >= n_cols && ldp >= n_cols && out_roll >= 0 && out_roll < N, "mlb_fft_cols_power: bad sizes");

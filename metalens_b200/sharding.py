@@ -67,7 +67,7 @@ class ShardedFarfield:
     the four device fields of an item this rank owns.
     """
 
-    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None):
+    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None, tail_priority=0):
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.group = group
@@ -85,6 +85,7 @@ class ShardedFarfield:
         # caller's stream, everything after it (column pass, power epilogue, tile copy, the collective) on a side
         # stream, so the tail of tile k executes under the aperture pass of tile k+1
         self._side = None
+        self._tail_priority = tail_priority             # side stream priority (-1 = high; measured: no effect on B200)
         self._tail_done = [None] * len(self.tiles)     # per plan: its buffers are free again (side-stream event)
         self._side_done = None
 
@@ -126,7 +127,7 @@ class ShardedFarfield:
         """overlap=True on CUDA: two-stream software pipeline over the local tiles (see __init__)."""
         main = torch.cuda.current_stream()
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.plans[0].P.device)
+            self._side = torch.cuda.Stream(device=self.plans[0].P.device, priority=self._tail_priority)
         side = self._side
         totals = []
         for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):

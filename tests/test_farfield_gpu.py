@@ -207,9 +207,11 @@ def fft_engines(request):
     rows, cols = request.param
     lib.mlb_set_option(b"rows_engine", rows)
     lib.mlb_set_option(b"cols_engine", cols)
+    lib.mlb_set_option(b"r16_min_lg", 8)            # radix-16 kernels from 256 points (default: from 1024)
     yield request.param
     lib.mlb_set_option(b"rows_engine", 2)
     lib.mlb_set_option(b"cols_engine", 1)
+    lib.mlb_set_option(b"r16_min_lg", 10)
 
 
 @pytest.mark.parametrize("fft_engines", [(0, 0), (2, 1)], indirect=True, ids=["radix4", "radix16"])
@@ -581,6 +583,7 @@ def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
     if wide == 16:
         lib.mlb_set_option(b"cols_engine", 1)
         lib.mlb_set_option(b"rows_engine", 2)
+        lib.mlb_set_option(b"r16_min_lg", 8)
         if Mx >= 4096:
             lib.mlb_set_option(b"cols_strip_mb", 1 if Mx == 4096 else 0)     # 4096: ten 32-column strips (ragged last)
     else:
@@ -613,6 +616,7 @@ def test_fused_cols_power_matches_separate_kernels(shape, stride, wide):
         lib.mlb_set_option(b"cols_engine", 1)
         lib.mlb_set_option(b"rows_engine", 2)
         lib.mlb_set_option(b"cols_strip_mb", 0)
+        lib.mlb_set_option(b"r16_min_lg", 10)
 
 
 @pytest.mark.parametrize("name,stride", [("lens256_seed1", 1), ("lens256_seed1_rot", 1)])
@@ -638,6 +642,7 @@ def test_options_api():
     assert lib.mlb_set_option(b"rows_ctas_per_sm", 7) != 0
     assert lib.mlb_fft_cols_power_blocks(1000, 64) == 0 and lib.mlb_fft_cols_power_blocks(16384, 64) == 0
     assert lib.mlb_get_option(b"cols_engine") == 1 and lib.mlb_get_option(b"rows_engine") == 2
+    assert lib.mlb_get_option(b"r16_min_lg") == 10 and lib.mlb_fft_cols_power_blocks(512, 512) == 128     # radix-4 tile
     assert lib.mlb_get_option(b"cols_strip_mb") == 0 and lib.mlb_set_option(b"cols_strip_mb", -1) != 0
     assert lib.mlb_fft_cols_power_blocks(1024, 1023) == 256 and lib.mlb_fft_cols_power_blocks(8192, 64) == 16 * 8
     lib.mlb_set_option(b"cols_engine", 0)
@@ -722,6 +727,7 @@ def test_radix16_row_kernels_match_numpy():
     lib = _lib.load()
     rng = np.random.default_rng(16)
     lib.mlb_set_option(b"rows_engine", 1)
+    lib.mlb_set_option(b"r16_min_lg", 8)
     try:
         for N, n_rows, s1, s2 in ((256, 37, 1, 1), (512, 9, 1, 1), (1024, 5, 1, 1), (2048, 3, 1, 1), (4096, 3, 1, 1),
                                   (8192, 2, 1, 1), (256, 7, 2, 3), (1024, 6, 4, 4), (4096, 2, 2, 1), (8192, 1, 1, 2)):
@@ -745,6 +751,7 @@ def test_radix16_row_kernels_match_numpy():
             assert float(dres[0][:, N:].abs().max()) == 0.0                     # pitch padding untouched
     finally:
         lib.mlb_set_option(b"rows_engine", 2)
+        lib.mlb_set_option(b"r16_min_lg", 10)
 
 
 def test_radix16_column_kernels_match_numpy():
@@ -755,6 +762,7 @@ def test_radix16_column_kernels_match_numpy():
     lib = _lib.load()
     rng = np.random.default_rng(17)
     lib.mlb_set_option(b"cols_engine", 1)
+    lib.mlb_set_option(b"r16_min_lg", 8)
     try:
         for N, n_cols, strip_mb in ((256, 45, 0), (512, 17, 0), (1024, 9, 0), (2048, 6, 0), (4096, 37, 0),
                                     (8192, 33, 0), (1024, 64, 0), (4096, 77, 1), (8192, 70, 48), (8192, 70, 2)):
@@ -785,3 +793,4 @@ def test_radix16_column_kernels_match_numpy():
     finally:
         lib.mlb_set_option(b"cols_engine", 1)
         lib.mlb_set_option(b"cols_strip_mb", 0)
+        lib.mlb_set_option(b"r16_min_lg", 10)
