@@ -794,3 +794,24 @@ def test_radix16_column_kernels_match_numpy():
         lib.mlb_set_option(b"cols_engine", 1)
         lib.mlb_set_option(b"cols_strip_mb", 0)
         lib.mlb_set_option(b"r16_min_lg", 10)
+
+
+def test_dynamic_row_distribution_is_bit_identical():
+    """mlb_fft_rows_ws: the TMA-fed row pass drawing its rows from a self-re-arming device counter gives the same
+    bits as the fixed-stride distribution, call after call (the counters are left zero)."""
+    from metalens_b200 import _lib
+    from metalens_b200.farfield import FarfieldPlan
+    lib = _lib.load()
+    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(1024, 5, WL)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
+    plan = FarfieldPlan((1024, 1024), x[1] - x[0], y[1] - y[0], WL, NG, stride=2)
+    assert plan.method == "fft"
+    P0 = plan.run(dev)[0].clone()
+    lib.mlb_set_option(b"rows_dynamic", 1)
+    try:
+        for _ in range(3):
+            P1 = plan.run(dev)[0]
+            assert _same(P0, P1)
+            assert int(plan.work_counter.abs().sum().item()) == 0
+    finally:
+        lib.mlb_set_option(b"rows_dynamic", 0)
