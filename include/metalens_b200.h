@@ -309,7 +309,8 @@ int mlb_nearfield_blocks(int nx, int ny);
 /* Fills ring_aux / ring_aux_f32 / ring_lut of the descriptor (device buffers owned by the caller) from its ring
  * arrays and table axes; once per lens and wavelength, before the first mlb_nearfield_assemble(). */
 int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream);
-/* tuning knob: register budget variant of the complex64 kernel (min resident blocks/SM: 1, 5 or 6) */
+/* tuning knob: register budget variant of the complex64 kernel (min resident blocks/SM: 1, 5, 6 or 8), or
+ * 100 + lg: warp tile of 2^lg samples along y times 32 / 2^lg along x (lg 2..5; query mlb_nearfield_blocks after) */
 int mlb_nearfield_tune(int min_blocks);
 int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
                            int out_is_double, double *power_block_sums, long long *stats, int want_stats,

@@ -118,12 +118,31 @@ __device__ __forceinline__ cplx expi(double x) {
     sincos(x, &s, &c);
     return {c, s};
 }
+// (cos, sin)(pi r) for |r| <= 1: quadrant q = rint(2r), Taylor polynomials on |z| = |r - q/2| <= 1/4 (truncation
+// < 3e-8, below the fp32 rounding); the library sincospif spends a third of its instructions on arguments
+// that cannot occur here
+__device__ __forceinline__ cf cospi_sinpi_unit(float r) {
+    const float q = rintf(r + r);
+    const float z = fmaf(q, -0.5f, r), z2 = z * z;
+    float sp = fmaf(z2, 0.0821458866f, -0.599264529f);        // pi^9/9!, -pi^7/7!
+    sp = fmaf(sp, z2, 2.55016404f);                           // pi^5/5!
+    sp = fmaf(sp, z2, -5.16771278f);                          // -pi^3/3!
+    sp = fmaf(sp, z2, 3.14159265f);
+    const float s0 = sp * z;
+    float cp = fmaf(z2, 0.235330630f, -1.33526277f);          // pi^8/8!, -pi^6/6!
+    cp = fmaf(cp, z2, 4.05871213f);                           // pi^4/4!
+    cp = fmaf(cp, z2, -4.93480220f);                          // -pi^2/2
+    const float c0 = fmaf(cp, z2, 1.0f);
+    const int iq = (int)q;                                    // -2..2
+    float s = (iq & 1) ? c0 : s0, c = (iq & 1) ? s0 : c0;
+    if (iq & 2) s = -s;
+    if (((iq >> 1) ^ iq) & 1) c = -c;
+    return {c, s};
+}
 __device__ __forceinline__ cf expi_fast(double x) {
     const double t = x * 0.15915494309189535;                 // x / 2 pi
     const double fr = t - rint(t);                            // [-1/2, 1/2] turns
-    float s, c;
-    sincospif((float)(fr + fr), &s, &c);                      // angle = pi * (2 fr)
-    return {c, s};
+    return cospi_sinpi_unit((float)(fr + fr));                // angle = pi * (2 fr)
 }
 
 // The interpolation cell of one sample in the float32 copy of a pack: every diffraction order of the sample
@@ -226,7 +245,7 @@ struct NfOut {
     double *power_warp_sums;
     long long *stats;
     int *violation;
-    int ld, out_is_double;
+    int ld, out_is_double, lg_wy;     // lg_wy: log2 of the warp tile's y extent (5 = 32 x 1 ... 2 = 4 x 8)
 };
 
 // The diffraction-order loop of one sample (periphery: primed grating frame, nearfield.py:263-327; centre:
@@ -293,11 +312,14 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                                                                       const __grid_constant__ NfUniform U, const NfOut out) {
     using Acc = typename std::conditional<FAST, cf, cplx>::type;      // per-sample field accumulators
     using W = typename std::conditional<FAST, float, double>::type;   // incident weights
-    const int j = blockIdx.x * NF_THREADS + threadIdx.x;   // y index (fast)
-    const int i = blockIdx.y;                              // x index
+    // a warp covers wy (y, fast) x 32/wy (x) samples, the four warps of a block are stacked along y: compact warp
+    // footprints touch fewer rings and table cells per gather than a 32 x 1 line that crosses the rings radially
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wy = 1 << out.lg_wy;
+    const int j = (blockIdx.x * (NF_THREADS / 32) + warp) * wy + (lane & (wy - 1));   // y index (fast)
+    const int i = blockIdx.y * (32 >> out.lg_wy) + (lane >> out.lg_wy);               // x index
     const double PI = 3.14159265358979323846;
     double local_power = 0.0;
-    if (j < L.ny) {
+    if (j < L.ny && i < L.nx) {
         const double x = L.x_pts[i], y = L.y_pts[j];
         const double r = sqrt(x * x + y * y);                                  // nearfield.py:118
         // which_ring = searchsorted(boundaries, r) - 1  (left-biased, :125-128): the bin table brackets the
@@ -545,18 +567,25 @@ __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n
 
 }  // namespace mlb
 
+static int g_nf_lg_wy = 3;       // warp tile: 2^lg_wy samples along y times 32 / 2^lg_wy along x (mlb_nearfield_tune(100 + lg_wy)); 8 x 4 measured fastest
 static int g_nf_minblocks = 6;   // 80 registers, 6 blocks/SM: fastest on B200 (scripts/tune_nearfield.py)
 /* tuning knob: minimum resident blocks per SM the complex64 kernel is compiled for (1, 5, 6 or 8) */
 extern "C" int mlb_nearfield_tune(int min_blocks) {
+    if (min_blocks >= 102 && min_blocks <= 105) { g_nf_lg_wy = min_blocks - 100; return MLB_OK; }   // warp tile shape
     MLB_REQUIRE(min_blocks == 1 || min_blocks == 5 || min_blocks == 6 || min_blocks == 8,
-                "mlb_nearfield_tune: min_blocks must be 1, 5, 6 or 8");
+                "mlb_nearfield_tune: min_blocks must be 1, 5, 6 or 8 (or 102..105 for the warp tile)");
     g_nf_minblocks = min_blocks;
     return MLB_OK;
 }
 
+static dim3 nf_grid(int nx, int ny) {
+    const int wy = 1 << g_nf_lg_wy, wx = 32 >> g_nf_lg_wy, by = wy * (mlb::NF_THREADS / 32);
+    return dim3((ny + by - 1) / by, (nx + wx - 1) / wx);
+}
 /* one incident-power partial sum per warp */
 extern "C" int mlb_nearfield_blocks(int nx, int ny) {
-    return nx * ((ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS) * (mlb::NF_THREADS / 32);
+    const dim3 g = nf_grid(nx, ny);
+    return (int)(g.x * g.y) * (mlb::NF_THREADS / 32);
 }
 
 static int check_pack(const mlb_table_pack &p, const char *what) {
@@ -610,11 +639,11 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     MLB_REQUIRE(L.source_pol >= 0 && L.source_pol <= 2 && !(L.plane_wave && L.source_pol == 2),
                 "mlb_nearfield_assemble: bad source polarisation (nearfield.py:85, :224)");
     MLB_REQUIRE(!want_stats || stats, "mlb_nearfield_assemble: want_stats needs a stats buffer");
-    MLB_REQUIRE((size_t)L.ny <= 65535u * mlb::NF_THREADS * 32u && L.nx <= 65535, "mlb_nearfield_assemble: grid too large");
+    MLB_REQUIRE(L.ny <= (1 << 24) && L.nx <= 65535, "mlb_nearfield_assemble: grid too large");
     mlb::NfOut out;
     out.F[0] = Ex; out.F[1] = Ey; out.F[2] = Hx; out.F[3] = Hy;
     out.power_warp_sums = power_block_sums; out.stats = stats; out.violation = violation;
-    out.ld = ld; out.out_is_double = out_is_double;
+    out.ld = ld; out.out_is_double = out_is_double; out.lg_wy = g_nf_lg_wy;
     // launch-uniform scalars in IEEE float64, the expressions of nearfield.py:213 / :262 / :287
     const double PI = 3.14159265358979323846;
     mlb::NfUniform U;
@@ -626,7 +655,7 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     U.lut_scale = L.n_lut / L.lut_r_max;
     U.ng2 = (float)((U.kg / U.kvac) * (U.kg / U.kvac));
     U.cf = (float)(L.Z0 * U.inv_kg_n * U.kvac);
-    dim3 grid((L.ny + mlb::NF_THREADS - 1) / mlb::NF_THREADS, L.nx);
+    const dim3 grid = nf_grid(L.nx, L.ny);
     const cudaStream_t st = (cudaStream_t)stream;
     if (want_stats) {
         if (out_is_double) mlb::nearfield_kernel<true, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);

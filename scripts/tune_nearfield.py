@@ -15,6 +15,20 @@ periph, center, _ = make_design(collections, f, spec["radius"], hgs)
 plan = NearfieldPlan(wl, periph, center, hgs)
 x = np.linspace(-R, R, M)
 ref = None
+for lg in (5, 4, 3, 2):          # warp tile 32x1, 16x2, 8x4, 4x8 (y x x)
+    _lib.check(lib.mlb_nearfield_tune(100 + lg), "tile")
+    _lib.check(lib.mlb_nearfield_tune(6), "tune")
+    out = torch.zeros((4, M, M), dtype=torch.complex64, device="cuda")
+    for _ in range(2): plan.run(0.0, 0.0, -f, "x", x, x, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): _o, pw = plan.run(0.0, 0.0, -f, "x", x, x, out=out)
+    e1.record(); torch.cuda.synchronize()
+    if lg == 5: ref5, pw5 = out.clone(), pw.item()
+    print("warp tile %2d x %d: %.3f ms  max|diff| vs 32x1 %.2e  power rel diff %.1e" % (1 << lg, 32 >> lg, e0.elapsed_time(e1) / 5,
+          (out - ref5).abs().max().item() / ref5.abs().max().item(), abs(pw.item() - pw5) / abs(pw5)), flush=True)
+_lib.check(lib.mlb_nearfield_tune(103), "tile")
 for variant, dtype in ((1, torch.complex64), (5, torch.complex64), (6, torch.complex64), (8, torch.complex64), (1, torch.complex128)):
     _lib.check(lib.mlb_nearfield_tune(variant), "tune")
     out = torch.zeros((4, M, M), dtype=dtype, device="cuda")

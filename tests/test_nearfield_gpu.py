@@ -210,3 +210,56 @@ def test_incoherent_xyz_dipoles_on_device(golden_dir):
     assert bool((torch.isnan(P_sum) == torch.isnan(ref)).all())
     assert ((P_sum - ref).abs()[fin].max() / ref[fin].max()).item() < 1e-6
     assert abs(total.item() - totals) <= 1e-12 * abs(totals)
+
+
+def test_ring_records_and_warp_tiles(golden_dir):
+    """mlb_nearfield_prepare: the per-ring records and the ring bin table equal their numpy definitions
+    (nearfield.py:125, :161-165; scipy RGI find_indices for the period axis); and the assembly kernel gives the
+    same fields for every warp tile shape (32x1 ... 4x8 samples) and register-budget variant."""
+    from metalens_b200 import _lib
+    from metalens_b200.nearfield import NearfieldPlan
+    lib = _lib.load()
+    g = np.load(os.path.join(golden_dir, "nearfield_small_x_ragged.npz"))
+    collections, hgs = library(synth_lens.SMALL_LENS)
+    periph = periphery_from(g, collections)
+    plan = NearfieldPlan(580e-9, periph, g["center"], hgs)
+    torch.cuda.synchronize()
+    n = plan.n_rings
+    aux = plan._keep["ring_aux"].cpu().numpy().reshape(n, 8)
+    ints = plan._keep["ring_aux"].cpu().view(torch.int32).numpy().reshape(n, 16)[:, 14:16]      # (gc, i2)
+    rc = np.asarray(periph["r_center_list"], float); gp = np.asarray(periph["grating_period_list"], float)
+    apg = 2.0 * np.pi / np.asarray(periph["num_around_circle_list"], float)
+    assert np.array_equal(aux[:, 0], rc) and np.array_equal(aux[:, 1], gp) and np.array_equal(aux[:, 2], apg)
+    assert np.array_equal(aux[:, 3], rc * apg) and np.array_equal(aux[:, 4], 2.0 * np.pi / gp)
+    assert np.array_equal(aux[:, 5], 2.0 * np.pi / (rc * apg))
+    gci = np.asarray(periph["gratingcollection_index_here_list"])
+    assert np.array_equal(ints[:, 0], gci)
+    for r in range(n):
+        axis = plan.packs[gci[r]].axes[-plan.packs[gci[r]].n[2]:]
+        i2 = int(np.clip(np.searchsorted(axis, gp[r], side="right") - 1, 0, axis.size - 2))
+        assert ints[r, 1] == i2 and aux[r, 6] == (gp[r] - axis[i2]) / (axis[i2 + 1] - axis[i2])
+    bounds = np.hstack((periph["r_min_list"], periph["r_max_list"][-1]))
+    lut = plan._keep["ring_lut"].cpu().numpy()
+    edges = np.arange(plan.n_lut) * (plan.lens_max_r / plan.n_lut)
+    assert np.array_equal(lut[:-1], np.searchsorted(bounds, edges, side="left")) and lut[-1] == n + 1
+    ref = None
+    try:
+        for tune in (105, 104, 103, 102):
+            _lib.check(lib.mlb_nearfield_tune(tune), "tile")
+            for variant in (6, 1):
+                _lib.check(lib.mlb_nearfield_tune(variant), "variant")
+                out, power = plan.run(0.0, 0.0, float(g["source"][2]), "x", g["x_pts"], g["y_pts"])
+                got = out[:, :, :g["y_pts"].size].cpu().numpy()
+                for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
+                    assert field_error(got[k], g[key]) < 3e-6
+                assert abs(power.item() - g["power"]) <= 1e-11 * abs(g["power"])
+                if ref is None:
+                    ref = got
+                assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+            out64, _ = plan.run(0.0, 0.0, float(g["source"][2]), "x", g["x_pts"], g["y_pts"], out_dtype=torch.complex128)
+            got64 = out64[:, :, :g["y_pts"].size].cpu().numpy()
+            for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
+                assert field_error(got64[k], g[key]) < 1e-9
+    finally:
+        lib.mlb_nearfield_tune(103)
+        lib.mlb_nearfield_tune(6)
