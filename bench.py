@@ -14,9 +14,11 @@ value  = far-field points/s with the aperture fields already resident in HBM
 e2e    = same metric through FarfieldPlan.run_host(): pinned host fields -> H2D ->
          kernels -> D2H of P, every step
 N > 1  : one process per GPU (torchrun), weak scaling -- every rank owns a full batch of its
-         own apertures (far-field tiles of different sources); one NCCL all-gather of the P
-         tiles per step is inside the timed region (asynchronous, double-buffered: it overlaps the
-         kernels of the next step).
+         own apertures (far-field tiles of different sources); one all-gather of the P tiles per
+         step is inside the timed region (asynchronous, double-buffered: it overlaps the kernels of
+         the next step).  The gather pulls the peers' tiles over NVLink with the copy engines
+         (torch symmetric memory; no SM-resident collective kernel next to the persistent row
+         pass) and falls back to NCCL all_gather_into_tensor where that cannot be set up.
 Extra keys on the same line: roofline (dominant kernel), kernels (CUDA-event time of every kernel of a
 step), paths_points_per_s (other formulations on the same workload), other_workloads (cfg2),
 nearfield_assembly (hot path B), fom_sweep (cfg5 shape), cpu_baseline.
@@ -485,7 +487,9 @@ def ours(args):
             "data": "synthetic",
             "config": {"workload": w["name"], "method": p0.method, "batch_items_per_gpu": n_items,
                        "aperture": [M, M], "far_field": [K, K], "l2": "inputs larger than L2 (%.0f MB per step)"
-                       % (n_items * 32 * M * M / 1e6), "parallelism": "far-field tiles sharded, %d rank(s)" % world},
+                       % (n_items * 32 * M * M / 1e6), "parallelism": "far-field tiles sharded, %d rank(s)%s" % (
+                           world, "" if world == 1 else ", tile exchange: " + {"p2p": "peer-to-peer pulls over NVLink (copy "
+                           "engines, symmetric memory)", "nccl": "NCCL all-gather"}.get(sharded._gather, sharded._gather))},
             "e2e": {"value": e2e_value, "unit": "far-field points/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),

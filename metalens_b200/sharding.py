@@ -67,7 +67,7 @@ class ShardedFarfield:
     the four device fields of an item this rank owns.
     """
 
-    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None, tail_priority=0):
+    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None, tail_priority=0, gather="auto"):
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.group = group
@@ -88,6 +88,70 @@ class ShardedFarfield:
         self._tail_priority = tail_priority             # side stream priority (-1 = high; measured: no effect on B200)
         self._tail_done = [None] * len(self.tiles)     # per plan: its buffers are free again (side-stream event)
         self._side_done = None
+        # gather="p2p": the finished tiles are exchanged by PULLING them from the peers' buffers over NVLink with the
+        # copy engines (torch symmetric memory: peer-mapped buffers + signal-pad barriers), no SM-resident collective
+        # kernel competing with the persistent row pass; "nccl": all_gather_into_tensor; "auto": p2p when it can be
+        # set up (CUDA, world > 1), else nccl
+        assert gather in ("auto", "nccl", "p2p")
+        self._gather = gather
+        self._symm = None                               # per flip buffer: (handle, [peer tile-stack tensors])
+        self._comm = None
+        self._gather_done = [None, None]
+
+    def _setup_p2p(self, shape, dtype, device):
+        """Allocate the two local tile stacks in symmetric memory and map the peers' (collective call)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        symm = []
+        for b in (0, 1):
+            t = symm_mem.empty(shape, dtype=dtype, device=device)
+            hdl = symm_mem.rendezvous(t, group)
+            peers = [hdl.get_buffer(r, shape, dtype) for r in range(self.world)]
+            self._local[b] = t
+            self._out[b] = torch.empty((self.world * shape[0],) + tuple(shape[1:]), dtype=dtype, device=device)
+            symm.append((hdl, peers))
+        self._symm = symm
+        self._comm = torch.cuda.Stream(device=device)
+
+    def _alloc(self, b, P):
+        """Tile stack + gather target of flip buffer b (first use)."""
+        shape = (len(self.tiles),) + tuple(P.shape)
+        if self._gather != "nccl" and self.world > 1 and P.is_cuda and self._symm is None:
+            try:
+                self._setup_p2p(shape, P.dtype, P.device)
+                self._gather = "p2p"
+                return
+            except Exception as e:                      # no symmetric memory here: the NCCL collective does the job
+                if self._gather == "p2p":
+                    raise
+                import sys
+                print("metalens_b200.sharding: peer-to-peer gather unavailable (%s: %s), using NCCL all-gather"
+                      % (type(e).__name__, str(e)[:200]), file=sys.stderr)
+                self._gather = "nccl"
+                self._symm = None
+        if self._local[b] is None:
+            self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
+            self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
+
+    def _gather_p2p(self, b, producer_stream):
+        """Pull every rank's tile stack into out[b] on the communication stream (copy engines), bracketed by the two
+        barriers of torch's low-contention all-gather: all stacks ready before anyone pulls, all pulls done before
+        anyone overwrites its stack.  Returns the (n_items, n_rows, Ky) view of out[b]; complete after finish()."""
+        hdl, peers = self._symm[b]
+        ready = torch.cuda.Event()
+        ready.record(producer_stream)
+        t = len(self.tiles)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            hdl.barrier(channel=b)
+            for step in range(self.world):
+                r = (self.rank - step) % self.world
+                self._out[b][r * t:(r + 1) * t].copy_(peers[r], non_blocking=True)
+            hdl.barrier(channel=b)
+            done = torch.cuda.Event()
+            done.record(self._comm)
+        self._gather_done[b] = done
+        return self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
 
     @property
     def items_needed(self):
@@ -111,12 +175,16 @@ class ShardedFarfield:
         for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
             P, total = plan.run(fields_of(tile.item)) if runner is None else runner(plan, fields_of(tile.item))
             if self._local[b] is None:
-                shape = (len(self.tiles),) + tuple(P.shape)
-                self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
-                self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
+                self._alloc(b, P)
+            if k == 0 and self._gather_done[b] is not None:      # peers may still be pulling this stack (p2p, two steps ago)
+                torch.cuda.current_stream().wait_event(self._gather_done[b])
             self._local[b][k].copy_(P)
             totals.append(total)
-        if overlap and self.world > 1:
+        if self._gather == "p2p" and self.world > 1 and self._symm is not None:
+            res = self._gather_p2p(b, torch.cuda.current_stream())
+            if not overlap:
+                torch.cuda.current_stream().wait_event(self._gather_done[b])
+        elif overlap and self.world > 1:
             res, self._work[b] = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group,
                                               out=self._out[b], async_op=True)
         else:
@@ -144,14 +212,20 @@ class ShardedFarfield:
                     self._work[b] = None
                 P, total = second()
                 if self._local[b] is None:
-                    shape = (len(self.tiles),) + tuple(P.shape)
-                    self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
-                    self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
+                    self._alloc(b, P)
+                if k == 0 and self._gather_done[b] is not None:  # peers may still be pulling this stack (p2p)
+                    side.wait_event(self._gather_done[b])
                 self._local[b][k].copy_(P)
                 totals.append(total)
                 done = torch.cuda.Event()
                 done.record(side)
                 self._tail_done[k] = done
+        if self._gather == "p2p" and self.world > 1 and self._symm is not None:
+            res = self._gather_p2p(b, side)
+            with torch.cuda.stream(side):
+                self._side_done = torch.cuda.Event()
+                self._side_done.record(side)
+            return res, totals
         with torch.cuda.stream(side):
             if self.world > 1:
                 res, self._work[b] = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group,
@@ -199,6 +273,9 @@ class ShardedFarfield:
                 else:
                     self._work[b].wait()
                 self._work[b] = None
+        for b in (0, 1):
+            if self._gather_done[b] is not None:
+                torch.cuda.current_stream().wait_event(self._gather_done[b])
         if self._side_done is not None:
             torch.cuda.current_stream().wait_event(self._side_done)
             self._side_done = None

@@ -1,5 +1,6 @@
-"""GPU (needs >= 2 devices, skipped otherwise): far-field tiles sharded over 2 ranks with NCCL equal the
-single-GPU far field bit for bit -- whole items per rank (fft) and row slabs of one item (fold)."""
+"""GPU (needs >= 2 devices, skipped otherwise): far-field tiles sharded over 2 ranks equal the single-GPU far
+field bit for bit -- whole items per rank (fft) and row slabs of one item (fold), with both exchange
+mechanisms (peer-to-peer pulls through symmetric memory, NCCL all-gather)."""
 import os
 import socket
 
@@ -19,7 +20,7 @@ def _fields(item):
     return apertures.focusing_lens(M, 50 + item, WL, NG, rotate=bool(item % 2))
 
 
-def _worker(rank, world, port, n_items, method, q):
+def _worker(rank, world, port, n_items, method, gather, q):
     import torch.distributed as dist
     from metalens_b200.farfield import FarfieldPlan
     from metalens_b200.sharding import ShardedFarfield
@@ -34,7 +35,7 @@ def _worker(rank, world, port, n_items, method, q):
         def make_plan(item, r0, r1):
             rows = None if (r0, r1) == (0, K) else (r0, r1)
             return FarfieldPlan((M, M), d, d, WL, NG, stride=4, method=method, rows=rows)
-        sh = ShardedFarfield(n_items, K, make_plan)
+        sh = ShardedFarfield(n_items, K, make_plan, gather=gather)
         dev = {i: [torch.from_numpy(a).cuda() for a in _fields(i)[:4]] for i in sh.items_needed}
         P, _ = sh.run(lambda item: dev[item])
         torch.cuda.synchronize()
@@ -49,20 +50,22 @@ def _worker(rank, world, port, n_items, method, q):
             ref.append(plan.run([torch.from_numpy(a).cuda() for a in _fields(i)[:4]])[0].clone())
         ref = torch.stack(ref)
         same = bool(((P == ref) | (torch.isnan(P) & torch.isnan(ref))).all())
-        q.put((rank, same))
+        q.put((rank, same and (gather == "auto" or sh._gather == gather)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_items,method", [(2, "fft"), (4, "fold"), (1, "fold"), (3, "dense")])
-def test_two_rank_nccl_gather_equals_single_gpu(n_items, method):
+@pytest.mark.parametrize("n_items,method,gather", [(2, "fft", "p2p"), (4, "fold", "nccl"), (1, "fold", "p2p"),
+                                                   (3, "dense", "auto"), (2, "fft", "nccl")])
+def test_two_rank_gather_equals_single_gpu(n_items, method, gather):
+    """gather: 'p2p' = tiles pulled over NVLink by the copy engines (symmetric memory), 'nccl' = all_gather_into_tensor"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, method, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, method, gather, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
