@@ -815,3 +815,56 @@ def test_dynamic_row_distribution_is_bit_identical():
             assert int(plan.work_counter.abs().sum().item()) == 0
     finally:
         lib.mlb_set_option(b"rows_dynamic", 0)
+
+
+@pytest.mark.parametrize("M", [3375, 2700])
+def test_reference_default_grid_full_size_properties(M):
+    """The reference's own usage at full size: a good_fft_number() aperture (3375 = 3^3 5^3, 2700 = 2^2 3^3 5^2),
+    ALL FFT bins, through the big-radix mixed engine.  Size-independent properties: a sample of bins against the
+    float64 direct sum (oracle), Parseval on the complex aperture sums, linearity, energy conservation of the lens
+    (KAT), and agreement of the register kernels with the shared-memory ones."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200 import _lib
+    from metalens_b200.farfield import FarfieldPlan
+    lib = _lib.load()
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 4, WL, NG)
+    d = x[1] - x[0]
+    dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+    plan = FarfieldPlan((M, M), d, d, WL, NG, stride=1)
+    assert plan.method == "fft"
+    P, total = plan.run(dev)
+    P = P.clone()
+    A = plan.amplitudes()                                           # (4, M, M) complex aperture sums
+    # Parseval: sum |F|^2 = M^2 sum |J|^2 per field
+    for f in range(4):
+        e_in = float((dev[f].abs().double() ** 2).sum())
+        e_out = float((A[f].abs().double() ** 2).sum())
+        assert abs(e_out - M * M * e_in) <= 2e-5 * max(M * M * e_in, 1e-300)
+    # oracle at a sample of bins
+    ii = np.array([0, 1, M // 3, M // 2 - 1, M // 2, M // 2 + 1, M - 7, M - 1])
+    jj = np.array([2, M // 5, M // 2, M // 2 + 9, M - 1])
+    P_ref, F_ref = fo.farfield_dense(Ex, Ey, Hx, Hy, d, d, plan.ux[ii], plan.uy[jj], WL, NG)
+    Pn = P.cpu().numpy()
+    sub = Pn[np.ix_(ii, jj)]
+    assert np.array_equal(np.isnan(sub), np.isnan(P_ref))
+    fin = np.isfinite(P_ref)
+    assert np.abs(sub - P_ref)[fin].max() / np.nanmax(Pn) < FF_TOL
+    for f in (0, 3):
+        got = A[f].cpu().numpy()[np.ix_(ii, jj)]
+        assert np.abs(got - F_ref[f]).max() <= 2e-5 * A[f].abs().max().item()
+    P_in = float((Ex * np.conj(Hy) - Ey * np.conj(Hx)).real.sum()) * d * d
+    assert abs(total.item() / P_in - 1) < 5e-3
+    # linearity of the aperture sums: FFT(2 a + i b) = 2 FFT(a) + i FFT(b)
+    other = [torch.roll(t, shifts=(5, -3), dims=(0, 1)).contiguous() for t in dev]
+    combo = [2.0 * a + 1j * b for a, b in zip(dev, other)]
+    A1 = A.clone()
+    plan.run(other); A2 = plan.amplitudes().clone()
+    plan.run(combo); A3 = plan.amplitudes()
+    assert ((A3 - (2.0 * A1 + 1j * A2)).abs().max() / A3.abs().max()).item() < 2e-5
+    # shared-memory (loop) kernels of the same engine give the same map
+    lib.mlb_set_option(b"mixed_registers", 0)
+    try:
+        P0, t0 = plan.run(dev)
+        assert power_map_error(P0.cpu().numpy(), Pn) < 1e-6 and abs(t0.item() - total.item()) <= 1e-6 * abs(total.item())
+    finally:
+        lib.mlb_set_option(b"mixed_registers", 1)
