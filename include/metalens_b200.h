@@ -119,6 +119,10 @@ int mlb_fft_twiddle(int N, mlb_c64 *out, void *stream);
  * samples per thread; 0 = first radix-4 stage done by the loader),
  * points per CTA, threads per CTA (64/128/256), vector width of the loads (1 or 2 complex). */
 int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_threads, int rows_vec);
+/* Host only (no GPU): radix sequence the mixed engine uses for a length N = 2^a 3^b 5^c (good_fft_number() sizes,
+ * nearfield.py:30-36): returns the stage count (< 0 on error), radix8[0..7] = radices (0-padded), *pad_shift = the
+ * shared-memory padding rule (4 = one pad per 16 elements, 30 = none). */
+int mlb_fft_mixed_plan(int N, int *radix8, int *pad_shift);
 /* longest transform the shared-memory passes support (8192 complex64) */
 int mlb_fft_max_length(void);
 /*

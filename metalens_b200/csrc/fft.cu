@@ -1133,6 +1133,18 @@ static int mix2_first(int A, const Mix2FirstArgs &f, int batch, cudaStream_t st)
 }
 }  // namespace mlb
 
+/* host only: the radix plan of the big-radix mixed engine for length N (no GPU needed) */
+extern "C" int mlb_fft_mixed_plan(int N, int *radix8, int *pad_shift) {
+    MLB_REQUIRE(radix8 != nullptr, "mlb_fft_mixed_plan: NULL output");
+    mlb::Mix2Args m;
+    const int ns = mlb::mix2_plan(m, N);
+    MLB_REQUIRE(ns > 0, "mlb_fft_mixed_plan: %d is not of the form 2^a 3^b 5^c (or needs more than %d stages)", N,
+                mlb::MIX2_MAX_STAGES);
+    for (int s = 0; s < mlb::MIX2_MAX_STAGES; ++s) radix8[s] = s < ns ? m.radix[s] : 0;
+    if (pad_shift) *pad_shift = m.pad_sh;
+    return ns;
+}
+
 extern "C" int mlb_fft_max_length(void) { return mlb::FFT_MAX_N; }
 
 extern "C" int mlb_fft_rows_can_transpose(int N) {

@@ -126,3 +126,24 @@ def test_reciprocals_are_exact():
         m = np.uint64(magic(d))
         lim = n[n * np.uint64(d) < (1 << 27)] if d > 64 else n
         assert np.array_equal((lim * m) >> np.uint64(32), lim // np.uint64(d)), d
+
+
+def test_library_planner_matches_the_emulated_one():
+    """mlb_fft_mixed_plan (host only) returns exactly the radix sequence emulated above, for every 5-smooth length
+    the engine serves, with odd radices first and the pad rule that follows from the first radix."""
+    import ctypes
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    sizes = sorted({2 ** a * 3 ** b * 5 ** c for a in range(14) for b in range(9) for c in range(6)
+                    if 2 <= 2 ** a * 3 ** b * 5 ** c <= 8192})
+    assert len(sizes) > 150
+    for N in sizes:
+        r = (ctypes.c_int * 8)()
+        sh = ctypes.c_int()
+        ns = lib.mlb_fft_mixed_plan(N, r, ctypes.byref(sh))
+        want = plan(N)
+        assert ns == len(want) and list(r)[:ns] == want and all(v == 0 for v in list(r)[ns:]), N
+        assert sh.value == (30 if want[0] % 2 else 4)
+        odd = [v % 2 for v in want]
+        assert odd == sorted(odd, reverse=True), (N, want)         # odd radices first
+    assert lib.mlb_fft_mixed_plan(14, (ctypes.c_int * 8)(), None) < 0   # 2 * 7: not 5-smooth
