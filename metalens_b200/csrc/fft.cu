@@ -1,4 +1,6 @@
-// Shared-memory FFT passes for power-of-two FFT-bin far-field grids.
+// FFT passes for FFT-bin far-field grids: this file holds the radix-4 shared-memory kernels, the
+// TMA-fed row pass and the host dispatch; fft16.cuh the register-resident radix-16 kernels (1024..8192 points),
+// fftmix.cuh the big-radix engine for the non-power-of-two good_fft_number() lengths.
 //
 // The reference's own algorithm is fft2(fftshift(J)) (nearfield_farfield.py:18-20).  For grids that
 // are (a stride of) the FFT bins, the aperture sum is a 2-D DFT of the (folded) aperture, done here
@@ -13,7 +15,8 @@
 //   * fftshift of input and output is index arithmetic ("rolls") at load/store time;
 //   * twiddles come from tables built with float64 phases, re-ordered per Stockham stage so that the
 //     shared-memory reads are conflict-free.
-// All sizes are powers of two, so index math is shifts and masks.
+// The kernels of this file serve powers of two (index math is shifts and masks) plus the first-generation
+// radix 2..5 kernels kept behind the option mixed_engine = 0.
 #include <math_constants.h>
 
 #include <string>
