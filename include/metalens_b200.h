@@ -325,6 +325,61 @@ int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void
 int mlb_table_eval(const double *axes, int n0, int n1, int n2, const double *values, const double *pts, int n,
                    double *out, void *stream);
 
+/* ---- 8e: multi-GPU exchange steps ------------------------------------------------------------------------------
+ * The reference is single-process; its independent units are the uy chunks of one transform
+ * (nearfield_farfield.py:45-66) and the y slabs of one assembly (nearfield.py:488-514).  Two families:
+ *  (1) peer-memory kernels (NVLink 5 / NVSwitch, plain ld/st on peer-mapped pointers).  The caller maps the peers'
+ *      buffers (CUDA IPC / torch symmetric memory) and passes host arrays of `world` device pointers, entry p = the
+ *      buffer of rank p as mapped in THIS process (entry `rank` = the local one);
+ *  (2) NCCL wrappers (mlb_comm_*) for callers without peer mappings.                                              */
+#define MLB_MAX_PEERS 16
+#define MLB_COMM_ID_BYTES 128
+/* sizes (in 32-bit words) of the two bookkeeping blocks of the peer kernels: `flags` -- one block per rank in
+ * peer-mapped (symmetric) memory, zero before first use -- and `local_state` -- plain device memory of the calling rank,
+ * zero before first use; word 3 of local_state becomes non-zero if a wait ever timed out (20 s: a lost peer must not
+ * hang the GPU).  One (flags, local_state) pair per stream of exchanges. */
+int mlb_peer_flag_words(void);
+int mlb_peer_state_words(void);
+/* Row pass of ONE 2-D transform spread over `world` ranks, fused with the all-to-all that follows it: like mlb_fft_rows
+ * (fold + fftshift rolls included) on this rank's n_rows folded rows -- input matrices [n_rows*s1][N*s2], folded row r
+ * = sum over t1 of input rows r + t1*n_rows, i.e. the rank holds the s1 aliased copies of ITS rows one after the other
+ * -- but output row r is row (out_row0 + r) mod n_rows_total of the distributed intermediate, and its column slab
+ * [p*N/world, (p+1)*N/world) is stored straight into rank p's buffer h_out_peers[p*batch + f] (pitch ld_out >= N/world
+ * complex) over NVLink while the next rows are still streaming in.  After a mlb_peer_barrier every rank holds all
+ * n_rows_total rows of its N/world columns and runs mlb_fft_cols / mlb_fft_cols_power on them.
+ * world must be a power of two <= MLB_MAX_PEERS dividing N; N in 256..2048 (the TMA-fed kernel), else
+ * MLB_ERR_UNSUPPORTED. */
+int mlb_fft_rows_scatter(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out_peers, int ld_out, int n_rows,
+                         int N, int s1, int s2, const mlb_c64 *tw, int in_roll_c, int out_roll, int out_row0,
+                         int n_rows_total, int world, int batch, void *stream);
+/* Flag barrier across the ranks, in stream order: returns (on the device) once every rank's stream has reached its
+ * matching mlb_peer_barrier -- all peer stores issued by earlier kernels of those streams are then visible. */
+int mlb_peer_barrier(void *const *h_flags, int rank, int world, void *local_state, void *stream);
+/* The ONE all-gather at the end, as pushes: copies the local block src (rows x row_bytes, pitch src_pitch)
+ * to byte offset dst_offset of every rank's destination h_dst[p] (pitch dst_pitch; a destination that IS the source is
+ * skipped), plus, optionally, n_aux doubles (the rank's total_P block sums) to h_aux_dst[p] + aux_offset.  Peers are
+ * written only after they entered the same gather (their previous result may be overwritten); completion is published
+ * with a release store that mlb_peer_wait acquires.  n_ctas (0 = default 16) CTAs of 512 threads; 16-byte granularity. */
+int mlb_peer_allgather(const void *src, long long src_pitch, int rows, long long row_bytes, void *const *h_dst,
+                       long long dst_pitch, long long dst_offset, const double *aux_src, void *const *h_aux_dst,
+                       int aux_offset, int n_aux, void *const *h_flags, int rank, int world, void *local_state,
+                       int n_ctas, void *stream);
+/* Wait (on the device, in stream order) until every peer's pushes of the latest mlb_peer_allgather this rank ran have
+ * landed in this rank's destination.  my_flags = this rank's flag block. */
+int mlb_peer_wait(const void *my_flags, int world, void *local_state, void *stream);
+
+/* NCCL wrappers (libnccl resolved at run time; MLB_ERR_UNSUPPORTED if it cannot be found).  mlb_comm_unique_id on one
+ * rank, ship the MLB_COMM_ID_BYTES bytes to the others by any means (the launcher's store, MPI, a file), then
+ * mlb_comm_init on every rank with its CUDA device current. */
+int mlb_comm_unique_id(char *h_id128);
+int mlb_comm_init(int rank, int world, const char *h_id128, void **comm);
+int mlb_comm_destroy(void *comm);
+/* recv[p*count + i] = send_p[i]: far-field power tiles (float32) / aperture slabs (complex64) */
+int mlb_allgather_P(void *comm, const float *send, float *recv, size_t count_per_rank, void *stream);
+int mlb_allgather_fields(void *comm, const mlb_c64 *send, mlb_c64 *recv, size_t count_per_rank, void *stream);
+/* recv[i] = sum over ranks of send[i], float64 (total_P, incident power); in place allowed */
+int mlb_allreduce_scalar(void *comm, const double *send, double *recv, int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

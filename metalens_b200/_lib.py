@@ -66,6 +66,22 @@ SIGNATURES = {
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_table_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),
+    # 8e: multi-GPU exchange steps (peer memory over NVLink; NCCL wrappers)
+    "mlb_peer_flag_words": (C.c_int, []),
+    "mlb_peer_state_words": (C.c_int, []),
+    "mlb_fft_rows_scatter": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mlb_peer_barrier": (C.c_int, [_PP, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_peer_allgather": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, _PP, C.c_longlong, C.c_longlong,
+                                     C.c_void_p, _PP, C.c_int, C.c_int, _PP, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p]),
+    "mlb_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "mlb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mlb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "mlb_allgather_P": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mlb_allgather_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mlb_allreduce_scalar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 _lib = None
@@ -96,8 +112,9 @@ def check(rc, what):
 
 
 def ptr_array(tensors):
-    """void*[len] of device pointers (host array, as the C-ABI's h_ arguments expect)."""
+    """void*[len] of device pointers (host array, as the C-ABI's h_ arguments expect); entries are
+    tensors or raw integer addresses (peer-mapped buffers)."""
     arr = (C.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
-        arr[i] = t.data_ptr()
+        arr[i] = t if isinstance(t, int) else t.data_ptr()
     return C.cast(arr, _PP), arr

@@ -106,6 +106,13 @@ struct FftArgs {
     unsigned int *work_counter;       // TMA-fed row pass: two zeroed device counters (next item, finished CTAs) or NULL
 };
 
+// Distributed 2-D transform (mlb_fft_rows_scatter): output row r of this rank is row (out_row0 + r) mod rows_total of
+// the intermediate, and its column slab p goes to rank p's peer-mapped buffer out[p][field].  world == 0: off.
+struct RowScatter {
+    float2 *out[MLB_MAX_PEERS][4];
+    int world, lg_slab, out_row0, rows_total;
+};
+
 // folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
 // Kept deliberately light (4 loads in flight, ~32 registers/thread): measured on B200, a deeper
 // per-thread load queue costs more in occupancy than it gains (scripts/tune_fft_rows.py).
@@ -222,7 +229,8 @@ struct RowsTmaCfg {
 };
 
 template <int LGN, int RING_KB = 64>
-__global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(const FftArgs a, int batch) {
+__global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(const FftArgs a, int batch,
+                                                                              const __grid_constant__ RowScatter sc) {
     using Cfg = RowsTmaCfg<LGN, RING_KB>;
     constexpr int N = Cfg::N, S = Cfg::SLOTS, EPT = Cfg::EPT;
     extern __shared__ __align__(128) unsigned char tsm[];
@@ -316,7 +324,20 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
         }
         const int cur = fft_ct<LGN, 0, 1, N, 0, true>(buf0, buf1, stw);
         const float2 *res = cur ? buf1 : buf0;
-        if (a.transpose_out) {
+        if (sc.world) {
+            // fused all-to-all: the row's column slabs go straight to their owners over NVLink (8-byte stores, a warp
+            // covers 256 contiguous bytes of one peer's row), overlapped with the TMA stream of the next rows
+            int R = sc.out_row0 + r;
+            if (R >= sc.rows_total) R -= sc.rows_total;
+            const size_t row_off = (size_t)R * a.ld_out;
+            const int slab_mask = (1 << sc.lg_slab) - 1;
+#pragma unroll
+            for (int v = 0; v < EPT; ++v) {
+                const int n = v * TMA_CONSUMERS + tid;
+                float2 *dst = sc.out[n >> sc.lg_slab][f];
+                dst[row_off + (n & slab_mask)] = res[(n - a.out_roll) & (N - 1)];
+            }
+        } else if (a.transpose_out) {
             // out[n][r]: the next pass transforms along r, so it finds ITS rows contiguous.  8-byte stores one
             // row pitch apart; the 33 MB intermediate lives in L2, which merges them into full sectors.
             float2 *dst = pick4(a.out, f) + r;
@@ -1156,15 +1177,19 @@ extern "C" int mlb_fft_rows_can_transpose(int N) {
 
 static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
                          int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
-                         int transpose_out, int batch, unsigned int *work_counter, void *stream) {
+                         int transpose_out, int batch, unsigned int *work_counter, void *stream,
+                         const mlb::RowScatter *scatter = nullptr) {
     mlb::FftArgs a;
+    static const mlb::RowScatter no_scatter = {};
+    const mlb::RowScatter &sc = scatter ? *scatter : no_scatter;
     a.work_counter = nullptr;
     if (int rc = mlb::fill_args(a, h_in, h_out, batch, "mlb_fft_rows")) return rc;
     int radix_probe[16];
     MLB_REQUIRE(N >= 2 && N <= mlb::FFT_MAX_N && mlb::factor_235(N, radix_probe) > 0,
                 "mlb_fft_rows: length %d must be of the form 2^a 3^b 5^c and <= %d", N, mlb::FFT_MAX_N);
     MLB_REQUIRE(s1 >= 1 && s2 >= 1, "mlb_fft_rows: fold factors must be >= 1");
-    MLB_REQUIRE(tw && n_rows > 0 && ld_in >= N * s2 && ld_out >= (transpose_out ? n_rows : N), "mlb_fft_rows: bad sizes");
+    MLB_REQUIRE(tw && n_rows > 0 && ld_in >= N * s2 && ld_out >= (transpose_out ? n_rows : (scatter ? N / sc.world : N)),
+                "mlb_fft_rows: bad sizes");
     a.transpose_out = transpose_out ? 1 : 0;
     MLB_REQUIRE(in_roll_r >= 0 && in_roll_r < n_rows && in_roll_c >= 0 && in_roll_c < N && out_roll >= 0 && out_roll < N,
                 "mlb_fft_rows: rolls out of range");
@@ -1172,6 +1197,10 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
         MLB_REQUIRE((in_roll_r == 0 && s1 == 1 && s2 == 1) || a.in[b] != a.out[b],
                     "mlb_fft_rows: in-place needs in_roll_r == 0 and no fold");
     a.tw = reinterpret_cast<const float2 *>(tw);
+    if (scatter && !(mlb::is_pow2(N) && N >= 256 && N <= 2048 && mlb::g_rows_tma && ld_in % 2 == 0)) {
+        mlb::set_error("mlb_fft_rows_scatter: needs the TMA-fed row kernel (power-of-two N in 256..2048, even pitch); N = %d", N);
+        return MLB_ERR_UNSUPPORTED;
+    }
     if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
         MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs a power-of-two length");
         if (mlb::g_mixed_engine == 1) {
@@ -1232,7 +1261,7 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
     for (int b = 0; b < batch; ++b) vec = vec && mlb::aligned16(a.in[b]);
     dim3 grid((n_rows + lanes - 1) / lanes, batch);
     // radix-16 register kernels (256..8192 points)
-    if (!transpose_out && a.lgN >= mlb::g_r16_min_lg && a.lgN <= 13 &&
+    if (!scatter && !transpose_out && a.lgN >= mlb::g_r16_min_lg && a.lgN <= 13 &&
         (mlb::g_rows_engine == 1 || (mlb::g_rows_engine == 2 && s1 == 1 && s2 == 1))) {
         bool inplace = false;
         for (int b = 0; b < batch; ++b) inplace = inplace || (a.in[b] == a.out[b]);
@@ -1306,7 +1335,7 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
         int grid = n_sm * per_sm;                                                                                    \
         if (grid > n_rows * batch) grid = n_rows * batch;                                                            \
         a.work_counter = work_counter;                                                                               \
-        mlb::fft_rows_tma_kernel<LG, KB><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch);                \
+        mlb::fft_rows_tma_kernel<LG, KB><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch, sc);            \
         return mlb::check_launch("mlb_fft_rows(tma)");                                                               \
     }
 #define MLB_ROWS_TMA(LG)                                                                                              \
@@ -1317,6 +1346,10 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
 #undef MLB_ROWS_TMA
 #undef MLB_ROWS_TMA_RING
         }
+    }
+    if (scatter) {
+        mlb::set_error("mlb_fft_rows_scatter: operands must be 16-byte aligned and distinct from the outputs");
+        return MLB_ERR_UNSUPPORTED;
     }
     MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs the TMA-fed kernel (256..2048 points, "
                                 "16-byte aligned even-pitch input, out != in); see mlb_fft_rows_can_transpose");
@@ -1367,6 +1400,26 @@ extern "C" int mlb_fft_rows_ws(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *c
                                int transpose_out, int batch, void *work_counter, void *stream) {
     return fft_rows_impl(h_in, ld_in, h_out, ld_out, n_rows, N, s1, s2, tw, in_roll_r, in_roll_c, out_roll, transpose_out,
                          batch, mlb::g_rows_dynamic ? reinterpret_cast<unsigned int *>(work_counter) : nullptr, stream);
+}
+
+extern "C" int mlb_fft_rows_scatter(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out_peers, int ld_out,
+                                    int n_rows, int N, int s1, int s2, const mlb_c64 *tw, int in_roll_c, int out_roll,
+                                    int out_row0, int n_rows_total, int world, int batch, void *stream) {
+    MLB_REQUIRE(h_out_peers && world >= 1 && world <= MLB_MAX_PEERS && (world & (world - 1)) == 0,
+                "mlb_fft_rows_scatter: world %d must be a power of two <= %d", world, MLB_MAX_PEERS);
+    MLB_REQUIRE(batch >= 1 && batch <= 4 && N > 0 && N % world == 0, "mlb_fft_rows_scatter: bad batch %d / N %d", batch, N);
+    MLB_REQUIRE(n_rows > 0 && n_rows <= n_rows_total && out_row0 >= 0 && out_row0 < n_rows_total,
+                "mlb_fft_rows_scatter: bad row window (%d rows at %d of %d)", n_rows, out_row0, n_rows_total);
+    mlb::RowScatter sc = {};
+    sc.world = world; sc.lg_slab = mlb::ilog2(N / world); sc.out_row0 = out_row0; sc.rows_total = n_rows_total;
+    for (int p = 0; p < world; ++p)
+        for (int f = 0; f < 4; ++f) {
+            const mlb_c64 *ptr = h_out_peers[p * batch + (f < batch ? f : 0)];
+            MLB_REQUIRE(ptr != nullptr, "mlb_fft_rows_scatter: NULL output (peer %d, field %d)", p, f);
+            sc.out[p][f] = reinterpret_cast<float2 *>(const_cast<mlb_c64 *>(ptr));
+        }
+    return fft_rows_impl(h_in, ld_in, h_out_peers, ld_out, n_rows, N, s1, s2, tw, 0, in_roll_c, out_roll, 0, batch,
+                         nullptr, stream, &sc);
 }
 
 namespace mlb {

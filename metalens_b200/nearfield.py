@@ -223,9 +223,11 @@ class NearfieldPlan:
         return np.linspace(-self.lens_max_r, self.lens_max_r, num=n)
 
     def run(self, source_x, source_y, source_z, source_pol, x_pts, y_pts, dipole_moment=1e-30,
-            out_dtype=torch.complex64, verbose=False, out=None):
+            out_dtype=torch.complex64, verbose=False, out=None, dxdy=None):
         """Launch the fused assembly kernel.  Returns (fields (4, nx, ld) device tensor -- logical
-        view [..., :ny] --, power device scalar float64).  Raises the reference's ValueErrors."""
+        view [..., :ny] --, power device scalar float64).  Raises the reference's ValueErrors.
+        x_pts / y_pts need not be uniform here (a multi-GPU rank passes ITS rows of the grid, slab.py); then
+        `dxdy` gives the area element of the incident-power sum (:476-477) explicitly."""
         dev = self.device
         d_x = torch.from_numpy(np.ascontiguousarray(x_pts, dtype=np.float64)).to(dev)
         d_y = torch.from_numpy(np.ascontiguousarray(y_pts, dtype=np.float64)).to(dev)
@@ -263,9 +265,11 @@ class NearfieldPlan:
                 violation.zero_()
                 launch(True)                 # slow path: collect min/max for the reference's messages
             self._report(stats.cpu().numpy(), verbose)
-        dx = float(x_pts[1] - x_pts[0]) if nx > 1 else float('nan')
-        dy = float(y_pts[1] - y_pts[0]) if ny > 1 else float('nan')
-        rc = self.lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, dx * dy, power.data_ptr(), _stream_ptr())   # :476-477
+        if dxdy is None:
+            dx = float(x_pts[1] - x_pts[0]) if nx > 1 else float('nan')
+            dy = float(y_pts[1] - y_pts[0]) if ny > 1 else float('nan')
+            dxdy = dx * dy
+        rc = self.lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, dxdy, power.data_ptr(), _stream_ptr())      # :476-477
         _lib.check(rc, "mlb_sum_f64")
         return out, power
 
@@ -316,7 +320,9 @@ _PLAN_CACHE = {}
 
 
 def _plan_for(wavelength, periphery, center, hexgridset):
-    key = (int(round(wavelength / nm)), id(periphery), id(center), id(hexgridset),
+    # the exact wavelength (k_vac, k_glass, the default grid depend on it; only the TABLE lookup uses the rounded nm,
+    # nearfield.py:86) and the device the plan's buffers live on
+    key = (float(wavelength), torch.cuda.current_device(), id(periphery), id(center), id(hexgridset),
            id(getattr(hexgridset, "interpolators", None)),
            tuple(id(getattr(gc, "interpolators", None)) for gc in periphery['gratingcollection_list']))
     hit = _PLAN_CACHE.get(key)

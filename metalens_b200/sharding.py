@@ -9,13 +9,21 @@ and G ranks every item is cut into S = G / gcd(B, G) slabs, giving B*S tiles, B*
 whole items per rank when G divides B (no aperture replication), finer slabs otherwise.
 
 `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing; the per-tile compute
-is a FarfieldPlan restricted to its rows.
+is a FarfieldPlan restricted to its rows.  On GPUs the exchange itself is a kernel of this package: every rank
+PUSHES its finished tiles into the peers' result buffers over NVLink (mlb_peer_allgather, csrc/peer.cu), or --
+without peer mappings -- calls the C-ABI's NCCL wrapper (mlb_allgather_P).  One aperture spread over the ranks
+(BASELINE config 4) is metalens_b200/slab.py.
 """
 import math
 from dataclasses import dataclass
 
 import torch
 import torch.distributed as dist
+
+
+def _lib_error(msg):
+    from ._lib import MetalensB200Error
+    return MetalensB200Error(msg)
 
 
 @dataclass(frozen=True)
@@ -67,7 +75,10 @@ class ShardedFarfield:
     the four device fields of an item this rank owns.
     """
 
-    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None, tail_priority=0, gather="auto"):
+    def __init__(self, n_items, n_rows, make_plan, rank=None, world=None, group=None, tail_priority=0, gather="auto",
+                 push_ctas=0):
+        self._push_ctas = push_ctas                     # CTAs of the push kernel (0 = library default)
+        self._pushed = False
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.group = group
@@ -86,15 +97,21 @@ class ShardedFarfield:
         # stream, so the tail of tile k executes under the aperture pass of tile k+1
         self._side = None
         self._tail_priority = tail_priority             # side stream priority (-1 = high; measured: no effect on B200)
-        self._tail_done = [None] * len(self.tiles)     # per plan: its buffers are free again (side-stream event)
+        self._tail_done = {}                            # per plan object: its buffers are free again (side-stream event)
         self._side_done = None
-        # gather="p2p": the finished tiles are exchanged by PULLING them from the peers' buffers over NVLink with the
-        # copy engines (torch symmetric memory: peer-mapped buffers + signal-pad barriers), no SM-resident collective
-        # kernel competing with the persistent row pass; "nccl": all_gather_into_tensor; "auto": p2p when it can be
-        # set up (CUDA, world > 1), else nccl
-        assert gather in ("auto", "nccl", "p2p")
+        # How the finished tiles travel (CUDA, world > 1):
+        #   "push" (default of "auto"): mlb_peer_allgather -- a few CTAs store the rank's tile stack into every peer's
+        #           result buffer (torch symmetric memory supplies the peer mappings); flag epochs instead of barriers, so
+        #           nothing on the per-step path blocks: a step's pushes run under the next step's row pass;
+        #   "p2p":  the peers' stacks are PULLED by the copy engines (round-1 path, two signal-pad barriers per step);
+        #   "nccl": mlb_allgather_P (the C-ABI's NCCL wrapper) on a communication stream.
+        # CPU tensors (gloo tests) always use torch's all_gather_into_tensor.
+        assert gather in ("auto", "nccl", "p2p", "push")
         self._gather = gather
-        self._symm = None                               # per flip buffer: (handle, [peer tile-stack tensors])
+        self._symm = None                               # p2p, per flip buffer: (handle, [peer tile-stack tensors])
+        self._chan = None                               # push: PeerChannel
+        self._out_ptrs = [None, None]                   # push: peer addresses of the two result buffers
+        self._nccl = None
         self._comm = None
         self._gather_done = [None, None]
 
@@ -113,22 +130,57 @@ class ShardedFarfield:
         self._symm = symm
         self._comm = torch.cuda.Stream(device=device)
 
+    def _setup_push(self, shape, dtype, device):
+        """Both result buffers in peer-mapped memory; a rank's tile stack IS its section of its own result buffer."""
+        from .peer import PeerChannel, SymmetricPeers
+        peers = SymmetricPeers(self.group, device)
+        t = shape[0]
+        nbytes = self.world * int(torch.tensor([], dtype=dtype).element_size()) * t * shape[1] * shape[2]
+        for b in (0, 1):
+            buf, ptrs = peers.alloc("tiles%d" % b, nbytes)
+            self._out[b] = buf[:nbytes].view(dtype).view((self.world * t,) + tuple(shape[1:]))
+            self._local[b] = self._out[b][self.rank * t:(self.rank + 1) * t]
+            self._out_ptrs[b] = ptrs
+        self._chan = PeerChannel(peers, "tiles.chan")
+        self._stack_bytes = nbytes // self.world
+        peers.sync()
+
     def _alloc(self, b, P):
-        """Tile stack + gather target of flip buffer b (first use)."""
+        """Tile stack + gather target of flip buffer b (first use).  The exchange mechanism is agreed on by ALL ranks
+        (a rank that cannot map peer memory makes everyone use NCCL: mixed protocols would hang)."""
         shape = (len(self.tiles),) + tuple(P.shape)
-        if self._gather != "nccl" and self.world > 1 and P.is_cuda and self._symm is None:
-            try:
-                self._setup_p2p(shape, P.dtype, P.device)
-                self._gather = "p2p"
-                return
-            except Exception as e:                      # no symmetric memory here: the NCCL collective does the job
-                if self._gather == "p2p":
-                    raise
+        if self.world > 1 and P.is_cuda and self._chan is None and self._symm is None and self._nccl is None:
+            mode, err = self._gather, None
+            if mode in ("auto", "push", "p2p"):
+                try:
+                    if mode == "p2p":
+                        self._setup_p2p(shape, P.dtype, P.device)
+                    else:
+                        if shape[1] * shape[2] * P.element_size() % 16:
+                            raise ValueError("tile bytes not a multiple of 16")
+                        self._setup_push(shape, P.dtype, P.device)
+                        mode = "push"
+                except Exception as e:
+                    err = e
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=P.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if self._gather in ("push", "p2p"):
+                    raise _lib_error("peer-memory tile exchange unavailable on some rank: %r" % (err,))
                 import sys
-                print("metalens_b200.sharding: peer-to-peer gather unavailable (%s: %s), using NCCL all-gather"
-                      % (type(e).__name__, str(e)[:200]), file=sys.stderr)
-                self._gather = "nccl"
-                self._symm = None
+                if err is not None:
+                    print("metalens_b200.sharding: peer-memory exchange unavailable (%s: %s), using NCCL"
+                          % (type(err).__name__, str(err)[:200]), file=sys.stderr)
+                mode = "nccl"
+                self._symm = self._chan = None
+                self._local, self._out = [None, None], [None, None]
+            self._gather = mode
+            if mode == "nccl":
+                from .peer import NcclComm
+                self._nccl = NcclComm(self.group)
+                self._comm = torch.cuda.Stream(device=P.device)
+            if mode != "nccl":
+                return
         if self._local[b] is None:
             self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
             self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
@@ -153,6 +205,25 @@ class ShardedFarfield:
         self._gather_done[b] = done
         return self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
 
+    def _gather_push(self, b):
+        """mlb_peer_allgather on the CURRENT stream (the one that produced the tiles): store this rank's stack into
+        every peer's out[b].  Nothing waits here; finish() acquires the peers' completion flags."""
+        self._chan.allgather(self._local[b].data_ptr(), self._stack_bytes, 1, self._stack_bytes, self._out_ptrs[b],
+                             self._stack_bytes, self.rank * self._stack_bytes, n_ctas=self._push_ctas)
+        self._pushed = True
+        return self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
+
+    def _gather_nccl(self, b, producer_stream):
+        ready = torch.cuda.Event()
+        ready.record(producer_stream)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            self._nccl.allgather_P(self._local[b], self._out[b])
+            done = torch.cuda.Event()
+            done.record(self._comm)
+        self._gather_done[b] = done
+        return self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
+
     @property
     def items_needed(self):
         return sorted({t.item for t in self.tiles})
@@ -160,9 +231,9 @@ class ShardedFarfield:
     def run(self, fields_of, runner=None, overlap=False):
         """Compute this rank's tiles, then the single all-gather.  Returns
         (P (n_items, n_rows, Ky) on every rank, partial total_P per local tile).
-        `runner(plan, fields)` defaults to ``plan.run(fields)``.  With overlap=True the collective is
-        asynchronous (the result is complete after ``finish()`` or a device synchronize) and runs
-        concurrently with the next call's kernels."""
+        `runner(plan, fields)` defaults to ``plan.run(fields)``.  With overlap=True the exchange is
+        asynchronous (the result is complete after ``finish()``) and runs concurrently with the next call's
+        kernels; the result buffers are double-buffered, so a result stays valid until the second-next run()."""
         b = self._flip
         self._flip ^= 1
         if overlap and runner is None and all(hasattr(p, "run_split") for p in self.plans) \
@@ -176,14 +247,20 @@ class ShardedFarfield:
             P, total = plan.run(fields_of(tile.item)) if runner is None else runner(plan, fields_of(tile.item))
             if self._local[b] is None:
                 self._alloc(b, P)
-            if k == 0 and self._gather_done[b] is not None:      # peers may still be pulling this stack (p2p, two steps ago)
+            if k == 0 and self._gather_done[b] is not None:      # peers may still be pulling this stack (two steps ago)
                 torch.cuda.current_stream().wait_event(self._gather_done[b])
             self._local[b][k].copy_(P)
             totals.append(total)
-        if self._gather == "p2p" and self.world > 1 and self._symm is not None:
-            res = self._gather_p2p(b, torch.cuda.current_stream())
+        cuda = self.world > 1 and self._local[b].is_cuda
+        if cuda and self._gather == "push":
+            res = self._gather_push(b)
             if not overlap:
-                torch.cuda.current_stream().wait_event(self._gather_done[b])
+                self._chan.wait()
+        elif cuda and self._gather in ("p2p", "nccl"):
+            cur = torch.cuda.current_stream()
+            res = self._gather_p2p(b, cur) if self._gather == "p2p" else self._gather_nccl(b, cur)
+            if not overlap:
+                cur.wait_event(self._gather_done[b])
         elif overlap and self.world > 1:
             res, self._work[b] = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group,
                                               out=self._out[b], async_op=True)
@@ -200,8 +277,9 @@ class ShardedFarfield:
         totals = []
         for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
             first, second = plan.run_split(fields_of(tile.item))
-            if self._tail_done[k] is not None:           # the previous tail of this plan still reads its buffers
-                main.wait_event(self._tail_done[k])
+            prev = self._tail_done.get(id(plan))
+            if prev is not None:                         # the previous tail of this plan still reads its buffers
+                main.wait_event(prev)
             first()
             ev = torch.cuda.Event()
             ev.record(main)
@@ -213,21 +291,22 @@ class ShardedFarfield:
                 P, total = second()
                 if self._local[b] is None:
                     self._alloc(b, P)
-                if k == 0 and self._gather_done[b] is not None:  # peers may still be pulling this stack (p2p)
+                if k == 0 and self._gather_done[b] is not None:  # peers may still be pulling this stack (p2p / nccl)
                     side.wait_event(self._gather_done[b])
                 self._local[b][k].copy_(P)
                 totals.append(total)
                 done = torch.cuda.Event()
                 done.record(side)
-                self._tail_done[k] = done
-        if self._gather == "p2p" and self.world > 1 and self._symm is not None:
-            res = self._gather_p2p(b, side)
-            with torch.cuda.stream(side):
-                self._side_done = torch.cuda.Event()
-                self._side_done.record(side)
-            return res, totals
+                self._tail_done[id(plan)] = done
+        cuda = self.world > 1
         with torch.cuda.stream(side):
-            if self.world > 1:
+            if cuda and self._gather == "push":
+                res = self._gather_push(b)               # on the side stream, right behind the last tile copy
+            elif cuda and self._gather == "p2p":
+                res = self._gather_p2p(b, side)
+            elif cuda and self._gather == "nccl":
+                res = self._gather_nccl(b, side)
+            elif self.world > 1:
                 res, self._work[b] = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group,
                                                   out=self._out[b], async_op=True)
             else:
@@ -239,19 +318,19 @@ class ShardedFarfield:
     def capture(self, fields_of):
         """Capture one pipelined step (every local tile, both streams, the tile copies) into a CUDA graph and
         return it; ``replay()`` then re-runs the step on whatever is in the same field buffers with a single
-        launch.  Single-rank only (world == 1): with more ranks the collective stays an eager NCCL call."""
+        launch.  Single-rank only (world == 1): with more ranks the exchange stays outside the graph."""
         if self.world != 1:
             raise ValueError("capture() is for world == 1; use run(overlap=True) across ranks")
         self.run(fields_of, overlap=True)                # warm-up outside capture (lazy allocations, attributes)
         self.finish()
         torch.cuda.synchronize()
-        self._tail_done = [None] * len(self.tiles)       # no dependencies on events recorded outside the capture
+        self._tail_done = {}                             # no dependencies on events recorded outside the capture
         self._flip = 0
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._graph_result = self.run(fields_of, overlap=True)
             self.finish()                                # joins the side stream back into the capturing stream
-        self._tail_done = [None] * len(self.tiles)
+        self._tail_done = {}
         self._graph = g
         return g
 
@@ -261,7 +340,7 @@ class ShardedFarfield:
         return self._graph_result
 
     def finish(self):
-        """Wait for outstanding asynchronous all-gathers (and, in pipelined mode, make the caller's stream
+        """Wait for outstanding asynchronous exchanges (and, in pipelined mode, make the caller's stream
         wait for the side stream)."""
         for b in (0, 1):
             if self._work[b] is not None:
@@ -279,3 +358,10 @@ class ShardedFarfield:
         if self._side_done is not None:
             torch.cuda.current_stream().wait_event(self._side_done)
             self._side_done = None
+        if self._pushed:                                 # the peers' pushes of the latest step have landed here
+            self._chan.wait()
+
+    def check(self):
+        """Raise if a peer exchange ever timed out (synchronises)."""
+        if self._chan is not None:
+            self._chan.check()

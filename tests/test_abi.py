@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, "include", "metalens_b200.h")
 def declared_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mlb_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(mlb_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
