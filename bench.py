@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- far-field points/s of the NF->FF hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4]
 
 One "step" = one pass of the hot path over one batch: every batch item (wavelength /
 polarisation) of the workload goes aperture fields -> far-field power map P.
@@ -9,6 +9,9 @@ polarisation) of the workload goes aperture fields -> far-field power map P.
   cfg3 (default; the configuration the north-star target is quoted on):
        4096^2 aperture -> 1024^2 far field (every 4th fftshifted FFT bin), 3 wavelengths
   cfg2 2048^2 aperture -> 512^2 far field, 532 nm, TE+TM (2 items)
+  cfg4 ONE 8192^2 aperture assembled from a synthetic NA 0.94 lens (hot path B) -> 2048^2 far field, the whole
+       step spread over the N GPUs (strong scaling; metalens_b200/slab.py).  Also reported as the `cfg4` block of
+       the default line at every N.
 
 value  = far-field points/s with the aperture fields already resident in HBM
 e2e    = same metric through FarfieldPlan.run_host(): pinned host fields -> H2D ->
@@ -16,9 +19,9 @@ e2e    = same metric through FarfieldPlan.run_host(): pinned host fields -> H2D 
 N > 1  : one process per GPU (torchrun), weak scaling -- every rank owns a full batch of its
          own apertures (far-field tiles of different sources); one all-gather of the P tiles per
          step is inside the timed region (asynchronous, double-buffered: it overlaps the kernels of
-         the next step).  The gather pulls the peers' tiles over NVLink with the copy engines
-         (torch symmetric memory; no SM-resident collective kernel next to the persistent row
-         pass) and falls back to NCCL all_gather_into_tensor where that cannot be set up.
+         the next step).  Every rank pushes its tiles into the peers' result buffers over NVLink with
+         the library's own kernel (mlb_peer_allgather; torch symmetric memory only maps the buffers);
+         the C-ABI's NCCL wrapper is the fallback where peer memory cannot be mapped.
 Extra keys on the same line: roofline (dominant kernel), kernels (CUDA-event time of every kernel of a
 step), paths_points_per_s (other formulations on the same workload), other_workloads (cfg2),
 nearfield_assembly (hot path B), fom_sweep (cfg5 shape), cpu_baseline.
@@ -45,6 +48,9 @@ WORKLOADS = {
                  name="cfg3: 4096x4096 aperture -> 1024x1024 far field (every 4th FFT bin), 450/532/635 nm"),
     "cfg2": dict(M=2048, stride=4, items=[(532e-9, 1.4607, False), (532e-9, 1.4607, True)],
                  name="cfg2: 2048x2048 aperture -> 512x512 far field (every 4th FFT bin), 532 nm, TE+TM"),
+    "cfg4": dict(M=8192, stride=4, items=[(580e-9, 1.459, False)],
+                 name="cfg4: NA 0.94 synthetic lens (3 GratingCollections + HexGridSet), ONE 8192x8192 aperture assembled "
+                      "on the GPUs -> 2048x2048 far field (every 4th FFT bin), 580 nm, whole step sharded over the ranks"),
 }
 
 
@@ -104,73 +110,149 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference(workload, sample_M, steps=1, warmup=0, parallel=True):
-    """Time the CPU reference path (4x fft2(fftshift) + radiated-power helper, float64 numpy: the oracle's
-    restatement of nearfield_farfield.py) on a bounded sample: the same workload with the aperture reduced to
-    sample_M^2 samples (stride kept), all batch items.  All host cores are used: the items run concurrently and
-    each spreads its four FFTs and the reference's own uy-chunk loop (:45-66) over its share of the cores
-    (threads; numpy releases the GIL).  The timed region is the transform only (input synthesis excluded)."""
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import farfield_oracle as fo
-    w = WORKLOADS[workload]
+def _host_cores():
     try:
-        avail = len(os.sched_getaffinity(0))
+        return len(os.sched_getaffinity(0))
     except AttributeError:
-        avail = os.cpu_count() or 1
-    cores = min(avail, 64) if parallel else 1          # 64: bounds the chunk temporaries on many-core hosts
-    n_items = len(w["items"])
-    per_item = max(1, -(-cores // n_items))
-    K = sample_M // w["stride"]
-    inputs = [apertures.focusing_lens(sample_M, 100 + i, wl, ng, rotate=rot) + (wl, ng)
-              for i, (wl, ng, rot) in enumerate(w["items"])]
+        return os.cpu_count() or 1
 
-    def one(a):
-        return float(fo.farfield_reference_path_threads(*a, workers=per_item)[1])
-    times = []
-    for it in range(warmup + steps):
+
+class ReferenceRunner:
+    """The reference's own CPU implementation of hot path A on the workload's apertures.
+
+    kind "reference": the UNMODIFIED nearfield_farfield.farfield_from_nearfield from baseline/_ref (installed by
+    __graft_entry__.build() from /root/reference; baseline/install_ref.py), fed the way its docstring prescribes
+    (nearfield_farfield.py:18-20): fft2(fftshift(E)) of the four complex128 fields, computed by the caller with
+    numpy.fft.  Host threads: the batch items run concurrently and each item's four FFTs run concurrently (numpy
+    releases the GIL); farfield_from_nearfield itself is single-threaded numpy, as shipped.
+    kind "port": oracle/farfield_oracle.py (same algorithm, threaded chunk loop) when baseline/_ref is absent."""
+
+    def __init__(self, workload, sample_M=None):
+        w = WORKLOADS[workload]
+        self.w = w
+        self.M = w["M"] if sample_M is None else sample_M
+        self.K = self.M // w["stride"]
+        self.cores = _host_cores()
+        sys.path.insert(0, ROOT)
+        from baseline import install_ref
+        self.ref = install_ref.load()
+        self.kind = "reference" if self.ref is not None else "port"
+        self.inputs = []
+        for i, (wl, ng, rot) in enumerate(w["items"]):
+            Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(self.M, 100 + i, wl, ng, rotate=rot)
+            # the reference's build_nearfield hands over complex128 fields
+            self.inputs.append(([a.astype(np.complex128) for a in (Ex, Ey, Hx, Hy)], x, y, wl, ng))
+
+    def _one(self, item):
+        import contextlib
+        import io
+        from concurrent.futures import ThreadPoolExecutor
+        fields, x, y, wl, ng = self.inputs[item]
+        if self.kind == "port":
+            from oracle import farfield_oracle as fo
+            per_item = max(1, self.cores // len(self.inputs))
+            return float(fo.farfield_reference_path_threads(*fields, x, y, wl, ng, workers=per_item)[1])
+        with ThreadPoolExecutor(4) as pool:
+            F = list(pool.map(lambda a: np.fft.fft2(np.fft.fftshift(a)), fields))             # :18-20
+        with contextlib.redirect_stdout(io.StringIO()):                                       # progress prints, :53
+            out = self.ref["nearfield_farfield"].farfield_from_nearfield(*F, x, y, wl, ng)   # :14
+        return float(out[1])
+
+    def step(self, items):
+        """One pass over `items` (indices into the batch), items concurrently.  Returns seconds."""
+        from concurrent.futures import ThreadPoolExecutor
         t0 = time.perf_counter()
-        if cores > 1:
-            with ThreadPoolExecutor(n_items) as pool:
-                list(pool.map(one, inputs))
+        if len(items) > 1 and self.cores > 1:
+            with ThreadPoolExecutor(len(items)) as pool:
+                list(pool.map(self._one, items))
         else:
-            for a in inputs:
-                fo.farfield_reference_path(*a)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    t = float(np.mean(times))
-    pts = n_items * K * K
-    used = min(cores, n_items * per_item)
-    return dict(value=pts / t, unit="far-field points/s", cores=used, kind="port",
-                sample="%d items, aperture %dx%d -> %dx%d requested bins (the numpy path computes all %d^2 bins: "
-                       "%.3g bins/s); oracle/farfield_oracle.py restating nearfield_farfield.py, float64, "
-                       "%d thread(s) (items concurrent, FFTs and the uy-chunk loop threaded), %.2f s per pass"
-                       % (n_items, sample_M, sample_M, K, K, sample_M, n_items * sample_M ** 2 / t, used, t)), t
+            for it in items:
+                self._one(it)
+        return time.perf_counter() - t0
+
+    def threads_used(self, n_items):
+        if self.kind == "port":
+            return min(self.cores, 64)
+        return min(self.cores, 4 * n_items)
+
+    def describe(self, items_per_step, t):
+        return ("%d of %d batch items per step, aperture %dx%d -> %dx%d requested bins (the numpy path always computes "
+                "all %d^2 bins: %.3g bins/s); %s, float64, %d host thread(s) (items and the four caller-side FFTs "
+                "concurrent), %.2f s per step"
+                % (items_per_step, len(self.inputs), self.M, self.M, self.K, self.K, self.M,
+                   items_per_step * self.M ** 2 / t,
+                   "UNMODIFIED reference farfield_from_nearfield (baseline/_ref) + numpy.fft.fft2(fftshift(.))"
+                   if self.kind == "reference" else "oracle/farfield_oracle.py port of nearfield_farfield.py",
+                   self.threads_used(items_per_step), t))
+
+
+def cpu_baseline_leg(workload, quick=False):
+    """cpu_baseline of our arm: ONE batch item of the workload at full aperture size (about 5-15 s of CPU work),
+    through the same runner as --impl reference."""
+    r = ReferenceRunner(workload, sample_M=512 if quick else None)
+    t = r.step([0])
+    return dict(value=r.K * r.K / t, unit="far-field points/s", cores=r.threads_used(1), kind=r.kind,
+                sample=r.describe(1, t))
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
-    pure Python and cannot travel to the GPU box) on all host cores (cpu_reference)."""
+    """--impl reference: the reference's CPU implementation of the path at the workload's FULL size, honouring
+    --steps / --warmup.  One full-size step is measured first; if (steps + warmup) such steps do not fit the time
+    budget, every step processes ONE batch item (rotating through the wavelengths: same aperture, same per-point
+    work) and, if even that does not fit, the warm-up shrinks (never below 1) -- the line says what was run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
-    sample_M = min(w["M"], 2048)
-    base, t = cpu_reference(args.workload, sample_M, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    workload = args.workload if args.workload in ("cfg3", "cfg2") else "cfg3"
+    r = ReferenceRunner(workload)
+    n = len(r.inputs)
+    budget = args.ref_budget
+    t_start = time.perf_counter()
+    rot = 0
+
+    def next_items():
+        nonlocal rot
+        if per_step == n:
+            return list(range(n))
+        rot = (rot + 1) % n
+        return [rot]
+    per_step = n
+    t_full = r.step(next_items())                           # warm-up step 1: the full batch
+    steps, warmup, warmed = args.steps, max(args.warmup, 1), 1
+    if (steps + warmup - 1) * t_full > budget and n > 1:
+        per_step = 1
+        t_one = r.step(next_items())                        # warm-up step 2: what a step will be from now on
+        warmed = 2
+        while warmup > warmed and (steps + warmup - warmed) * t_one > budget:
+            warmup -= 1
+        warmup = max(warmup, warmed)
+    for _ in range(warmup - warmed):
+        r.step(next_items())
+    times = []
+    for _ in range(steps):
+        times.append(r.step(next_items()))
+        if time.perf_counter() - t_start > 3 * budget:      # hard stop: never run away
+            break
+    t = float(np.mean(times))
+    value = per_step * r.K * r.K / t
+    base = dict(value=value, unit="far-field points/s", cores=r.threads_used(per_step), kind=r.kind,
+                sample=r.describe(per_step, t))
     line = {
-        "impl": "reference", "metric": "far-field points/sec (NF->FF)", "value": base["value"],
-        "unit": "far-field points/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
-        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": "far-field points/sec (NF->FF)", "value": value,
+        "unit": "far-field points/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "sample": base["sample"]},
+        "config": common_config(WORKLOADS[workload], r.M, r.K, n),
+        "details": {"batch_items_per_step": per_step, "sample": base["sample"], "budget_s": budget,
+                    "requested_steps": args.steps, "requested_warmup": args.warmup},
         "cpu_baseline": base,
-        "e2e": {"value": base["value"], "unit": "far-field points/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": "far-field points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 # ----------------------------------------------------------------------------- hot path B
-def bench_nearfield(M, torch, cpu_cols=384):
+def bench_nearfield(M, torch, peaks, cpu_cols=384):
     """Aperture-field assembly (build_nearfield) on a synthetic round lens filling an M x M grid
     (SURVEY 8d cfg4 shape): samples/s and achieved write bandwidth of the fused kernel, next to the
     numpy oracle timed on a strip of the same grid."""
@@ -202,6 +284,11 @@ def bench_nearfield(M, torch, cpu_cols=384):
     t = e0.elapsed_time(e1) / reps * 1e-3
     res = dict(aperture=[M, M], rings=int(len(periph["r_min_list"])), hex_cells=int(len(center)),
                ms=t * 1e3, samples_per_s=M * M / t, write_gbs=32.0 * M * M / t / 1e9,
+               roofline=dict(kernel="nearfield_kernel", bound="hbm", achieved=32.0 * M * M / t / 1e9, peak=peaks["hbm_gbs"],
+                             unit="GB/s", frac=32.0 * M * M / t / 1e9 / peaks["hbm_gbs"], traffic=None,
+                             algorithmic_bytes_per_launch=32 * M * M,
+                             note="SURVEY 8(d): bytes_B = 32*M^2 written; the kernel is bound by instruction issue "
+                                  "(float64 geometry), see profiles/"),
                note="one fused kernel launch incl. host packing of x/y and the violation read-back; "
                     "algorithmic bytes = 32*M^2 written (4 complex64 fields)", design_seconds=t_design)
     # CPU oracle on a strip of the same grid (off-centre so centre and rings are both represented)
@@ -253,7 +340,136 @@ def bench_sweep(torch, steps=56, M=256):
                 note="wall clock per step incl. the device copy of the step's aperture; 56 angles 5..60 deg")
 
 
+# ----------------------------------------------------------------------------- cfg4: one aperture over N GPUs
+def cfg4_lens(M, wl=580e-9):
+    """synthetic NA ~0.94 lens filling an M x M grid (lambda/2.2 sampling)."""
+    import synth_lens
+    from metalens_b200 import grating, lens_center
+    from metalens_b200.design import make_design
+    R = M * (wl / 2.2) / 2
+    f = R / math.tan(math.asin(0.94))
+    spec = dict(bands=[(15.0, 25.0, 1000e-9, 0.3), (25.0, 45.0, 650e-9, 1.1), (45.0, 71.0, 300e-9, 2.3)],
+                source_distance=f, radius=R * 0.999)
+    collections, hgs = synth_lens.make_library(grating, lens_center, spec)
+    periph, center, _ = make_design(collections, f, spec["radius"], hgs)
+    return periph, center, hgs, R, f
+
+
+def bench_cfg4(torch, dist, rank, world, steps, warmup, M=8192, stride=4, check=True, sample_clocks=None):
+    """BASELINE config 4 as ONE job over `world` GPUs (strong scaling): every rank assembles its rows of the aperture
+    (hot path B), folds + row-transforms them while scattering the column slabs to their owners over NVLink, column
+    pass + power on its slab, one pushed all-gather of P (metalens_b200/slab.py).  Timed: K steps of
+    [assembly -> far field complete on every rank], CUDA events, max over ranks.  On rank 0 the result is compared
+    BIT FOR BIT with the single-GPU pipeline (full assembly -> FarfieldPlan) after the timed region."""
+    from metalens_b200 import _lib
+    from metalens_b200.farfield import FarfieldPlan
+    from metalens_b200.nearfield import NearfieldPlan
+    from metalens_b200.peer import SymmetricPeers, VirtualPeers
+    from metalens_b200.slab import SlabFarfield, assemble_slab
+    lib = _lib.load()
+    wl = 580e-9
+    t0 = time.perf_counter()
+    periph, center, hgs, R, f = cfg4_lens(M, wl)
+    t_design = time.perf_counter() - t0
+    nf = NearfieldPlan(wl, periph, center, hgs)
+    x = np.linspace(-R, R, M)
+    d = float(x[1] - x[0])
+    peers = SymmetricPeers() if world > 1 else VirtualPeers(1).view(0)
+    slab = SlabFarfield((M, M), d, d, wl, nf.n_glass, stride, peers)
+    K = slab.K1
+    out = torch.zeros((4, slab.x_rows.size, M), dtype=torch.complex64, device="cuda")
+    fields = [out[i] for i in range(4)]
+    src = (0.0, 0.0, -f)
+    power = [None]
+
+    def assemble():
+        power[0] = assemble_slab(nf, slab, src, "x", x, x, out=out, check=False)[1]
+
+    def farfield():
+        return slab.run(fields)
+
+    def step():
+        assemble()
+        return farfield()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.mlb_launch_count()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        launches = lib.mlb_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        barrier()
+        return ms, launches
+
+    sampler = sample_clocks() if sample_clocks else None
+    ms_step, launches = timed(step, steps, warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_nf, _ = timed(assemble, max(3, steps // 2), 2)
+    ms_ff, _ = timed(farfield, max(3, steps // 2), 2)
+    nf.check_violation()
+    slab.chan.check()
+    P, total = step()
+    torch.cuda.synchronize()
+    p_in = power[0].clone()
+    if world > 1:
+        dist.all_reduce(p_in, op=dist.ReduceOp.SUM)
+    res = dict(workload=WORKLOADS["cfg4"]["name"], aperture=[M, M], far_field=[K, K], n_gpus=world,
+               rings=int(len(periph["r_min_list"])), hex_cells=int(len(center)), design_seconds=t_design,
+               ms_per_step=ms_step, ms_assembly=ms_nf, ms_farfield=ms_ff, steps=steps, warmup=warmup,
+               far_field_points_per_s=K * K / ms_step * 1e3, aperture_samples_per_s=M * M / ms_step * 1e3,
+               assembly_write_gbs=32.0 * M * M / world / ms_nf / 1e6,
+               nvlink_bytes_per_rank=dict(all_to_all=32 * K * K * (world - 1) // world ** 2,
+                                          gather=4 * K * K * (world - 1) // world),
+               total_P=float(total), incident_power=float(p_in), gpu_launches_per_step=launches / steps,
+               scaling="strong", exchange="peer stores over NVLink (mlb_fft_rows_scatter, mlb_peer_barrier, "
+                                          "mlb_peer_allgather)" if world > 1 else "single GPU",
+               note="total_P is the Riemann sum of P over every 4th FFT bin: the far field of a coherent lens is not "
+                    "band-limited enough for that quadrature to equal the radiated power (tests/test_farfield_gpu.py::"
+                    "test_strided_total_is_a_subsampled_sum)")
+    if clocks is not None:
+        res["clocks"] = clocks
+    if check and rank == 0:
+        # the same lens on ONE GPU: full assembly, single-GPU far field with the same kernels
+        full = torch.zeros((4, M, M), dtype=torch.complex64, device="cuda")
+        nf.run(src[0], src[1], src[2], "x", x, x, out=full)
+        plan = FarfieldPlan((M, M), d, d, wl, nf.n_glass, stride=stride, method="fft", fuse_power="always")
+        old = lib.mlb_get_option(b"rows_engine")
+        lib.mlb_set_option(b"rows_engine", 0)
+        P1, total1 = plan.run([full[i] for i in range(4)])
+        lib.mlb_set_option(b"rows_engine", old)
+        torch.cuda.synchronize()
+        same = bool(((P == P1) | (torch.isnan(P) & torch.isnan(P1))).all())
+        res["bit_identical_to_single_gpu"] = same and float(total) == float(total1)
+        assert res["bit_identical_to_single_gpu"], "cfg4: sharded far field differs from the single-GPU result"
+        del full, plan, P1
+        torch.cuda.empty_cache()
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
+def common_config(w, M, K, n_items):
+    """`config` keys shared by both arms (ours / --impl reference), so that the two lines name the same job."""
+    return {"workload": w["name"], "aperture": [M, M], "far_field": [K, K], "batch_items_per_gpu": n_items,
+            "l2": "inputs larger than L2 (%.0f MB of complex64 fields per step and GPU)" % (n_items * 32 * M * M / 1e6)}
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -266,23 +482,53 @@ def ours(args):
     # CPU baseline first (rank 0, N=1 only), before the GPU work so that the host cores are idle
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        wl_M = WORKLOADS[args.workload]["M"]
-        cpu, _ = cpu_reference(args.workload, min(wl_M, 2048) if not args.quick_cpu else 512, steps=1, warmup=0)
+        cpu = cpu_baseline_leg(args.workload if args.workload in ("cfg2", "cfg3") else "cfg3", quick=args.quick_cpu)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
+    peaks = measured_peaks()
+
+    if args.workload == "cfg4":
+        c4 = bench_cfg4(torch, dist, rank, world, args.steps, args.warmup,
+                        sample_clocks=lambda: _started(ClockSampler(local)))
+        if rank == 0:
+            K = c4["far_field"][0]
+            line = {
+                "metric": "far-field points/sec (NF->FF)", "value": c4["far_field_points_per_s"],
+                "unit": "far-field points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32 (complex64 fields, fp32 accumulate, f64 geometry/phases)",
+                "data": "synthetic",
+                "config": {"workload": c4["workload"], "aperture": c4["aperture"], "far_field": c4["far_field"],
+                           "l2": "the step writes and re-reads a 2.1 GB aperture: larger than L2",
+                           "parallelism": "one aperture over %d rank(s): rows of the assembly + fold/row FFT per rank, "
+                                          "all-to-all fused into the row pass (peer stores), column slabs, one pushed "
+                                          "all-gather of P" % world},
+                "e2e": {"value": c4["far_field_points_per_s"], "unit": "far-field points/s",
+                        "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "the step starts from the lens description (device-resident tables): no host fields exist"},
+                "gpu_launches": int(round(c4["gpu_launches_per_step"] * args.steps)), "clocks": c4.pop("clocks", None),
+                "roofline": dict(kernel="nearfield_kernel", bound="hbm", achieved=c4["assembly_write_gbs"],
+                                 peak=peaks["hbm_gbs"], unit="GB/s", frac=c4["assembly_write_gbs"] / peaks["hbm_gbs"],
+                                 traffic=None, peak_source=peaks["source"],
+                                 note="algorithmic bytes = 32*M^2/G written per rank; the kernel is instruction-bound"),
+                "cfg4": c4, "cpu_baseline": cpu,
+            }
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     w = WORKLOADS[args.workload]
     M, s = w["M"], w["stride"]
     K = M // s
     n_items = len(w["items"])
-    peaks = measured_peaks()
 
     # far-field tiles over the ranks (metalens_b200/sharding.py): weak scaling -> world x n_items batch
     # items, whole items per rank, so each rank synthesises and owns only its own apertures
     from metalens_b200.sharding import ShardedFarfield
     n_global = n_items * world
-    geom = {}
 
     def make_plan(item, r0, r1):
         wl, ng, rot = w["items"][item % n_items]
@@ -291,7 +537,8 @@ def ours(args):
         rows = None if (r0, r1) == (0, K) else (r0, r1)
         return FarfieldPlan((M, M), d, d, wl, ng, stride=s, method=args.method if rows is None else "fold", rows=rows)
 
-    sharded = ShardedFarfield(n_global, K, make_plan, rank=rank, world=world)
+    sharded = ShardedFarfield(n_global, K, make_plan, rank=rank, world=world, gather=args.gather,
+                              push_ctas=args.push_ctas)
     plans = sharded.plans
     pinned, dev_fields = {}, {}
     for item in sharded.items_needed:
@@ -307,9 +554,24 @@ def ours(args):
     def fields_of(item):
         return [dev_fields[item][f] for f in range(4)]
 
-    def step_device():
+    def step_eager():
         # local tiles + the one all-gather, which overlaps the next step's kernels (double-buffered)
         return sharded.run(fields_of, overlap=True)
+
+    # the whole step as ONE graph launch (+ the push kernel behind it across ranks); eager launches if capture fails
+    graphed = False
+    if not args.no_graph:
+        try:
+            sharded.capture(fields_of)
+            graphed = True
+        except Exception as e:                                 # noqa: BLE001 -- report and carry on eagerly
+            print("bench: CUDA-graph capture of the step unavailable (%s: %s); eager launches"
+                  % (type(e).__name__, str(e)[:200]), file=sys.stderr)
+    if world > 1:                                              # every rank must take the same path
+        flag = torch.tensor([1 if graphed else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        graphed = bool(flag.item())
+    step_device = sharded.replay if graphed else step_eager
 
     def host_runner(plan, pin):
         plan.run_host(pin)                       # pinned host -> H2D -> kernels -> D2H of P and total_P
@@ -327,6 +589,7 @@ def ours(args):
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
             fn()
+        sharded.finish()
         barrier()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
@@ -338,7 +601,7 @@ def ours(args):
         e0.record()
         for _ in range(steps):
             fn()
-        sharded.finish()                          # outstanding asynchronous all-gathers
+        sharded.finish()                          # outstanding exchanges: every peer's tiles have landed
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -354,8 +617,40 @@ def ours(args):
 
     # ---- headline: device-resident
     dev_s, _, launches, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    if graphed:
+        # graph replays do not pass through the C-ABI: count the kernels of one eager step instead
+        l0 = lib.mlb_launch_count()
+        step_eager()
+        sharded.finish()
+        torch.cuda.synchronize()
+        launches = (lib.mlb_launch_count() - l0) * args.steps
+    sharded.check()
+    sharded_gather = sharded._gather
     pts_per_step = world * n_items * K * K
     value = pts_per_step * args.steps / dev_s
+
+    # ---- parity inside the bench (rank 0): the gathered tiles of the LAST step against single-GPU plans
+    gathered_ok = None
+    if world > 1:
+        P_all, _ = step_eager()
+        sharded.finish()
+        torch.cuda.synchronize()
+        mine = sharded.items_needed
+        ok = True
+        for it, plan in zip(mine, plans):
+            Pl, _t = plan.run(fields_of(it))
+            ok = ok and bool(((P_all[it] == Pl) | (torch.isnan(P_all[it]) & torch.isnan(Pl))).all())
+        # foreign items: same apertures (seeded by item number modulo the batch) are NOT on this rank; check instead that
+        # every rank received identical bytes (checksum all-reduce MIN == MAX)
+        cs = torch.nan_to_num(P_all.double(), nan=0.0).sum(dim=(1, 2))
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = ok and bool(torch.equal(lo, hi))
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gathered_ok = bool(flag.item())
+        assert gathered_ok, "gathered far-field tiles differ from the single-GPU result / between ranks"
 
     # ---- e2e: pinned host -> H2D -> kernels -> D2H every step
     e2e_steps = max(3, min(args.steps, 10))
@@ -413,10 +708,16 @@ def ours(args):
     dom = max(kernels, key=lambda k: kernels[k]["seconds"])
     kd = kernels[dom]
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12       # nominal fp32 FMA pipe, TFLOP/s at max clock
-    if not dom.startswith("cgemm"):
-        ach = kd["bytes"] / kd["seconds"] / 1e9
+    # algorithmic bytes of NF->FF per item = 32*M^2 (four complex64 fields read once) + 4*K^2 (P written
+    # once).  The kernel that touches the aperture is charged the 32*M^2 it must read; the K x K intermediate it also
+    # writes is not algorithmic
+    algo = {"fold_fft_rows": 32 * M * M, "fft_rows": 32 * M * M, "fold": 32 * M * M}
+    if not dom.startswith("cgemm") and not dom.startswith("tc_"):
+        ab = algo.get(dom, kd["bytes"])
+        ach = ab / kd["seconds"] / 1e9
         roof = dict(kernel=dom, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=ach / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"])
+                    frac=ach / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                    algorithmic_bytes_per_launch=ab, us_per_launch=kd["seconds"] * 1e6)
     else:
         ach = kd["flops"] / kd["seconds"] / 1e12
         roof = dict(kernel=dom, bound="fp32-fma (SIMT; not a tensor-core kernel)", achieved=ach, peak=fp32_peak,
@@ -431,6 +732,11 @@ def ours(args):
             roof["traffic_source"] = t["source"]
     step_kernel_s = sum(k["seconds"] for k in kernels.values())
     roof["share_of_step"] = kd["seconds"] / step_kernel_s
+    # the whole step against the floor of its algorithmic bytes at the measured HBM peak
+    step_bytes = n_items * (32 * M * M + 4 * K * K)
+    roof["step"] = dict(algorithmic_bytes=step_bytes, ms=dev_s / args.steps * 1e3,
+                        achieved=step_bytes / (dev_s / args.steps) / 1e9,
+                        frac=step_bytes / (dev_s / args.steps) / 1e9 / peaks["hbm_gbs"])
     if "fold" in kernels:
         a = kernels["fold"]["bytes"] / kernels["fold"]["seconds"] / 1e9
         roof["fold_hbm"] = dict(achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
@@ -465,33 +771,57 @@ def ours(args):
         other["ref_default_grid"] = {"workload": "3375x3375 aperture (good_fft_number size) -> all 3375x3375 FFT bins, 580 nm",
                                      "method": p3.method, "value": M3 * M3 * 5 / t3, "ms_per_step": t3 / 5 * 1e3,
                                      "note": "big-radix mixed engine (3 x radix-15 stages in registers; columns as 15 x 225 in two passes)"}
-        del f3, p3
+        # the strict drop-in (reference signature: host complex128 FFT'd fields in, host float64 P out; only the
+        # epilogue runs on the GPU) on the same grid, wall clock
+        from metalens_b200.farfield import farfield_from_nearfield
+        F = [np.fft.fft2(np.fft.fftshift(a.astype(np.complex128))) for a in (Ex, Ey, Hx, Hy)]
+        farfield_from_nearfield(*F, x, y, wl3, ng3)
+        t0 = time.perf_counter()
+        farfield_from_nearfield(*F, x, y, wl3, ng3)
+        td = time.perf_counter() - t0
+        other["dropin_farfield_from_nearfield"] = {
+            "workload": "reference signature, 3375x3375 FFT'd complex128 host arrays -> float64 host P",
+            "seconds": td, "value": M3 * M3 / td,
+            "note": "pageable H2D of 4 x 182 MB + epilogue + D2H; the caller-side numpy FFTs are not included"}
+        del f3, p3, F
         torch.cuda.empty_cache()
 
     nf = None
     if rank == 0 and world == 1 and not args.no_nearfield:
-        del dev_fields, pinned
-        torch.cuda.empty_cache()
-        nf = bench_nearfield(args.nearfield_m, torch)
+        nf = bench_nearfield(args.nearfield_m, torch, peaks)
 
     sweep = None
     if rank == 0 and world == 1 and not args.no_paths:
         sweep = bench_sweep(torch)
 
+    # ---- BASELINE config 4 as ONE job over all ranks (strong scaling), every N
+    c4 = None
+    if not args.no_cfg4:
+        del dev_fields, pinned, sharded, plans, all_steps
+        torch.cuda.empty_cache()
+        c4 = bench_cfg4(torch, dist, rank, world, max(5, args.steps // 2), 3)
+
     if rank == 0:
+        cfg = common_config(w, M, K, n_items)
         line = {
             "metric": "far-field points/sec (NF->FF)", "value": value, "unit": "far-field points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (complex64 fields, fp32 accumulate, f64 twiddle phases/epilogue)",
             "data": "synthetic",
-            "config": {"workload": w["name"], "method": p0.method, "batch_items_per_gpu": n_items,
-                       "aperture": [M, M], "far_field": [K, K], "l2": "inputs larger than L2 (%.0f MB per step)"
-                       % (n_items * 32 * M * M / 1e6), "parallelism": "far-field tiles sharded, %d rank(s)%s" % (
-                           world, "" if world == 1 else ", tile exchange: " + {"p2p": "peer-to-peer pulls over NVLink (copy "
-                           "engines, symmetric memory)", "nccl": "NCCL all-gather"}.get(sharded._gather, sharded._gather))},
+            "config": cfg,
+            "details": {"method": p0.method, "step": "one CUDA-graph launch per step" if graphed else "eager launches",
+                        "parallelism": "far-field tiles sharded, %d rank(s)%s" % (
+                            world, "" if world == 1 else ", tile exchange: " + {
+                                "push": "every rank pushes its tiles into the peers' result buffers over NVLink "
+                                        "(mlb_peer_allgather, peer-mapped symmetric memory)",
+                                "p2p": "peer-to-peer pulls over NVLink (copy engines, symmetric memory)",
+                                "nccl": "NCCL all-gather (mlb_allgather_P)"}.get(sharded_gather, sharded_gather)),
+                        "gathered_tiles_bit_identical": gathered_ok},
             "e2e": {"value": e2e_value, "unit": "far-field points/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "h2d_gbs": h2d / world * e2e_steps / e2e_wall / 1e9,
+                    "note": "PCIe-bound: 32*M^2 bytes of host fields per item against ~0.1 ms of kernels"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -501,11 +831,18 @@ def ours(args):
             "other_workloads": other,
             "nearfield_assembly": nf,
             "fom_sweep": sweep,
+            "cfg4": c4,
             "cpu_baseline": cpu,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _started(sampler):
+    sampler.start()
+    time.sleep(0.25)
+    return sampler
 
 
 def _quiet_stdout():
@@ -540,6 +877,11 @@ def main():
     ap.add_argument("--no-nearfield", action="store_true", help="skip the aperture-assembly (hot path B) section")
     ap.add_argument("--nearfield-m", type=int, default=4096, help="aperture size of the hot path B section")
     ap.add_argument("--quick-cpu", action="store_true", help="tiny cpu_baseline sample (debug)")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 (one aperture over all ranks) block")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured step graph")
+    ap.add_argument("--gather", default="auto", choices=["auto", "push", "p2p", "nccl"], help="tile exchange (N > 1)")
+    ap.add_argument("--push-ctas", type=int, default=0, help="CTAs of the push kernel (0 = library default)")
+    ap.add_argument("--ref-budget", type=float, default=300.0, help="--impl reference: seconds for all steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -222,15 +222,28 @@ class NearfieldPlan:
         n = good_fft_number(2 * self.lens_max_r / (self.wavelength / 2.2))
         return np.linspace(-self.lens_max_r, self.lens_max_r, num=n)
 
+    def _coords(self, pts):
+        """Device copy of a coordinate list, cached on its bytes (a sweep calls run() with the same grid)."""
+        a = np.ascontiguousarray(pts, dtype=np.float64)
+        key = hash(a.tobytes())
+        cache = self.__dict__.setdefault("_coord_cache", {})
+        hit = cache.get(key)
+        if hit is None or hit.numel() != a.size:
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            hit = cache[key] = torch.from_numpy(a).to(self.device)
+        return hit
+
     def run(self, source_x, source_y, source_z, source_pol, x_pts, y_pts, dipole_moment=1e-30,
-            out_dtype=torch.complex64, verbose=False, out=None, dxdy=None):
+            out_dtype=torch.complex64, verbose=False, out=None, dxdy=None, check=True):
         """Launch the fused assembly kernel.  Returns (fields (4, nx, ld) device tensor -- logical
         view [..., :ny] --, power device scalar float64).  Raises the reference's ValueErrors.
         x_pts / y_pts need not be uniform here (a multi-GPU rank passes ITS rows of the grid, slab.py); then
-        `dxdy` gives the area element of the incident-power sum (:476-477) explicitly."""
+        `dxdy` gives the area element of the incident-power sum (:476-477) explicitly.
+        check=False does not read the bounds-violation flag back (no host synchronisation: the launch stays
+        asynchronous, e.g. inside a pipelined step); call check_violation() later -- it raises the same ValueError."""
         dev = self.device
-        d_x = torch.from_numpy(np.ascontiguousarray(x_pts, dtype=np.float64)).to(dev)
-        d_y = torch.from_numpy(np.ascontiguousarray(y_pts, dtype=np.float64)).to(dev)
+        d_x, d_y = self._coords(x_pts), self._coords(y_pts)
         nx, ny = d_x.numel(), d_y.numel()
         ld = ny + (ny & 1)
         if out is None:
@@ -238,8 +251,14 @@ class NearfieldPlan:
         assert out.dtype in (torch.complex64, torch.complex128) and tuple(out.shape) == (4, nx, ld)
         nblocks = self.lib.mlb_nearfield_blocks(nx, ny)
         block_sums = torch.empty(nblocks, dtype=torch.float64, device=dev)
-        power = torch.zeros(1, dtype=torch.float64, device=dev)
-        violation = torch.zeros(1, dtype=torch.int32, device=dev)
+        power = torch.empty(1, dtype=torch.float64, device=dev)
+        if check:
+            violation = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            if getattr(self, "_deferred", None) is None:
+                self._deferred = torch.zeros(1, dtype=torch.int32, device=dev)
+            violation = self._deferred
+            self._deferred_args = (source_x, source_y, source_z, source_pol, x_pts, y_pts, dipole_moment)
         L = self._desc(d_x, d_y, source_x, source_y, source_z, source_pol, dipole_moment)
         stats = None
 
@@ -260,7 +279,7 @@ class NearfieldPlan:
             _lib.check(rc, "mlb_nearfield_assemble")
 
         launch(bool(verbose))
-        if int(violation.item()) != 0 or verbose:
+        if check and (int(violation.item()) != 0 or verbose):
             if stats is None:
                 violation.zero_()
                 launch(True)                 # slow path: collect min/max for the reference's messages
@@ -272,6 +291,16 @@ class NearfieldPlan:
         rc = self.lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, dxdy, power.data_ptr(), _stream_ptr())      # :476-477
         _lib.check(rc, "mlb_sum_f64")
         return out, power
+
+    def check_violation(self):
+        """Deferred bounds check of run(check=False) calls: raises the reference's ValueError (:294-305, :412-419)
+        if any of them left the tables (by re-running the last one with statistics)."""
+        flag = getattr(self, "_deferred", None)
+        if flag is not None and int(flag.item()) != 0:
+            flag.zero_()
+            a = self._deferred_args
+            self.run(a[0], a[1], a[2], a[3], a[4], a[5], dipole_moment=a[6], check=True)
+            raise _lib.MetalensB200Error("an earlier run(check=False) call left the interpolation tables")
 
     def _report(self, stats, verbose):
         """Replay the reference's per-order bounds checks in its own loop order

@@ -268,8 +268,9 @@ class ShardedFarfield:
             res = gather_tiles(self._local[b], self.n_items, self.n_rows, self.world, self.group, out=self._out[b])
         return res, totals
 
-    def _run_pipelined(self, fields_of, b):
-        """overlap=True on CUDA: two-stream software pipeline over the local tiles (see __init__)."""
+    def _run_pipelined(self, fields_of, b, exchange=True):
+        """overlap=True on CUDA: two-stream software pipeline over the local tiles (see __init__).
+        exchange=False stops after the tile copies (the captured part of a step, see capture())."""
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.plans[0].P.device, priority=self._tail_priority)
@@ -300,7 +301,11 @@ class ShardedFarfield:
                 self._tail_done[id(plan)] = done
         cuda = self.world > 1
         with torch.cuda.stream(side):
-            if cuda and self._gather == "push":
+            if not exchange:
+                res = self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
+                if self.world == 1:
+                    gather_tiles(self._local[b], self.n_items, self.n_rows, 1, self.group, out=self._out[b])
+            elif cuda and self._gather == "push":
                 res = self._gather_push(b)               # on the side stream, right behind the last tile copy
             elif cuda and self._gather == "p2p":
                 res = self._gather_p2p(b, side)
@@ -316,28 +321,52 @@ class ShardedFarfield:
         return res, totals
 
     def capture(self, fields_of):
-        """Capture one pipelined step (every local tile, both streams, the tile copies) into a CUDA graph and
-        return it; ``replay()`` then re-runs the step on whatever is in the same field buffers with a single
-        launch.  Single-rank only (world == 1): with more ranks the exchange stays outside the graph."""
-        if self.world != 1:
-            raise ValueError("capture() is for world == 1; use run(overlap=True) across ranks")
-        self.run(fields_of, overlap=True)                # warm-up outside capture (lazy allocations, attributes)
+        """Capture the pipelined step (every local tile, both streams, the tile copies) into CUDA graphs, one per
+        flip buffer; ``replay()`` then re-runs the step on whatever is in the same field buffers with a single graph
+        launch.  Across ranks (push exchange only) the exchange stays OUTSIDE the graphs: replay() launches the push
+        kernel on the side stream behind the graph, so it still runs under the next step's graph."""
+        if self.world != 1 and self._gather not in ("auto", "push"):
+            raise ValueError("capture() across ranks needs the push exchange")
+        for _ in range(2):                               # warm-up outside capture (lazy allocations, both flip buffers)
+            self.run(fields_of, overlap=True)
         self.finish()
         torch.cuda.synchronize()
-        self._tail_done = {}                             # no dependencies on events recorded outside the capture
-        self._flip = 0
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._graph_result = self.run(fields_of, overlap=True)
-            self.finish()                                # joins the side stream back into the capturing stream
+        if self.world != 1 and self._gather != "push":
+            raise ValueError("capture() across ranks needs the push exchange (got %s)" % self._gather)
+        self._graphs, self._graph_results = [], []
+        for b in (0, 1):
+            self._tail_done = {}                         # no dependencies on events recorded outside the capture
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self._run_pipelined(fields_of, b, exchange=False)
+                torch.cuda.current_stream().wait_event(self._side_done)   # join the side stream back
+                self._side_done = None
+            self._graphs.append(g)
+            self._graph_results.append(res)
         self._tail_done = {}
-        self._graph = g
-        return g
+        self._push_done = [None, None]
+        self._flip = 0
+        return self._graphs
 
     def replay(self):
-        """Replay the captured step; returns (P (n_items, n_rows, Ky), totals) like run()."""
-        self._graph.replay()
-        return self._graph_result
+        """Replay the captured step; returns (P (n_items, n_rows, Ky), totals) like run(overlap=True)."""
+        b = self._flip
+        self._flip ^= 1
+        main = torch.cuda.current_stream()
+        if self._push_done[b] is not None:               # the push that last read this tile stack
+            main.wait_event(self._push_done[b])
+        self._graphs[b].replay()
+        if self.world > 1:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                self._gather_push(b)
+                done = torch.cuda.Event()
+                done.record(self._side)
+            self._push_done[b] = done
+            self._side_done = done
+        return self._graph_results[b]
 
     def finish(self):
         """Wait for outstanding asynchronous exchanges (and, in pipelined mode, make the caller's stream

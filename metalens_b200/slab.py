@@ -171,7 +171,7 @@ class SlabFarfield:
         return self.P, self.total
 
 
-def assemble_slab(nf_plan, slab, source, source_pol, x_pts, y_pts, dipole_moment=1e-30, out=None):
+def assemble_slab(nf_plan, slab, source, source_pol, x_pts, y_pts, dipole_moment=1e-30, out=None, check=True):
     """Hot path B for a SlabFarfield rank: the fused assembly kernel on this rank's aperture rows only
     (nearfield.py:488-514 builds disjoint slabs independently).  Returns (fields (4, rows, ld) complex64,
     partial incident power (device scalar, sum over ranks = the full lens))."""
@@ -179,4 +179,4 @@ def assemble_slab(nf_plan, slab, source, source_pol, x_pts, y_pts, dipole_moment
     y_pts = np.asarray(y_pts, dtype=np.float64)
     dxdy = float(x_pts[1] - x_pts[0]) * float(y_pts[1] - y_pts[0])
     return nf_plan.run(source[0], source[1], source[2], source_pol, x_pts[slab.x_rows], y_pts,
-                       dipole_moment=dipole_moment, out=out, dxdy=dxdy)
+                       dipole_moment=dipole_moment, out=out, dxdy=dxdy, check=check)
