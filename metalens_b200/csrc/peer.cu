@@ -86,18 +86,34 @@ __global__ void __launch_bounds__(512) peer_allgather_kernel(const __grid_consta
             atomicExch(state + ST_ERROR, 1u);
     }
     __syncthreads();
-    // push: peers in rotated order so that at any moment the ranks write to different destinations
+    // push: every 16-byte vector is loaded once and stored to all peers (rotated order, so that at any moment the ranks
+    // write to different destinations); U vectors per thread in flight -- the loop is latency-bound otherwise
+    constexpr int U = 4;
     const long long per_peer = (long long)a.rows * a.row_vec;
-    const long long total = per_peer * a.world;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int step = (int)(idx / per_peer);
-        const long long rem = idx - (long long)step * per_peer;
-        const int row = (int)(rem / a.row_vec), v = (int)(rem - (long long)row * a.row_vec);
-        int p = a.rank + 1 + step;
-        if (p >= a.world) p -= a.world;
-        const uint4 x = *reinterpret_cast<const uint4 *>(a.src + (long long)row * a.src_pitch + (long long)v * 16);
-        unsigned char *d = reinterpret_cast<unsigned char *>(a.dst.p[p]) + a.dst_offset + (long long)row * a.dst_pitch + (long long)v * 16;
-        if (d != a.src + (long long)row * a.src_pitch + (long long)v * 16) *reinterpret_cast<uint4 *>(d) = x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + tid; base < per_peer; base += stride * U) {
+        uint4 x[U];
+        long long soff[U], doff[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long idx = base + u * stride;
+            if (idx < per_peer) {
+                const int row = (int)(idx / a.row_vec), v = (int)(idx - (long long)row * a.row_vec);
+                soff[u] = (long long)row * a.src_pitch + (long long)v * 16;
+                doff[u] = a.dst_offset + (long long)row * a.dst_pitch + (long long)v * 16;
+                x[u] = *reinterpret_cast<const uint4 *>(a.src + soff[u]);
+            } else {
+                soff[u] = -1;
+            }
+        }
+        for (int step = 0; step < a.world; ++step) {
+            int p = a.rank + 1 + step;
+            if (p >= a.world) p -= a.world;
+            unsigned char *dbase = reinterpret_cast<unsigned char *>(a.dst.p[p]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (soff[u] >= 0 && dbase + doff[u] != a.src + soff[u]) *reinterpret_cast<uint4 *>(dbase + doff[u]) = x[u];
+        }
     }
     if (blockIdx.x == 0 && a.n_aux > 0) {
         for (int i = tid; i < a.n_aux * a.world; i += blockDim.x) {
@@ -193,7 +209,7 @@ extern "C" int mlb_peer_allgather(const void *src, long long src_pitch, int rows
         a.n_aux = n_aux;
     }
     if (n_ctas <= 0) n_ctas = 16;
-    const long long work = ((long long)rows * a.row_vec * world + 511) / 512;
+    const long long work = ((long long)rows * a.row_vec + 511) / 512;
     if (n_ctas > work) n_ctas = (int)work;
     if (n_ctas > 148) n_ctas = 148;                 // all CTAs must be co-resident: they wait for each other's peers
     mlb::peer_allgather_kernel<<<n_ctas, 512, 0, (cudaStream_t)stream>>>(a, reinterpret_cast<unsigned int *>(local_state));

@@ -456,6 +456,12 @@ class FarfieldPlan:
         _lib.check(rc, "mlb_sum_f64")
         return self.P, self.total
 
+    def bind_output(self, P):
+        """Make run() write the power map straight into the caller's (Kx, Ky) tensor (e.g. a slot of a tile stack that
+        is exchanged between GPUs) instead of the plan's own buffer: saves the copy."""
+        assert tuple(P.shape) == (self.Kx, self.Ky) and P.dtype == self.p_dtype and P.is_contiguous() and P.is_cuda
+        self.P = P
+
     def run(self, fields, accumulate=False):
         """Device-resident fields (4 CUDA complex64 (Mx,My) tensors) -> (P, total_P) on device.
         accumulate=True adds this item's power to P (total_P is that of this item alone)."""

@@ -100,10 +100,12 @@ class ShardedFarfield:
         self._tail_done = {}                            # per plan object: its buffers are free again (side-stream event)
         self._side_done = None
         # How the finished tiles travel (CUDA, world > 1):
-        #   "push" (default of "auto"): mlb_peer_allgather -- a few CTAs store the rank's tile stack into every peer's
-        #           result buffer (torch symmetric memory supplies the peer mappings); flag epochs instead of barriers, so
-        #           nothing on the per-step path blocks: a step's pushes run under the next step's row pass;
-        #   "p2p":  the peers' stacks are PULLED by the copy engines (round-1 path, two signal-pad barriers per step);
+        #   "p2p" (default of "auto"): the peers' stacks are PULLED over NVLink by the copy engines (torch symmetric
+        #           memory: peer-mapped stacks + two signal-pad barriers per step) -- no SM time next to the persistent,
+        #           HBM-bound row pass.  Measured best for this overlapped exchange: 2 GPUs 0.358 ms/step vs 0.386 pushed;
+        #   "push": mlb_peer_allgather -- CTAs of this library store the rank's stack into every peer's result buffer
+        #           (flag epochs instead of barriers).  The mechanism of the one-aperture path (slab.py), where the
+        #           exchange is on the critical path anyway; here its CTAs take issue slots from the row pass;
         #   "nccl": mlb_allgather_P (the C-ABI's NCCL wrapper) on a communication stream.
         # CPU tensors (gloo tests) always use torch's all_gather_into_tensor.
         assert gather in ("auto", "nccl", "p2p", "push")
@@ -143,6 +145,7 @@ class ShardedFarfield:
             self._out_ptrs[b] = ptrs
         self._chan = PeerChannel(peers, "tiles.chan")
         self._stack_bytes = nbytes // self.world
+        self._comm = torch.cuda.Stream(device=device)
         peers.sync()
 
     def _alloc(self, b, P):
@@ -153,13 +156,13 @@ class ShardedFarfield:
             mode, err = self._gather, None
             if mode in ("auto", "push", "p2p"):
                 try:
-                    if mode == "p2p":
-                        self._setup_p2p(shape, P.dtype, P.device)
-                    else:
+                    if mode == "push":
                         if shape[1] * shape[2] * P.element_size() % 16:
                             raise ValueError("tile bytes not a multiple of 16")
                         self._setup_push(shape, P.dtype, P.device)
-                        mode = "push"
+                    else:
+                        self._setup_p2p(shape, P.dtype, P.device)
+                        mode = "p2p"
                 except Exception as e:
                     err = e
             ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=P.device)
@@ -185,6 +188,13 @@ class ShardedFarfield:
             self._local[b] = torch.empty(shape, dtype=P.dtype, device=P.device)
             self._out[b] = torch.empty((self.world * shape[0],) + shape[1:], dtype=P.dtype, device=P.device)
 
+    def _bind(self, plan, b, k):
+        """The plan writes tile k of flip buffer b straight into its slot of the tile stack (no copy)."""
+        if self._local[b] is not None and hasattr(plan, "bind_output"):
+            slot = self._local[b][k]
+            if slot.is_cuda and tuple(slot.shape) == (plan.Kx, plan.Ky) and slot.dtype == plan.p_dtype:
+                plan.bind_output(slot)
+
     def _gather_p2p(self, b, producer_stream):
         """Pull every rank's tile stack into out[b] on the communication stream (copy engines), bracketed by the two
         barriers of torch's low-contention all-gather: all stacks ready before anyone pulls, all pulls done before
@@ -205,11 +215,20 @@ class ShardedFarfield:
         self._gather_done[b] = done
         return self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
 
-    def _gather_push(self, b):
-        """mlb_peer_allgather on the CURRENT stream (the one that produced the tiles): store this rank's stack into
-        every peer's out[b].  Nothing waits here; finish() acquires the peers' completion flags."""
-        self._chan.allgather(self._local[b].data_ptr(), self._stack_bytes, 1, self._stack_bytes, self._out_ptrs[b],
-                             self._stack_bytes, self.rank * self._stack_bytes, n_ctas=self._push_ctas)
+    def _gather_push(self, b, producer_stream):
+        """mlb_peer_allgather on the communication stream, behind the producer's last tile copy: store this rank's
+        stack into every peer's out[b].  Its own stream, because the kernel first waits for the peers to enter the
+        same gather: that wait must not hold up the tails of the next step's tiles.  Nothing else waits here;
+        finish() acquires the peers' completion flags."""
+        ready = torch.cuda.Event()
+        ready.record(producer_stream)
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            self._chan.allgather(self._local[b].data_ptr(), self._stack_bytes, 1, self._stack_bytes, self._out_ptrs[b],
+                                 self._stack_bytes, self.rank * self._stack_bytes, n_ctas=self._push_ctas)
+            done = torch.cuda.Event()
+            done.record(self._comm)
+        self._gather_done[b] = done                     # the stack may be overwritten once its push has run
         self._pushed = True
         return self._out[b].view(self.n_items, self.n_rows, self._out[b].shape[-1])
 
@@ -244,17 +263,20 @@ class ShardedFarfield:
             self._work[b] = None
         totals = []
         for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
+            if k == 0 and self._gather_done[b] is not None:      # peers may still be pulling this stack (two steps ago)
+                torch.cuda.current_stream().wait_event(self._gather_done[b])
+            self._bind(plan, b, k)
             P, total = plan.run(fields_of(tile.item)) if runner is None else runner(plan, fields_of(tile.item))
             if self._local[b] is None:
                 self._alloc(b, P)
-            if k == 0 and self._gather_done[b] is not None:      # peers may still be pulling this stack (two steps ago)
-                torch.cuda.current_stream().wait_event(self._gather_done[b])
-            self._local[b][k].copy_(P)
+            if P.data_ptr() != self._local[b][k].data_ptr():
+                self._local[b][k].copy_(P)
             totals.append(total)
         cuda = self.world > 1 and self._local[b].is_cuda
         if cuda and self._gather == "push":
-            res = self._gather_push(b)
+            res = self._gather_push(b, torch.cuda.current_stream())
             if not overlap:
+                torch.cuda.current_stream().wait_event(self._gather_done[b])
                 self._chan.wait()
         elif cuda and self._gather in ("p2p", "nccl"):
             cur = torch.cuda.current_stream()
@@ -277,6 +299,7 @@ class ShardedFarfield:
         side = self._side
         totals = []
         for k, (tile, plan) in enumerate(zip(self.tiles, self.plans)):
+            self._bind(plan, b, k)
             first, second = plan.run_split(fields_of(tile.item))
             prev = self._tail_done.get(id(plan))
             if prev is not None:                         # the previous tail of this plan still reads its buffers
@@ -289,12 +312,13 @@ class ShardedFarfield:
                 if k == 0 and self._work[b] is not None:     # the collective that last used this buffer pair
                     self._work[b].wait()
                     self._work[b] = None
+                if k == 0 and self._gather_done[b] is not None:  # peers may still be reading this stack (two steps ago)
+                    side.wait_event(self._gather_done[b])
                 P, total = second()
                 if self._local[b] is None:
                     self._alloc(b, P)
-                if k == 0 and self._gather_done[b] is not None:  # peers may still be pulling this stack (p2p / nccl)
-                    side.wait_event(self._gather_done[b])
-                self._local[b][k].copy_(P)
+                if P.data_ptr() != self._local[b][k].data_ptr():
+                    self._local[b][k].copy_(P)
                 totals.append(total)
                 done = torch.cuda.Event()
                 done.record(side)
@@ -306,7 +330,7 @@ class ShardedFarfield:
                 if self.world == 1:
                     gather_tiles(self._local[b], self.n_items, self.n_rows, 1, self.group, out=self._out[b])
             elif cuda and self._gather == "push":
-                res = self._gather_push(b)               # on the side stream, right behind the last tile copy
+                res = self._gather_push(b, side)
             elif cuda and self._gather == "p2p":
                 res = self._gather_p2p(b, side)
             elif cuda and self._gather == "nccl":
@@ -333,6 +357,7 @@ class ShardedFarfield:
         torch.cuda.synchronize()
         if self.world != 1 and self._gather != "push":
             raise ValueError("capture() across ranks needs the push exchange (got %s)" % self._gather)
+        self._gather_done = [None, None]                 # recorded outside the capture: nothing to wait for after the sync
         self._graphs, self._graph_results = [], []
         for b in (0, 1):
             self._tail_done = {}                         # no dependencies on events recorded outside the capture
@@ -344,7 +369,6 @@ class ShardedFarfield:
             self._graphs.append(g)
             self._graph_results.append(res)
         self._tail_done = {}
-        self._push_done = [None, None]
         self._flip = 0
         return self._graphs
 
@@ -353,19 +377,11 @@ class ShardedFarfield:
         b = self._flip
         self._flip ^= 1
         main = torch.cuda.current_stream()
-        if self._push_done[b] is not None:               # the push that last read this tile stack
-            main.wait_event(self._push_done[b])
+        if self._gather_done[b] is not None:             # the push that last read this tile stack
+            main.wait_event(self._gather_done[b])
         self._graphs[b].replay()
         if self.world > 1:
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(self._side):
-                self._side.wait_event(ev)
-                self._gather_push(b)
-                done = torch.cuda.Event()
-                done.record(self._side)
-            self._push_done[b] = done
-            self._side_done = done
+            self._gather_push(b, main)
         return self._graph_results[b]
 
     def finish(self):

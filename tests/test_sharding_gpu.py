@@ -35,15 +35,23 @@ def _worker(rank, world, port, n_items, method, gather, q):
         def make_plan(item, r0, r1):
             rows = None if (r0, r1) == (0, K) else (r0, r1)
             return FarfieldPlan((M, M), d, d, WL, NG, stride=4, method=method, rows=rows)
+        graph = gather == "graph"
+        gather = "push" if graph else gather
         sh = ShardedFarfield(n_items, K, make_plan, gather=gather)
         dev = {i: [torch.from_numpy(a).cuda() for a in _fields(i)[:4]] for i in sh.items_needed}
         P, _ = sh.run(lambda item: dev[item])
         torch.cuda.synchronize()
+        P = P.clone()
         # overlapped (asynchronous, double-buffered) gathers give the same result
-        outs = [sh.run(lambda item: dev[item], overlap=True)[0] for _ in range(3)]
+        if graph:
+            sh.capture(lambda item: dev[item])
+            outs = [sh.replay()[0] for _ in range(5)]
+        else:
+            outs = [sh.run(lambda item: dev[item], overlap=True)[0] for _ in range(3)]
         sh.finish()
         torch.cuda.synchronize()
-        assert all(bool(((o == P) | (torch.isnan(o) & torch.isnan(P))).all()) for o in outs)
+        sh.check()
+        assert all(bool(((o == P) | (torch.isnan(o) & torch.isnan(P))).all()) for o in outs[-2:])
         ref = []
         for i in range(n_items):
             plan = FarfieldPlan((M, M), d, d, WL, NG, stride=4, method=method)
@@ -55,10 +63,12 @@ def _worker(rank, world, port, n_items, method, gather, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_items,method,gather", [(2, "fft", "p2p"), (4, "fold", "nccl"), (1, "fold", "p2p"),
-                                                   (3, "dense", "auto"), (2, "fft", "nccl")])
+@pytest.mark.parametrize("n_items,method,gather", [(2, "fft", "push"), (4, "fold", "nccl"), (1, "fold", "push"),
+                                                   (3, "dense", "auto"), (2, "fft", "p2p"), (6, "fft", "graph")])
 def test_two_rank_gather_equals_single_gpu(n_items, method, gather):
-    """gather: 'p2p' = tiles pulled over NVLink by the copy engines (symmetric memory), 'nccl' = all_gather_into_tensor"""
+    """gather: 'push' = mlb_peer_allgather (every rank stores its tiles into the peers' buffers over NVLink), 'p2p' =
+    tiles pulled by the copy engines, 'nccl' = mlb_allgather_P (the C-ABI's NCCL wrapper); 'graph' = push with the
+    step replayed as CUDA graphs"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
