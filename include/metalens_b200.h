@@ -252,6 +252,11 @@ typedef struct mlb_table_pack {
     double bounds[6];
     int stats_slot;
     int order_radius;
+    /* uniform01 != 0: the ux and uy axes are uniformly spaced (what characterize() produces, grating.py:1167-1172):
+     * the complex64-output kernel then locates the interpolation cell arithmetically, cell = (u - u_first) * inv_step,
+     * instead of by bisection (same interpolant; an index may differ from searchsorted only where the weight is 0 or 1) */
+    int uniform01, _pad;
+    double u0_first, u0_inv_step, u1_first, u1_inv_step;
 } mlb_table_pack;
 
 /* Everything build_nearfield (nearfield.py:66-480) reads, as device arrays + scalars. */
@@ -319,6 +324,18 @@ int mlb_nearfield_tune(int min_blocks);
 int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
                            int out_is_double, double *power_block_sums, long long *stats, int want_stats,
                            int *violation, void *stream);
+/* Exact nearest-cell ties (nearfield.py:363-364).  A centre sample exactly equidistant from two hex cells gets the
+ * highest original row here, while the reference's cKDTree returns whichever cell its traversal meets first.
+ * mlb_nearfield_assemble_ties is mlb_nearfield_assemble that also reports those samples: tie_count[0] (zero it first)
+ * counts them and tie_list receives the first `tie_capacity` linear sample indices i*ny + j.  A binding that wants the
+ * reference's choice resolves them on the host with the same cKDTree call and re-assembles just those samples with
+ * mlb_nearfield_fixup: sample fix_samples[t] takes the cell with SORTED position fix_cells[t] (index into
+ * cell_x / cell_y); the power sums are not touched. */
+int mlb_nearfield_assemble_ties(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
+                                int out_is_double, double *power_block_sums, long long *stats, int want_stats,
+                                int *violation, int *tie_count, int *tie_list, int tie_capacity, void *stream);
+int mlb_nearfield_fixup(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld, int out_is_double,
+                        const int *fix_samples, const int *fix_cells, int n_fix, int *violation, void *stream);
 
 /* Trilinear gather of ONE table (scipy RegularGridInterpolator linear mode):
  * axes = u0[n0]|u1[n1]|u2[n2], values complex128 [n0][n1][n2], pts float64 [n][3] -> out complex128 [n] */

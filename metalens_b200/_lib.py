@@ -64,6 +64,11 @@ SIGNATURES = {
     "mlb_nearfield_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mlb_nearfield_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_nearfield_assemble_ties": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_void_p]),
+    "mlb_nearfield_fixup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_table_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     # 8e: multi-GPU exchange steps (peer memory over NVLink; NCCL wrappers)

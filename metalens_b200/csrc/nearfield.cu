@@ -62,8 +62,22 @@ struct NfUniform {
     float ng2, cf;
 };
 
+// cell and weight on a uniformly spaced axis: (u - first) * inv_step, clipped like scipy's find_indices
+__device__ __forceinline__ void locate_uniform(double u, double first, double inv_step, int n, int &i, double &t) {
+    const double f = (u - first) * inv_step;
+    int c = (int)f;                                   // f >= 0 inside the bounds; clipping handles the rest
+    c = min(max(c, 0), n - 2);
+    i = c;
+    t = f - (double)c;
+}
 // first two axes of the table (third: precomputed per ring, or located by the caller)
+template <bool FAST>
 __device__ __forceinline__ void locate2(const mlb_table_pack &p, double u0, double u1, Interp3 &q) {
+    if (FAST && p.uniform01) {
+        locate_uniform(u0, p.u0_first, p.u0_inv_step, p.n_ux, q.i0, q.t0);
+        locate_uniform(u1, p.u1_first, p.u1_inv_step, p.n_uy, q.i1, q.t1);
+        return;
+    }
     const double *a0 = p.axes, *a1 = p.axes + p.n_ux;
     q.i0 = find_interval(a0, p.n_ux, u0);
     q.i1 = find_interval(a1, p.n_uy, u1);
@@ -112,6 +126,16 @@ __device__ __forceinline__ cf operator+(cf a, cf b) { return {a.re + b.re, a.im 
 __device__ __forceinline__ cf operator*(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 __device__ __forceinline__ cf operator*(cf a, float s) { return {a.re * s, a.im * s}; }
 __device__ __forceinline__ cf operator*(float s, cf a) { return {a.re * s, a.im * s}; }
+
+// 1/sqrt(v) for positive, fp32-representable v: fp32 seed (2^-22) + two Newton steps in float64 (-> ~1 ulp);
+// a third of the instructions of sqrt + division
+__device__ __forceinline__ double rsqrt_fast(double v) {
+    double y = (double)rsqrtf((float)v);
+    const double h = 0.5 * v;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
 
 __device__ __forceinline__ cplx expi(double x) {
     double s, c;
@@ -246,6 +270,11 @@ struct NfOut {
     long long *stats;
     int *violation;
     int ld, out_is_double, lg_wy;     // lg_wy: log2 of the warp tile's y extent (5 = 32 x 1 ... 2 = 4 x 8)
+    // exact nearest-cell ties: reported to (tie_count, tie_list[tie_capacity]) when tie_count != NULL;
+    // fix-up launches (FIX): thread t re-assembles sample fix_samples[t] with the forced cell fix_cells[t]
+    int *tie_count, *tie_list;
+    int tie_capacity, n_fix;
+    const int *fix_samples, *fix_cells;
 };
 
 // The diffraction-order loop of one sample (periphery: primed grating frame, nearfield.py:263-327; centre:
@@ -282,7 +311,7 @@ __device__ __forceinline__ void order_loop(const mlb_table_pack &p, const NfUnif
                 if (!located) {
                     located = true;
                     if (out_of_bounds(p, u0, u1, u2, check2)) atomicOr(out.violation, 1);   // :294-305 / :412-419
-                    locate2(p, u0, u1, q);
+                    locate2<FAST>(p, u0, u1, q);
                     if (!have_q3) locate3(p, u2, q);
                     if constexpr (FAST) cell = make_cell(p, q);
                 }
@@ -307,7 +336,7 @@ __device__ __forceinline__ void store_c(void *base, size_t off, cplx v, int is_d
     else reinterpret_cast<float2 *>(base)[off] = make_float2((float)v.re, (float)v.im);
 }
 
-template <bool STATS, bool FAST, int MINB>
+template <bool STATS, bool FAST, int MINB, bool FIX = false>
 __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __grid_constant__ mlb_lens_desc L,
                                                                       const __grid_constant__ NfUniform U, const NfOut out) {
     using Acc = typename std::conditional<FAST, cf, cplx>::type;      // per-sample field accumulators
@@ -315,8 +344,18 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
     // a warp covers wy (y, fast) x 32/wy (x) samples, the four warps of a block are stacked along y: compact warp
     // footprints touch fewer rings and table cells per gather than a 32 x 1 line that crosses the rings radially
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wy = 1 << out.lg_wy;
-    const int j = (blockIdx.x * (NF_THREADS / 32) + warp) * wy + (lane & (wy - 1));   // y index (fast)
-    const int i = blockIdx.y * (32 >> out.lg_wy) + (lane >> out.lg_wy);               // x index
+    int j = (blockIdx.x * (NF_THREADS / 32) + warp) * wy + (lane & (wy - 1));         // y index (fast)
+    int i = blockIdx.y * (32 >> out.lg_wy) + (lane >> out.lg_wy);                     // x index
+    int forced_cell = -1;
+    if (FIX) {                                                                        // one listed sample per thread
+        const int t = blockIdx.x * NF_THREADS + threadIdx.x;
+        i = L.nx; j = L.ny;
+        if (t < out.n_fix) {
+            const int lin = out.fix_samples[t];
+            i = lin / L.ny; j = lin - i * L.ny;
+            forced_cell = out.fix_cells[t];
+        }
+    }
     const double PI = 3.14159265358979323846;
     double local_power = 0.0;
     if (j < L.ny && i < L.nx) {
@@ -347,14 +386,14 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             dHx = -py * dm / L.Z0; dHy = px * dm / L.Z0;
         } else {
             const double dx = x - L.source_x, dy = y - L.source_y, dz = 0.0 - L.source_z;
-            const double dist = sqrt(dx * dx + dy * dy + dz * dz);
             double a;
             if (FAST) {
-                const double inv = 1.0 / dist;
+                const double inv = rsqrt_fast(dx * dx + dy * dy + dz * dz);
                 ux = dx * inv; uy = dy * inv; uz = dz * inv;
-                a = sqrt(uz) * inv;
+                a = uz * rsqrt_fast(uz) * inv;                                      // sqrt(uz) / dist
                 scale = U.Hcoef;
             } else {
+                const double dist = sqrt(dx * dx + dy * dy + dz * dz);
                 ux = dx / dist; uy = dy / dist; uz = dz / dist;
                 a = U.Hcoef * sqrt(uz) / dist;                                      // :213-219
                 scale = 1.0;
@@ -402,8 +441,9 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             }
             if (!L.plane_wave) {                                                    // :337-346
                 const double gx = rc * c, gy = rc * s;                              // :170-171
-                const double path = sqrt((gx - L.source_x) * (gx - L.source_x) + (gy - L.source_y) * (gy - L.source_y) +
-                                         L.source_z * L.source_z);
+                const double path2 = (gx - L.source_x) * (gx - L.source_x) + (gy - L.source_y) * (gy - L.source_y) +
+                                     L.source_z * L.source_z;
+                const double path = FAST ? path2 * rsqrt_fast(path2) : sqrt(path2);
                 if constexpr (FAST) {
                     const cf e = expi_fast(U.kvac * path);
                     Exp = Exp * e; Eyp = Eyp * e; Hxp = Hxp * e; Hyp = Hyp * e;
@@ -423,10 +463,18 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             local_power = (dEx * dHy - dEy * dHx) * (scale * scale);
             int best = -1, best_orig = -1;
             double best_d2 = CUDART_INF;
-            if (L.n_cells > 0) {
-                int bx = (int)floor((x - L.bin_x0) / L.bin_size), by = (int)floor((y - L.bin_y0) / L.bin_size);
+            bool tie = false;
+            if (FIX) {
+                best = forced_cell;
+            } else if (L.n_cells > 0) {
+                const double fx = (x - L.bin_x0) / L.bin_size, fy = (y - L.bin_y0) / L.bin_size;
+                int bx = (int)floor(fx), by = (int)floor(fy);
                 bx = min(max(bx, 0), L.nbx - 1);
                 by = min(max(by, 0), L.nby - 1);
+                // distance from the sample to the border of its own bin: after ring k of bins every unvisited cell is at
+                // least (k + that) bins away (0 if the sample lies outside the bin grid)
+                const double inside = fmin(fmin(fx - bx, bx + 1 - fx), fmin(fy - by, by + 1 - fy));
+                const double edge = fmax(inside, 0.0) * L.bin_size;
                 const int kmax = max(L.nbx, L.nby);
                 for (int k = 0; k <= kmax; ++k) {
                     for (int iy = by - k; iy <= by + k; ++iy) {
@@ -439,15 +487,22 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                             for (int cidx = L.bin_start[bb]; cidx < L.bin_start[bb + 1]; ++cidx) {
                                 const double ddx = L.cell_x[cidx] - x, ddy = L.cell_y[cidx] - y;
                                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                                const int orig = L.cell_orig[cidx];
-                                if (d2 < best_d2 || (d2 == best_d2 && orig > best_orig)) {   // exact ties: highest row wins
-                                    best_d2 = d2; best = cidx; best_orig = orig;
+                                if (d2 < best_d2) {
+                                    best_d2 = d2; best = cidx; best_orig = L.cell_orig[cidx]; tie = false;
+                                } else if (d2 == best_d2) {                     // exact tie: highest row wins, and is reported
+                                    tie = true;
+                                    const int orig = L.cell_orig[cidx];
+                                    if (orig > best_orig) { best = cidx; best_orig = orig; }
                                 }
                             }
                         }
                     }
-                    const double reach = k * L.bin_size;
-                    if (best >= 0 && best_d2 <= reach * reach) break;
+                    const double reach = (k * L.bin_size + edge) * (1.0 - 1e-12);
+                    if (best >= 0 && best_d2 < reach * reach) break;
+                }
+                if (tie && out.tie_count) {
+                    const int slot = atomicAdd(out.tie_count, 1);
+                    if (slot < out.tie_capacity) out.tie_list[slot] = i * L.ny + j;
                 }
             }
             if (best >= 0) {
@@ -461,8 +516,9 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                 order_loop<STATS, FAST, Acc, W>(L.hex, U, L.Z0, ux, uy, which, false, false, q, x - cx, y - cy, qx, qy, fqx, fqy,
                                                 1.0f / fqx, 1.0f / fqy, (W)dHy, (W)dHx, out, Ex, Ey, Hx, Hy);
                 if (!L.plane_wave) {                                                // :453-461
-                    const double path = sqrt((cx - L.source_x) * (cx - L.source_x) + (cy - L.source_y) * (cy - L.source_y) +
-                                             L.source_z * L.source_z);
+                    const double path2 = (cx - L.source_x) * (cx - L.source_x) + (cy - L.source_y) * (cy - L.source_y) +
+                                         L.source_z * L.source_z;
+                    const double path = FAST ? path2 * rsqrt_fast(path2) : sqrt(path2);
                     if constexpr (FAST) {
                         const cf e = expi_fast(U.kvac * path);
                         Ex = Ex * e; Ey = Ey * e; Hx = Hx * e; Hy = Hy * e;
@@ -489,6 +545,7 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
     }
     // incident power through the lens (:474-477), deterministic per-warp partial sums (no block barrier: the
     // warps of a block finish at very different times)
+    if (FIX) return;
     double v = local_power;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -520,7 +577,9 @@ __global__ void nearfield_prepare_kernel(const __grid_constant__ mlb_lens_desc L
         rf.fqx = (float)(ra.qx / kvac); rf.fqy = (float)(ra.qy / kvac);
         rf.inv_fqx = 1.0f / rf.fqx; rf.inv_fqy = 1.0f / rf.fqy;
         rf.inv_apg = (float)(1.0 / ra.apg);
-        rf.guard = fminf(0.5f, 4e-6f * rf.inv_apg + 1e-6f);
+        // |error of atan2f(yf, xf) * inv_apg| <= (2 ulp of pi-sized results 4.8e-7 + input rounding 6e-8 + the roundings
+        // of inv_apg and of the product, 1.2e-7 * pi) * inv_apg = 9.2e-7 * inv_apg; guard = 1.6 x that
+        rf.guard = fminf(0.5f, 1.5e-6f * rf.inv_apg + 1e-6f);
         rf.pad0 = rf.pad1 = 0.f;
         reinterpret_cast<RingAuxF *>(L.ring_aux_f32)[t] = rf;
     }
@@ -621,29 +680,35 @@ extern "C" int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream) 
     return mlb::check_launch("mlb_nearfield_prepare");
 }
 
-extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
-                                      int out_is_double, double *power_block_sums, long long *stats, int want_stats,
-                                      int *violation, void *stream) {
-    MLB_REQUIRE(h_desc && Ex && Ey && Hx && Hy && power_block_sums && violation, "mlb_nearfield_assemble: NULL pointer");
+static int nearfield_launch(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld, int out_is_double,
+                            double *power_block_sums, long long *stats, int want_stats, int *violation, int *tie_count,
+                            int *tie_list, int tie_capacity, const int *fix_samples, const int *fix_cells, int n_fix,
+                            void *stream, const char *who) {
+    const bool fix = fix_samples != nullptr;
+    MLB_REQUIRE(h_desc && Ex && Ey && Hx && Hy && (fix || power_block_sums) && violation, "%s: NULL pointer", who);
     const mlb_lens_desc &L = *h_desc;
-    MLB_REQUIRE(L.nx > 0 && L.ny > 0 && ld >= L.ny, "mlb_nearfield_assemble: bad grid (%d,%d,ld=%d)", L.nx, L.ny, ld);
-    MLB_REQUIRE(L.x_pts && L.y_pts, "mlb_nearfield_assemble: NULL sample coordinates");
-    if (int rc = check_desc(L, "mlb_nearfield_assemble")) return rc;
+    MLB_REQUIRE(L.nx > 0 && L.ny > 0 && ld >= L.ny, "%s: bad grid (%d,%d,ld=%d)", who, L.nx, L.ny, ld);
+    MLB_REQUIRE(L.x_pts && L.y_pts, "%s: NULL sample coordinates", who);
+    if (int rc = check_desc(L, who)) return rc;
     if (L.n_cells > 0) {
         if (int rc = check_pack(L.hex, "hexgridset")) return rc;
         MLB_REQUIRE(L.cell_x && L.cell_y && L.cell_which && L.cell_orig && L.bin_start && L.nbx > 0 && L.nby > 0 &&
                         L.bin_size > 0,
-                    "mlb_nearfield_assemble: bad centre-cell bin grid");
+                    "%s: bad centre-cell bin grid", who);
     }
-    MLB_REQUIRE(L.plane_wave || L.source_z < 0, "mlb_nearfield_assemble: source_z must be negative (nearfield.py:84)");
+    MLB_REQUIRE(L.plane_wave || L.source_z < 0, "%s: source_z must be negative (nearfield.py:84)", who);
     MLB_REQUIRE(L.source_pol >= 0 && L.source_pol <= 2 && !(L.plane_wave && L.source_pol == 2),
-                "mlb_nearfield_assemble: bad source polarisation (nearfield.py:85, :224)");
-    MLB_REQUIRE(!want_stats || stats, "mlb_nearfield_assemble: want_stats needs a stats buffer");
-    MLB_REQUIRE(L.ny <= (1 << 24) && L.nx <= 65535, "mlb_nearfield_assemble: grid too large");
+                "%s: bad source polarisation (nearfield.py:85, :224)", who);
+    MLB_REQUIRE(!want_stats || stats, "%s: want_stats needs a stats buffer", who);
+    MLB_REQUIRE(L.ny <= (1 << 24) && L.nx <= 65535 && (long long)L.nx * L.ny < (1LL << 31), "%s: grid too large", who);
+    MLB_REQUIRE(!tie_count || (tie_list && tie_capacity > 0), "%s: tie_count needs a tie_list", who);
+    MLB_REQUIRE(!fix || (fix_cells && n_fix > 0 && L.n_cells > 0), "%s: bad fix-up list", who);
     mlb::NfOut out;
     out.F[0] = Ex; out.F[1] = Ey; out.F[2] = Hx; out.F[3] = Hy;
     out.power_warp_sums = power_block_sums; out.stats = stats; out.violation = violation;
     out.ld = ld; out.out_is_double = out_is_double; out.lg_wy = g_nf_lg_wy;
+    out.tie_count = tie_count; out.tie_list = tie_list; out.tie_capacity = tie_capacity;
+    out.fix_samples = fix_samples; out.fix_cells = fix_cells; out.n_fix = n_fix;
     // launch-uniform scalars in IEEE float64, the expressions of nearfield.py:213 / :262 / :287
     const double PI = 3.14159265358979323846;
     mlb::NfUniform U;
@@ -655,8 +720,14 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
     U.lut_scale = L.n_lut / L.lut_r_max;
     U.ng2 = (float)((U.kg / U.kvac) * (U.kg / U.kvac));
     U.cf = (float)(L.Z0 * U.inv_kg_n * U.kvac);
-    const dim3 grid = nf_grid(L.nx, L.ny);
     const cudaStream_t st = (cudaStream_t)stream;
+    if (fix) {
+        const dim3 grid((n_fix + mlb::NF_THREADS - 1) / mlb::NF_THREADS);
+        if (out_is_double) mlb::nearfield_kernel<false, false, 1, true><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        else mlb::nearfield_kernel<false, true, 1, true><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
+        return mlb::check_launch(who);
+    }
+    const dim3 grid = nf_grid(L.nx, L.ny);
     if (want_stats) {
         if (out_is_double) mlb::nearfield_kernel<true, false, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
         else mlb::nearfield_kernel<true, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
@@ -667,7 +738,30 @@ extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, voi
         else if (g_nf_minblocks == 8) mlb::nearfield_kernel<false, true, 8><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
         else mlb::nearfield_kernel<false, true, 1><<<grid, mlb::NF_THREADS, 0, st>>>(L, U, out);
     }
-    return mlb::check_launch("mlb_nearfield_assemble");
+    return mlb::check_launch(who);
+}
+
+extern "C" int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
+                                      int out_is_double, double *power_block_sums, long long *stats, int want_stats,
+                                      int *violation, void *stream) {
+    return nearfield_launch(h_desc, Ex, Ey, Hx, Hy, ld, out_is_double, power_block_sums, stats, want_stats, violation,
+                            nullptr, nullptr, 0, nullptr, nullptr, 0, stream, "mlb_nearfield_assemble");
+}
+
+extern "C" int mlb_nearfield_assemble_ties(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
+                                           int out_is_double, double *power_block_sums, long long *stats, int want_stats,
+                                           int *violation, int *tie_count, int *tie_list, int tie_capacity, void *stream) {
+    MLB_REQUIRE(tie_count && tie_list && tie_capacity > 0, "mlb_nearfield_assemble_ties: tie buffers missing");
+    return nearfield_launch(h_desc, Ex, Ey, Hx, Hy, ld, out_is_double, power_block_sums, stats, want_stats, violation,
+                            tie_count, tie_list, tie_capacity, nullptr, nullptr, 0, stream, "mlb_nearfield_assemble_ties");
+}
+
+extern "C" int mlb_nearfield_fixup(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
+                                   int out_is_double, const int *fix_samples, const int *fix_cells, int n_fix,
+                                   int *violation, void *stream) {
+    MLB_REQUIRE(fix_samples && fix_cells && n_fix > 0, "mlb_nearfield_fixup: empty fix-up list");
+    return nearfield_launch(h_desc, Ex, Ey, Hx, Hy, ld, out_is_double, nullptr, nullptr, 0, violation, nullptr, nullptr, 0,
+                            fix_samples, fix_cells, n_fix, stream, "mlb_nearfield_fixup");
 }
 
 extern "C" int mlb_table_eval(const double *axes, int n0, int n1, int n2, const double *values, const double *pts,

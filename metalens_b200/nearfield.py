@@ -29,7 +29,9 @@ class _PackC(C.Structure):
     _fields_ = [("axes", C.c_void_p), ("values", C.c_void_p), ("values_f32", C.c_void_p), ("orders", C.c_void_p),
                 ("order_map", C.c_void_p),
                 ("n_ux", C.c_int), ("n_uy", C.c_int), ("n_g", C.c_int), ("n_orders", C.c_int),
-                ("bounds", C.c_double * 6), ("stats_slot", C.c_int), ("order_radius", C.c_int)]
+                ("bounds", C.c_double * 6), ("stats_slot", C.c_int), ("order_radius", C.c_int),
+                ("uniform01", C.c_int), ("_pad", C.c_int),
+                ("u0_first", C.c_double), ("u0_inv_step", C.c_double), ("u1_first", C.c_double), ("u1_inv_step", C.c_double)]
 
 
 class _LensC(C.Structure):
@@ -148,7 +150,9 @@ class NearfieldPlan:
             cx, cy = cells[:, 0], cells[:, 1]
             span_x, span_y = cx.max() - cx.min(), cy.max() - cy.min()
             area = max(span_x * span_y, 1e-300)
-            b = 2.0 * math.sqrt(area / self.n_cells) if area > 1e-300 else 1.0
+            # about one cell per bin: with the exact reach test of the kernel a sample visits its own bin and the ring
+            # of eight around it (~9 cells) instead of 9 bins of ~4 cells
+            b = math.sqrt(area / self.n_cells) if area > 1e-300 else 1.0
             b = max(b, 1e-12 * max(span_x, span_y, 1e-30))
             self.bin_x0, self.bin_y0, self.bin_size = float(cx.min()), float(cy.min()), float(b)
             self.nbx = int(math.floor(span_x / b)) + 1
@@ -157,6 +161,9 @@ class NearfieldPlan:
             by = np.minimum(np.floor((cy - self.bin_y0) / b).astype(np.int64), self.nby - 1)
             key = by * self.nbx + bx
             order = np.argsort(key, kind="stable")
+            self._cells_host = cells[:, 0:2].copy()              # for the reference's tie choice (resolve_ties)
+            self._sorted_pos = np.empty(self.n_cells, dtype=np.int64)
+            self._sorted_pos[order] = np.arange(self.n_cells)
             counts = np.bincount(key, minlength=self.nbx * self.nby)
             self._keep.update(
                 cell_x=up(cx[order], np.float64), cell_y=up(cy[order], np.float64),
@@ -187,6 +194,9 @@ class NearfieldPlan:
         for k in range(6):
             s.bounds[k] = pack.bounds[k]
         s.stats_slot = pack.stats_slot
+        s.uniform01 = 1 if pack.uniform01 else 0
+        s.u0_first, s.u1_first = pack.u_first
+        s.u0_inv_step, s.u1_inv_step = pack.u_inv_step
         return s
 
     def _desc(self, d_x, d_y, source_x, source_y, source_z, source_pol, dipole_moment):
@@ -235,13 +245,17 @@ class NearfieldPlan:
         return hit
 
     def run(self, source_x, source_y, source_z, source_pol, x_pts, y_pts, dipole_moment=1e-30,
-            out_dtype=torch.complex64, verbose=False, out=None, dxdy=None, check=True):
+            out_dtype=torch.complex64, verbose=False, out=None, dxdy=None, check=True, ties="fast"):
         """Launch the fused assembly kernel.  Returns (fields (4, nx, ld) device tensor -- logical
         view [..., :ny] --, power device scalar float64).  Raises the reference's ValueErrors.
         x_pts / y_pts need not be uniform here (a multi-GPU rank passes ITS rows of the grid, slab.py); then
         `dxdy` gives the area element of the incident-power sum (:476-477) explicitly.
         check=False does not read the bounds-violation flag back (no host synchronisation: the launch stays
-        asynchronous, e.g. inside a pipelined step); call check_violation() later -- it raises the same ValueError."""
+        asynchronous, e.g. inside a pipelined step); call check_violation() later -- it raises the same ValueError.
+        ties: a centre sample EXACTLY equidistant from two hex cells (they sit on symmetry lines of symmetric grids) gets
+        the highest cell row with "fast"; with "reference" those samples -- the kernel reports them -- are re-assembled
+        with the cell the reference's own scipy cKDTree.query call returns (nearfield.py:363-364: whichever its
+        traversal meets first), which makes the result equal to the reference's there as well.  Synchronises."""
         dev = self.device
         d_x, d_y = self._coords(x_pts), self._coords(y_pts)
         nx, ny = d_x.numel(), d_y.numel()
@@ -272,18 +286,33 @@ class NearfieldPlan:
                 init[:, 7] = 0
                 stats = torch.from_numpy(init).to(dev)
                 sptr = stats.data_ptr()
+            if tie_buf is not None:
+                tie_buf[0].zero_()
+                rc = self.lib.mlb_nearfield_assemble_ties(
+                    C.byref(L), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), ld,
+                    1 if out.dtype == torch.complex128 else 0, block_sums.data_ptr(), sptr, 1 if want_stats else 0,
+                    violation.data_ptr(), tie_buf[0].data_ptr(), tie_buf[1].data_ptr(), tie_buf[1].numel(), _stream_ptr())
+                _lib.check(rc, "mlb_nearfield_assemble_ties")
+                return
             rc = self.lib.mlb_nearfield_assemble(C.byref(L), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                                  out[3].data_ptr(), ld, 1 if out.dtype == torch.complex128 else 0,
                                                  block_sums.data_ptr(), sptr, 1 if want_stats else 0,
                                                  violation.data_ptr(), _stream_ptr())
             _lib.check(rc, "mlb_nearfield_assemble")
 
+        assert ties in ("fast", "reference")
+        tie_buf = None
+        if ties == "reference" and self.n_cells:
+            cap = 1 << 20
+            tie_buf = (torch.zeros(1, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev))
         launch(bool(verbose))
         if check and (int(violation.item()) != 0 or verbose):
             if stats is None:
                 violation.zero_()
                 launch(True)                 # slow path: collect min/max for the reference's messages
             self._report(stats.cpu().numpy(), verbose)
+        if tie_buf is not None:
+            self._resolve_ties(L, out, ld, tie_buf, x_pts, y_pts, violation)
         if dxdy is None:
             dx = float(x_pts[1] - x_pts[0]) if nx > 1 else float('nan')
             dy = float(y_pts[1] - y_pts[0]) if ny > 1 else float('nan')
@@ -291,6 +320,29 @@ class NearfieldPlan:
         rc = self.lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, dxdy, power.data_ptr(), _stream_ptr())      # :476-477
         _lib.check(rc, "mlb_sum_f64")
         return out, power
+
+    def _resolve_ties(self, L, out, ld, tie_buf, x_pts, y_pts, violation):
+        """Re-assemble the exactly tied centre samples with the reference's own nearest-cell choice: the same
+        ``cKDTree(lens_center_summary[:, 0:2]).query(points)`` call as nearfield.py:363-364 on just those points."""
+        n = int(tie_buf[0].item())
+        self.last_tie_count = n
+        if n == 0:
+            return
+        if n > tie_buf[1].numel():
+            raise _lib.MetalensB200Error("more exact nearest-cell ties (%d) than the report list holds" % n)
+        from scipy.spatial import cKDTree            # the reference's own dependency (nearfield.py:17)
+        if getattr(self, "_tree", None) is None:
+            self._tree = cKDTree(self._cells_host)
+        lin = np.sort(tie_buf[1][:n].cpu().numpy().astype(np.int64))
+        ny = len(y_pts)
+        pts = np.stack((np.asarray(x_pts, dtype=np.float64)[lin // ny], np.asarray(y_pts, dtype=np.float64)[lin % ny]), axis=1)
+        winner = self._tree.query(pts)[1]                                      # original row numbers
+        d_lin = torch.from_numpy(lin.astype(np.int32)).to(self.device)
+        d_cell = torch.from_numpy(self._sorted_pos[winner].astype(np.int32)).to(self.device)
+        rc = self.lib.mlb_nearfield_fixup(C.byref(L), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                          out[3].data_ptr(), ld, 1 if out.dtype == torch.complex128 else 0,
+                                          d_lin.data_ptr(), d_cell.data_ptr(), n, violation.data_ptr(), _stream_ptr())
+        _lib.check(rc, "mlb_nearfield_fixup")
 
     def check_violation(self):
         """Deferred bounds check of run(check=False) calls: raises the reference's ValueError (:294-305, :412-419)
@@ -389,7 +441,7 @@ def build_nearfield(source_x, source_y, source_z, source_pol, wavelength,
     if source_z == -inf:
         assert source_pol != 'z'                                               # :224
     out, power = plan.run(source_x, source_y, source_z, source_pol, x_pts, y_pts, dipole_moment=dipole_moment,
-                          out_dtype=torch.complex128, verbose=verbose)
+                          out_dtype=torch.complex128, verbose=verbose, ties="reference")
     ny = len(y_pts)
     host = out[:, :, :ny].cpu().numpy()
     return host[0], host[1], host[2], host[3], x_pts, y_pts, float(power.item()), plan.n_glass

@@ -104,6 +104,14 @@ class TablePack:
         self.values = np.ascontiguousarray(np.stack(blocks, axis=0))   # [order][iu][iv][ig][slot]
         self.bounds = tuple(float(b) for b in owner.interpolator_bounds)
         self.axes = np.concatenate(grid)
+        # uniformly spaced ux / uy axes (what characterize() produces): the kernel may locate cells arithmetically
+        def uniform(a):
+            d = np.diff(a)
+            return bool(a.size >= 2 and np.all(np.abs(d - d[0]) <= 1e-12 * abs(d[0])))
+        self.uniform01 = uniform(grid[0]) and uniform(grid[1])
+        self.u_first = (float(grid[0][0]), float(grid[1][0]))
+        self.u_inv_step = ((grid[0].size - 1) / float(grid[0][-1] - grid[0][0]),
+                           (grid[1].size - 1) / float(grid[1][-1] - grid[1][0]))
         self.order_array = np.asarray(self.orders, dtype=np.int32).reshape(-1, 2)
         # dense (ox,oy) -> order index map so the kernel can visit just the orders that may propagate
         self.order_radius = int(np.abs(self.order_array).max()) if len(self.orders) else 0

@@ -114,3 +114,6 @@ def make_library(grating_mod, lens_center_mod, spec=SMALL_LENS, wavelength_nm=58
     hgs = make_hexgridset(lens_center_mod, grating_mod, wavelength_nm=wavelength_nm, n_glass=n_glass)
     hgs.build_interpolators()
     return collections, hgs
+
+# SURVEY section 8 probe-sized lens: default grid 675 x 675 (= good_fft_number), ~20 rings, ~1.2e5 hex cells
+MID_LENS = dict(bands=[(15.0, 25.0, 1000 * nm, 0.3)], source_distance=216.5 * um, radius=88.9 * um)
