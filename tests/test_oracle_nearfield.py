@@ -66,6 +66,24 @@ def test_oracle_matches_reference(name, golden_dir):
     assert res[7] == g["n_glass"]
 
 
+@pytest.mark.parametrize("name", ["mid_z_offaxis", "mid_y_onaxis"])
+def test_oracle_matches_mid_reference(name, golden_dir):
+    """The probe-sized lens of SURVEY section 8 (17 rings, 1.26e5 hex cells, off-axis z-dipole / odd on-axis grid with 148
+    exact nearest-cell ties): the oracle against the stored subset of the UNMODIFIED reference's output."""
+    g = np.load(os.path.join(golden_dir, "nearfield_%s.npz" % name))
+    collections, hgs = synth_lens.make_library(grating, lens_center, synth_lens.MID_LENS)
+    sx, sy, sz = g["source"]
+    explicit = g["shape"][0] != 720
+    res = no.build_nearfield(sx, sy, sz, str(g["pol"]), float(g["wavelength"]), periphery_from(g, collections),
+                             g["center"], hgs, x_pts=g["x_pts"] if explicit else None,
+                             y_pts=g["y_pts"] if explicit else None)
+    idx = g["index"]
+    for k, key in enumerate(("Ex", "Ey", "Hx", "Hy")):
+        scale = float(g["scale_E"] if k < 2 else g["scale_H"])
+        assert np.abs(res[k].ravel()[idx] - g[key]).max() / scale < 1e-11, key
+    assert abs(res[6] - float(g["power"])) <= 1e-12 * abs(float(g["power"]))
+
+
 def test_oracle_big_equals_single(golden_dir):
     g = np.load(os.path.join(golden_dir, "nearfield_small_x_ragged.npz"))
     collections, hgs = library(synth_lens.SMALL_LENS)
