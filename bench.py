@@ -440,9 +440,9 @@ def bench_cfg4(torch, dist, rank, world, steps, warmup, M=8192, stride=4, check=
                total_P=float(total), incident_power=float(p_in), gpu_launches_per_step=launches / steps,
                scaling="strong", exchange="peer stores over NVLink (mlb_fft_rows_scatter, mlb_peer_barrier, "
                                           "mlb_peer_allgather)" if world > 1 else "single GPU",
-               note="total_P is the Riemann sum of P over every 4th FFT bin: the far field of a coherent lens is not "
-                    "band-limited enough for that quadrature to equal the radiated power (tests/test_farfield_gpu.py::"
-                    "test_strided_total_is_a_subsampled_sum)")
+               note="total_P is the Riemann sum of P over every 4th FFT bin: a collimator radiates into a spot about one "
+                    "bin wide, which that coarse quadrature over-weights (tests/test_full_configs_gpu.py::"
+                    "test_strided_total_is_a_subsampled_sum); P itself is exact at every sampled bin")
     if clocks is not None:
         res["clocks"] = clocks
     if check and rank == 0:

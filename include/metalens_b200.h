@@ -324,13 +324,17 @@ int mlb_nearfield_tune(int min_blocks);
 int mlb_nearfield_assemble(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
                            int out_is_double, double *power_block_sums, long long *stats, int want_stats,
                            int *violation, void *stream);
-/* Exact nearest-cell ties (nearfield.py:363-364).  A centre sample exactly equidistant from two hex cells gets the
- * highest original row here, while the reference's cKDTree returns whichever cell its traversal meets first.
+/* Samples whose INDEX choice hinges on the last bit of a library call in the reference:
+ *  (1) exact nearest-cell ties (nearfield.py:363-364): a centre sample exactly equidistant from two hex cells gets the
+ *      highest original row here, while the reference's cKDTree returns whichever cell its traversal meets first;
+ *  (2) periphery samples within 1e-9 of the boundary between two grating copies: round(phi / angle_per_grating)
+ *      (nearfield.py:167-169) flips with one ulp of arctan2.
  * mlb_nearfield_assemble_ties is mlb_nearfield_assemble that also reports those samples: tie_count[0] (zero it first)
  * counts them and tie_list receives the first `tie_capacity` linear sample indices i*ny + j.  A binding that wants the
- * reference's choice resolves them on the host with the same cKDTree call and re-assembles just those samples with
- * mlb_nearfield_fixup: sample fix_samples[t] takes the cell with SORTED position fix_cells[t] (index into
- * cell_x / cell_y); the power sums are not touched. */
+ * reference's choice computes it on the host with the reference's own calls (cKDTree.query; numpy arctan2 / round) and
+ * re-assembles just those samples with mlb_nearfield_fixup: sample fix_samples[t] takes fix_cells[t] = the SORTED
+ * position of its cell (index into cell_x / cell_y) if it lies in the centre region, = the grating-copy index
+ * round(phi / angle_per_grating) if it lies on a ring; the power sums are not touched. */
 int mlb_nearfield_assemble_ties(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld,
                                 int out_is_double, double *power_block_sums, long long *stats, int want_stats,
                                 int *violation, int *tie_count, int *tie_list, int tie_capacity, void *stream);

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             // grating copy: rot = round(phi / angle_per_grating) * angle_per_grating (:167, half to even)
             double kd;
             bool have_k = false;
-            if (FAST) {
+            if (FAST && !FIX) {
                 // fp32 screen: |error of phi_f / apg| < guard (atan2f <= 2 ulp, float inputs), so unless the
                 // quotient is within `guard` of a half-integer the rounded index equals the float64 one
                 const float yf = (float)y;
@@ -423,7 +423,18 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                 const float kr = rintf(kf);
                 if (fabsf(kf - kr) < 0.5f - rf.guard && fabsf(yf) > 1e-30f) { kd = (double)kr; have_k = true; }
             }
-            if (!have_k) kd = rint(atan2(y, x) / apg);
+            if (FIX) {
+                kd = (double)forced_cell;               // the copy index the reference's own arithmetic gives (fix-up launch)
+            } else if (!have_k) {
+                const double q = atan2(y, x) / apg;
+                kd = rint(q);
+                // a sample (numerically) ON the boundary between two grating copies: round() hinges on the last bit of
+                // atan2, which differs between math libraries -- reported like an exact nearest-cell tie
+                if (out.tie_count && fabs(fabs(q - kd) - 0.5) < 1e-9) {
+                    const int slot = atomicAdd(out.tie_count, 1);
+                    if (slot < out.tie_capacity) out.tie_list[slot] = i * L.ny + j;
+                }
+            }
             const double rot = kd * apg;
             double s, c;
             sincos(rot, &s, &c);

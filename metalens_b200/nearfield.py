@@ -302,7 +302,7 @@ class NearfieldPlan:
 
         assert ties in ("fast", "reference")
         tie_buf = None
-        if ties == "reference" and self.n_cells:
+        if ties == "reference":
             cap = 1 << 20
             tie_buf = (torch.zeros(1, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int32, device=dev))
         launch(bool(verbose))
@@ -322,26 +322,42 @@ class NearfieldPlan:
         return out, power
 
     def _resolve_ties(self, L, out, ld, tie_buf, x_pts, y_pts, violation):
-        """Re-assemble the exactly tied centre samples with the reference's own nearest-cell choice: the same
-        ``cKDTree(lens_center_summary[:, 0:2]).query(points)`` call as nearfield.py:363-364 on just those points."""
+        """Re-assemble the samples whose index choice hinges on the last bit of a library call with the reference's own
+        choice: centre samples exactly equidistant from two cells through the same
+        ``cKDTree(lens_center_summary[:, 0:2]).query(points)`` call as nearfield.py:363-364, periphery samples on the
+        boundary between two grating copies through numpy's ``round(arctan2(y, x) / angle_per_grating)`` (:119, :167-169)."""
         n = int(tie_buf[0].item())
         self.last_tie_count = n
         if n == 0:
             return
         if n > tie_buf[1].numel():
-            raise _lib.MetalensB200Error("more exact nearest-cell ties (%d) than the report list holds" % n)
-        from scipy.spatial import cKDTree            # the reference's own dependency (nearfield.py:17)
-        if getattr(self, "_tree", None) is None:
-            self._tree = cKDTree(self._cells_host)
+            raise _lib.MetalensB200Error("more index ties (%d) than the report list holds" % n)
         lin = np.sort(tie_buf[1][:n].cpu().numpy().astype(np.int64))
         ny = len(y_pts)
-        pts = np.stack((np.asarray(x_pts, dtype=np.float64)[lin // ny], np.asarray(y_pts, dtype=np.float64)[lin % ny]), axis=1)
-        winner = self._tree.query(pts)[1]                                      # original row numbers
+        px = np.asarray(x_pts, dtype=np.float64)[lin // ny]
+        py = np.asarray(y_pts, dtype=np.float64)[lin % ny]
+        k = self._keep
+        bounds = k['ring_boundary'].cpu().numpy()
+        ring = np.searchsorted(bounds, np.sqrt(px ** 2 + py ** 2)) - 1                           # :118, :125-126
+        forced = np.zeros(n, dtype=np.int64)
+        in_center = ring == -1
+        self.last_tie_classes = (int(in_center.sum()), int((~in_center).sum()))
+        if in_center.any():
+            from scipy.spatial import cKDTree            # the reference's own dependency (nearfield.py:17)
+            if getattr(self, "_tree", None) is None:
+                self._tree = cKDTree(self._cells_host)
+            winner = self._tree.query(np.stack((px[in_center], py[in_center]), axis=1))[1]      # original row numbers
+            forced[in_center] = self._sorted_pos[winner]
+        on_ring = ~in_center
+        if on_ring.any():
+            num = k['num_around'].cpu().numpy()[np.clip(ring[on_ring], 0, self.n_rings - 1)]
+            apg = 2 * np.pi / num                                                                 # :161
+            forced[on_ring] = np.round(np.arctan2(py[on_ring], px[on_ring]) / apg).astype(np.int64)   # :119, :167
         d_lin = torch.from_numpy(lin.astype(np.int32)).to(self.device)
-        d_cell = torch.from_numpy(self._sorted_pos[winner].astype(np.int32)).to(self.device)
+        d_forced = torch.from_numpy(forced.astype(np.int32)).to(self.device)
         rc = self.lib.mlb_nearfield_fixup(C.byref(L), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
                                           out[3].data_ptr(), ld, 1 if out.dtype == torch.complex128 else 0,
-                                          d_lin.data_ptr(), d_cell.data_ptr(), n, violation.data_ptr(), _stream_ptr())
+                                          d_lin.data_ptr(), d_forced.data_ptr(), n, violation.data_ptr(), _stream_ptr())
         _lib.check(rc, "mlb_nearfield_fixup")
 
     def check_violation(self):

@@ -124,9 +124,7 @@ class SlabFarfield:
         self._pw_mine, self._k2 = _lib.ptr_array(self._w_ptrs[self.rank])
 
     # ------------------------------------------------------------------
-    def run(self, fields, wait=True):
-        """fields: 4 CUDA complex64 tensors (len(x_rows), My) sharing one even row pitch.  Launches the five steps
-        on the current stream.  wait=False leaves out the final mlb_peer_wait (call finish() before reading P)."""
+    def _rows(self, fields):
         lib = self.lib
         n_loc = self.x_rows.size
         for f in fields:
@@ -135,19 +133,37 @@ class SlabFarfield:
         ld = fields[0].stride(0)
         assert all(f.stride(0) == ld for f in fields)
         pin, keep = _lib.ptr_array(list(fields))
-        col0 = self.rank * self.cols_per_rank
         _lib.check(lib.mlb_fft_rows_scatter(pin, ld, self._pw_all, self.ldw, self.rows_per_rank, self.K2, self.sx, self.sy,
                                             self.tw2.data_ptr(), self.roll_c, self.out_roll_rows, self.out_row0,
                                             self.K1, self.world, 4, _stream_ptr()), "mlb_fft_rows_scatter")
-        self.chan.barrier()
+
+    def _cols(self):
+        col0 = self.rank * self.cols_per_rank
         bs0 = self.rank * self.nb_local
-        _lib.check(lib.mlb_fft_cols_power(self._pw_mine, self.ldw, self.K1, self.cols_per_rank, self.tw1.data_ptr(),
-                                          self.out_roll_cols, self.d_ux.data_ptr(), self.d_uy.data_ptr() + 8 * col0,
-                                          self.dxp * self.dyp, self.wavelength, self.n_glass, Z0,
-                                          self.P.data_ptr() + 4 * col0, self.K2, 0,
-                                          self.block_sums.data_ptr() + 8 * bs0, None, 0, _stream_ptr()),
+        _lib.check(self.lib.mlb_fft_cols_power(self._pw_mine, self.ldw, self.K1, self.cols_per_rank, self.tw1.data_ptr(),
+                                               self.out_roll_cols, self.d_ux.data_ptr(), self.d_uy.data_ptr() + 8 * col0,
+                                               self.dxp * self.dyp, self.wavelength, self.n_glass, Z0,
+                                               self.P.data_ptr() + 4 * col0, self.K2, 0,
+                                               self.block_sums.data_ptr() + 8 * bs0, None, 0, _stream_ptr()),
                    "mlb_fft_cols_power")
+
+    def warm(self, fields):
+        """Launch the compute kernels once without any exchange (loads them: CUDA loads kernels lazily, and a first
+        launch may have to wait for running kernels -- fatal for virtual ranks whose kernels wait for each other)."""
+        self._rows(fields)
+        self._cols()
+        self._sum()
+        torch.cuda.current_stream().synchronize()
+
+    def run(self, fields, wait=True):
+        """fields: 4 CUDA complex64 tensors (len(x_rows), My) sharing one even row pitch.  Launches the five steps
+        on the current stream.  wait=False leaves out the final mlb_peer_wait (call finish() before reading P)."""
+        self._rows(fields)
+        self.chan.barrier()
+        self._cols()
         if self.world > 1:
+            col0 = self.rank * self.cols_per_rank
+            bs0 = self.rank * self.nb_local
             self.chan.allgather(self.P.data_ptr() + 4 * col0, 4 * self.K2, self.K1, 4 * self.cols_per_rank,
                                 self._p_ptrs, 4 * self.K2, 4 * col0,
                                 aux=(self.block_sums.data_ptr() + 8 * bs0, self._bs_ptrs, bs0, self.nb_local),

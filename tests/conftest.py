@@ -11,9 +11,8 @@ for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
 # the virtual-rank tests (test_slab_gpu.py) run up to 8 streams whose kernels wait for each other: give every stream
 # its own hardware queue (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# ... and load every kernel at start-up: with lazy loading the first launch of a kernel can block the host until running
-# kernels finish, which deadlocks virtual ranks whose kernels wait for launches the host has not issued yet
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# (CUDA loads kernels lazily and a first launch can block the host until running kernels finish: the virtual-rank tests
+# launch every kernel once -- SlabFarfield.warm() -- before ranks start waiting for each other)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

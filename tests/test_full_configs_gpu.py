@@ -61,21 +61,25 @@ def test_full_map_of_every_item(name):
 
 def test_strided_total_is_a_subsampled_sum():
     """total_P on an every-s-th-bin grid is the Riemann sum of P over those bins with the coarser cell s*du (what
-    nearfield_farfield.py:74 does on its own grid).  It equals the stride-1 total when the s x s aliased copies of the
-    aperture are uncorrelated (random aperture: ~1) and exceeds it for a coherent lens, whose far field is not
-    band-limited enough for the coarse quadrature (the 1.37 of the 8192^2 lens in profiles/): sum_q |G^(q)|^2 =
-    K^2 sum_p |G(p)|^2 with G the FOLDED aperture, cross terms between the copies included."""
+    nearfield_farfield.py:74 does on its own grid).  It reproduces the stride-1 total when the far field is smooth on the
+    scale of s bins (random aperture, a converging lens wave: ~1).  A COLLIMATED aperture -- what the design_collimator
+    lens of cfg4 produces -- radiates into a diffraction-limited spot about one FFT bin wide that sits on a sampled bin:
+    the coarse quadrature weights it with a cell s^2 times too large (the total_P / P_in = 1.37 of the 8192^2 lens at
+    stride 4 against 0.91 at stride 1 in profiles/).  P itself is exact at every sampled bin in all cases."""
     from metalens_b200.farfield import FarfieldPlan
     M, s = 1024, 4
     wl, ng = 532e-9, apertures.N_GLASS[532]
     ratios = {}
-    for kind in ("random", "lens"):
+    for kind in ("random", "converging", "collimated"):
         if kind == "random":
             Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(M, 3, wl)
-        else:
+        elif kind == "converging":
             Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 3, wl, ng, na=0.9, noise=0.0)
+        else:
+            Ex, Ey, Hx, Hy, x, y = apertures.disc(M, wl, ng, radius_samples=400)
+            Ex, Ey, Hx, Hy = (a.astype(np.complex64) for a in (Ex, Ey, Hx, Hy))
         d = float(x[1] - x[0])
-        dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+        dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
         full = FarfieldPlan((M, M), d, d, wl, ng, stride=1)
         P1, t1 = full.run(dev)
         P1 = P1.cpu().numpy().astype(np.float64)
@@ -86,8 +90,8 @@ def test_strided_total_is_a_subsampled_sum():
         riemann = coarse[np.isfinite(coarse)].sum() * sub.dux * sub.duy
         assert abs(ts.item() - riemann) <= 2e-5 * abs(riemann)
         ratios[kind] = ts.item() / t1.item()
-    assert abs(ratios["random"] - 1.0) < 0.05
-    assert ratios["lens"] > 1.05
+    assert abs(ratios["random"] - 1.0) < 0.05 and abs(ratios["converging"] - 1.0) < 0.05
+    assert ratios["collimated"] > 1.5
 
 
 # ----------------------------------------------------------------------------- cfg4
@@ -146,17 +150,19 @@ def test_cfg4_full_size_8192():
     d = float(x[1] - x[0])
     nf = NearfieldPlan(wl, periph, center, hgs)
     full = torch.zeros((4, M, M), dtype=torch.complex64, device="cuda")
-    _, p_in = nf.run(0.0, 0.0, -f, "x", x, x, out=full, ties="reference")
-    assert nf.last_tie_count == 0          # even sample count: no sample on the symmetry lines of the hex lattice
-    # hot path B on 48 random aperture rows (all 8192 columns each) against the oracle
+    _, p_in = nf.run(0.0, 0.0, -f, "x", x, x, out=full)
+    # hot path B on 6 random blocks of 8 aperture rows (all 8192 columns each: 3.9e5 samples) against the oracle
     rng = np.random.default_rng(4)
-    rows = np.sort(rng.choice(M, size=48, replace=False))
-    ref = no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center, hgs, x_pts=x[rows], y_pts=x)
-    got = full[:, torch.from_numpy(rows).cuda(), :].cpu().numpy()
-    scale_e = max(np.abs(ref[0]).max(), np.abs(ref[1]).max())
-    scale_h = max(np.abs(ref[2]).max(), np.abs(ref[3]).max())
-    for k in range(4):
-        assert np.abs(got[k] - ref[k]).max() / (scale_e if k < 2 else scale_h) < 3e-6, k
+    for r0 in np.sort(rng.choice(M - 8, size=6, replace=False)):
+        ref = no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center, hgs, x_pts=x[r0:r0 + 8], y_pts=x)
+        blk, _p = nf.run(0.0, 0.0, -f, "x", x[r0:r0 + 8], x, ties="reference")      # index ties as the reference takes them
+        got = blk.cpu().numpy()
+        same = (blk.view(torch.float32) == full[:, r0:r0 + 8, :].contiguous().view(torch.float32)).all(dim=-1)
+        assert float(same.float().mean()) > 0.999                                  # ... which touches a handful of samples
+        scale_e = max(np.abs(ref[0]).max(), np.abs(ref[1]).max(), 1e-300)
+        scale_h = max(np.abs(ref[2]).max(), np.abs(ref[3]).max(), 1e-300)
+        for k in range(4):
+            assert np.abs(got[k] - ref[k]).max() / (scale_e if k < 2 else scale_h) < 3e-6, (r0, k)
     # hot path A: single-GPU far field (same kernels as the ranks) ...
     lib = _lib.load()
     plan = FarfieldPlan((M, M), d, d, wl, nf.n_glass, stride=s, method="fft", fuse_power="always")
@@ -191,6 +197,8 @@ def test_cfg4_full_size_8192():
         powers.append(float(p))
     assert abs(sum(powers) - float(p_in)) <= 1e-12 * abs(float(p_in))
     del full
+    for r, sl in enumerate(slabs):
+        sl.warm([local[r][i] for i in range(4)])
     torch.cuda.synchronize()
     for r, sl in enumerate(slabs):
         with torch.cuda.stream(streams[r]):

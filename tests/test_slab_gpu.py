@@ -61,6 +61,8 @@ def test_virtual_ranks_equal_single_gpu(M, stride, world):
         local.append([f.index_select(0, idx).contiguous() for f in full])
     covered = np.sort(np.concatenate([s.x_rows for s in slabs]))
     assert np.array_equal(covered, np.arange(M))                       # every aperture row on exactly one rank
+    for r, s in enumerate(slabs):
+        s.warm(local[r])
     torch.cuda.synchronize()
     for rep in range(3):                                               # epochs advance; buffers are reused
         for r, s in enumerate(slabs):
@@ -101,6 +103,8 @@ def test_pushed_allgather_epochs():
     aux = [v.alloc("aux", 8 * 3 * world) for v in views]
     streams = [torch.cuda.Stream() for _ in range(world)]
     late = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    late.normal_()                     # first launches load their kernels: none may happen while ranks wait for each other
+    torch.cuda.synchronize()
     for epoch in range(5):
         srcs = []
         for r in range(world):
