@@ -62,6 +62,7 @@ SIGNATURES = {
     "mlb_nearfield_blocks": (C.c_int, [C.c_int, C.c_int]),
     "mlb_nearfield_tune": (C.c_int, [C.c_int]),
     "mlb_nearfield_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mlb_nearfield_ring_table_floats": (C.c_longlong, [C.c_void_p]),
     "mlb_nearfield_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_nearfield_assemble_ties": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -165,31 +165,29 @@ __device__ __forceinline__ cf cospi_sinpi_unit(float r) {
 }
 __device__ __forceinline__ cf expi_fast(double x) {
     const double t = x * 0.15915494309189535;                 // x / 2 pi
-    const double fr = t - rint(t);                            // [-1/2, 1/2] turns
-    return cospi_sinpi_unit((float)(fr + fr));                // angle = pi * (2 fr)
+    const double fr = t - rint(t);                            // [-1/2, 1/2] turns, exact to ~1e-16 turns
+    // the special-function unit on the reduced angle: |error| <= 2^-21.4 (4e-7) on [-pi, pi], a fifth of the
+    // instructions of the polynomial above and still 8x below the complex64 tolerance of the path
+    const float a = (float)fr * 6.28318530717958647692f;
+    return {__cosf(a), __sinf(a)};
 }
 
-// The interpolation cell of one sample in the float32 copy of a pack: every diffraction order of the sample
-// reads the SAME cell (the interpolation point (ux', uy', period) does not depend on the order, nearfield.py:293),
-// so corner offsets and the 8 trilinear weights are formed once per sample, not once per order.
+// The interpolation cell of one sample in a float32 2-D slice [order][iu][iv][slot] of a pack -- the third table
+// coordinate is fixed per sample: the ring's grating period (slice pre-interpolated per ring by
+// nearfield_ring_tables_kernel) or, in the centre, the integer cell kind (a node of the axis, nearfield.py:411).  Every
+// diffraction order of the sample reads the SAME cell (the interpolation point does not depend on the order, :293), so
+// the corner offsets and the 4 bilinear weights are formed once per sample, not once per order.
 struct CellF {
     int base, sA, sB;         // float4 offsets: first corner, stride of the ux axis, stride of the uy axis
-    float w[8];               // weight of corner (a, b, c) at index 4a + 2b + c
+    float w[4];               // weight of corner (a, b) at index 2a + b
 };
-__device__ __forceinline__ CellF make_cell(const mlb_table_pack &p, const Interp3 &q) {
+__device__ __forceinline__ CellF make_cell(const Interp3 &q, int sA, int sB) {
     CellF cell;
-    cell.sB = p.n_g * 2;
-    cell.sA = p.n_uy * cell.sB;
-    cell.base = q.i0 * cell.sA + q.i1 * cell.sB + q.i2 * 2;
-    const float t0 = (float)q.t0, t1 = (float)q.t1, t2 = (float)q.t2;
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const float wab = (a ? t0 : 1.f - t0) * (b ? t1 : 1.f - t1);
-            cell.w[4 * a + 2 * b] = wab * (1.f - t2);
-            cell.w[4 * a + 2 * b + 1] = wab * t2;
-        }
+    cell.sA = sA; cell.sB = sB;
+    cell.base = q.i0 * sA + q.i1 * sB;
+    const float t0 = (float)q.t0, t1 = (float)q.t1;
+    cell.w[0] = (1.f - t0) * (1.f - t1); cell.w[1] = (1.f - t0) * t1;
+    cell.w[2] = t0 * (1.f - t1);         cell.w[3] = t0 * t1;
     return cell;
 }
 
@@ -210,25 +208,26 @@ __device__ __forceinline__ void order_fast(const float4 *__restrict__ tbl, int p
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const float4 *c0 = v + (a ? cell.sA : 0) + (b ? cell.sB : 0);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const float w = cell.w[4 * a + 2 * b + c];
-                const float4 x0 = __ldg(c0 + 2 * c), x1 = __ldg(c0 + 2 * c + 1);   // slots (0,1) and (2,3)
-                amp[0].re = fmaf(x0.x, w, amp[0].re); amp[0].im = fmaf(x0.y, w, amp[0].im);
-                amp[1].re = fmaf(x0.z, w, amp[1].re); amp[1].im = fmaf(x0.w, w, amp[1].im);
-                amp[2].re = fmaf(x1.x, w, amp[2].re); amp[2].im = fmaf(x1.y, w, amp[2].im);
-                amp[3].re = fmaf(x1.z, w, amp[3].re); amp[3].im = fmaf(x1.w, w, amp[3].im);
-            }
+            const float w = cell.w[2 * a + b];
+            const float4 x0 = __ldg(c0), x1 = __ldg(c0 + 1);                       // slots (0,1) and (2,3)
+            amp[0].re = fmaf(x0.x, w, amp[0].re); amp[0].im = fmaf(x0.y, w, amp[0].im);
+            amp[1].re = fmaf(x0.z, w, amp[1].re); amp[1].im = fmaf(x0.w, w, amp[1].im);
+            amp[2].re = fmaf(x1.x, w, amp[2].re); amp[2].im = fmaf(x1.y, w, amp[2].im);
+            amp[3].re = fmaf(x1.z, w, amp[3].re); amp[3].im = fmaf(x1.w, w, amp[3].im);
         }
     const float nz2 = ng2 - nx * nx - ny * ny;                // > 0: the order propagates in air, n_glass > 1
-    const float rs = rsqrtf(nz2);
-    const float f = cfac * rs;                                // Z0 / (k_g kz n) in units of 1/kvac
-    const cf Sfy = Hw_x * amp[0] + Hw_y * amp[2];
-    const cf Sfx = Hw_x * amp[1] + Hw_y * amp[3];
-    const cf ea = ((Sfy * (nx * ny) + Sfx * (ny * ny + nz2)) * f) * phase;
-    const cf eb = ((Sfy * (-nx * nx - nz2) + Sfx * (-nx * ny)) * f) * phase;
-    Ea = Ea + ea; Eb = Eb + eb;
-    Ha = Ha + Sfy * phase; Hb = Hb + Sfx * phase;
+    const float f = cfac * rsqrtf(nz2);                       // Z0 / (k_g kz n) in units of 1/kvac
+    // P1 = S_fy phase, P2 = S_fx phase; the E terms are real combinations of them:
+    //   E_a += f [ P1 nx ny + P2 (ny^2 + nz^2) ],   E_b += f [ -P1 (nx^2 + nz^2) - P2 nx ny ],   H_a += P1,  H_b += P2
+    const cf Sfy = {fmaf(Hw_x, amp[0].re, Hw_y * amp[2].re), fmaf(Hw_x, amp[0].im, Hw_y * amp[2].im)};
+    const cf Sfx = {fmaf(Hw_x, amp[1].re, Hw_y * amp[3].re), fmaf(Hw_x, amp[1].im, Hw_y * amp[3].im)};
+    const cf P1 = {fmaf(Sfy.re, phase.re, -Sfy.im * phase.im), fmaf(Sfy.re, phase.im, Sfy.im * phase.re)};
+    const cf P2 = {fmaf(Sfx.re, phase.re, -Sfx.im * phase.im), fmaf(Sfx.re, phase.im, Sfx.im * phase.re)};
+    const float cxy = f * (nx * ny), cyy = f * fmaf(ny, ny, nz2), cxx = -f * fmaf(nx, nx, nz2);
+    Ea.re = fmaf(P1.re, cxy, fmaf(P2.re, cyy, Ea.re)); Ea.im = fmaf(P1.im, cxy, fmaf(P2.im, cyy, Ea.im));
+    Eb.re = fmaf(P1.re, cxx, fmaf(P2.re, -cxy, Eb.re)); Eb.im = fmaf(P1.im, cxx, fmaf(P2.im, -cxy, Eb.im));
+    Ha.re += P1.re; Ha.im += P1.im;
+    Hb.re += P2.re; Hb.im += P2.im;
 }
 
 // one diffraction order's contribution in float64 (nearfield.py:306-327 / :420-441), both incident
@@ -288,32 +287,35 @@ template <bool STATS, bool FAST, typename Acc, typename W>
 __device__ __forceinline__ void order_loop(const mlb_table_pack &p, const NfUniform &U, double Z0, double u0, double u1,
                                            double u2, bool check2, bool have_q3, Interp3 q, double X, double Y,
                                            double qx, double qy, float fqx, float fqy, float inv_fqx, float inv_fqy,
-                                           W Hw_x, W Hw_y, const NfOut &out, Acc &Ea, Acc &Eb, Acc &Ha, Acc &Hb) {
+                                           W Hw_x, W Hw_y, const NfOut &out, Acc &Ea, Acc &Eb, Acc &Ha, Acc &Hb,
+                                           const float4 *__restrict__ tbl, int sA, int sB, int per_order2) {
     const float fu0 = (float)u0, fu1 = (float)u1;
     const int R = p.order_radius, Wd = 2 * R + 1;
     const int ox_lo = max(-R, (int)ceilf((-1.001f - fu0) * inv_fqx)), ox_hi = min(R, (int)floorf((1.001f - fu0) * inv_fqx));
     const int oy_lo = max(-R, (int)ceilf((-1.001f - fu1) * inv_fqy)), oy_hi = min(R, (int)floorf((1.001f - fu1) * inv_fqy));
-    (void)fqx; (void)fqy;
     const double k0 = U.kvac * u0, k1 = U.kvac * u1, kv2 = U.kvac * U.kvac;
     bool located = false;
     CellF cell;
-    const float4 *tbl = reinterpret_cast<const float4 *>(p.values_f32);
-    const int per_order2 = p.n_ux * p.n_uy * p.n_g * 2;
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        const double kx = k0 + ox * qx;                                                // :268 / :395
+        const float nxf = fmaf((float)ox, fqx, fu0);
         const int *__restrict__ map_row = p.order_map + (ox + R) * Wd + R;
         for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            // fp32 screen of :279 / :398 (|error| < 2e-6): clearly evanescent orders never reach the float64 test
+            const float nyf = fmaf((float)oy, fqy, fu1);
+            const float s2 = fmaf(nxf, nxf, nyf * nyf);
+            if (s2 > 1.00002f) continue;
             const int o = map_row[oy];
             if (o < 0) continue;                                                       // order not in the tables
+            const double kx = k0 + ox * qx;                                            // :268 / :395
             const double ky = k1 + oy * qy;                                            // :269 / :396
-            if (kx * kx + ky * ky <= kv2) {                                            // :279 / :398
+            if (s2 < 0.99998f || kx * kx + ky * ky <= kv2) {                           // :279 / :398
                 if (STATS) record_stats(p, o, u0, u1, u2, out.stats);
                 if (!located) {
                     located = true;
                     if (out_of_bounds(p, u0, u1, u2, check2)) atomicOr(out.violation, 1);   // :294-305 / :412-419
                     locate2<FAST>(p, u0, u1, q);
-                    if (!have_q3) locate3(p, u2, q);
-                    if constexpr (FAST) cell = make_cell(p, q);
+                    if constexpr (FAST) cell = make_cell(q, sA, sB);
+                    else if (!have_q3) locate3(p, u2, q);
                 }
                 // kz (:287), phase about the grating / cell centre (:291, :408-409), table gathers, accumulation
                 const double phase_arg = kx * X + ky * Y;
@@ -437,7 +439,8 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
             }
             const double rot = kd * apg;
             double s, c;
-            sincos(rot, &s, &c);
+            if (FAST) sincospi(kd * (apg * 0.31830988618379067154), &s, &c);       // rot / pi: no large-argument reduction
+            else sincos(rot, &s, &c);
             const double uxp = ux * c + uy * s, uyp = -ux * s + uy * c;             // :195-196
             const double xp = x * c + y * s - rc, yp = -x * s + y * c;              // :200-201
             const double Hxp_w = dHx * c + dHy * s, Hyp_w = -dHx * s + dHy * c;     // :231-234
@@ -446,9 +449,12 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                 Interp3 q;
                 q.i2 = ra.i2; q.t2 = ra.t2;
                 // weights: H_xp_weight = Hyp, H_yp_weight = Hxp (:246-247)
-                order_loop<STATS, FAST, Acc, W>(L.packs[gc], U, L.Z0, uxp, uyp, ra.gp, true, true, q, xp, yp, ra.qx, ra.qy,
+                // float32 slice of the ring: the tables of its collection interpolated at the ring's grating period
+                const mlb_table_pack &pk = L.packs[gc];
+                const float4 *rt = reinterpret_cast<const float4 *>(L.ring_tables) + (size_t)ring * (L.ring_table_stride >> 2);
+                order_loop<STATS, FAST, Acc, W>(pk, U, L.Z0, uxp, uyp, ra.gp, true, true, q, xp, yp, ra.qx, ra.qy,
                                                 rf.fqx, rf.fqy, rf.inv_fqx, rf.inv_fqy, (W)Hyp_w, (W)Hxp_w, out,
-                                                Exp, Eyp, Hxp, Hyp);
+                                                Exp, Eyp, Hxp, Hyp, rt, pk.n_uy * 2, 2, pk.n_ux * pk.n_uy * 2);
             }
             if (!L.plane_wave) {                                                    // :337-346
                 const double gx = rc * c, gy = rc * s;                              // :170-171
@@ -524,8 +530,12 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nearfield_kernel(const __gri
                 Interp3 q;
                 q.i2 = 0; q.t2 = 0.0;
                 // weights un-rotated: H_x_weight = Hy, H_y_weight = Hx (:375-376)
+                // float32 slice of the cell kind: an exact node of the third axis (:411), so bilinear in (ux, uy)
+                const int node = min(max(L.cell_which[best], 0), L.hex.n_g - 1);
+                const float4 *ht = reinterpret_cast<const float4 *>(L.hex.values_f32) + node * 2;
                 order_loop<STATS, FAST, Acc, W>(L.hex, U, L.Z0, ux, uy, which, false, false, q, x - cx, y - cy, qx, qy, fqx, fqy,
-                                                1.0f / fqx, 1.0f / fqy, (W)dHy, (W)dHx, out, Ex, Ey, Hx, Hy);
+                                                1.0f / fqx, 1.0f / fqy, (W)dHy, (W)dHx, out, Ex, Ey, Hx, Hy,
+                                                ht, L.hex.n_uy * L.hex.n_g * 2, L.hex.n_g * 2, L.hex.n_ux * L.hex.n_uy * L.hex.n_g * 2);
                 if (!L.plane_wave) {                                                // :453-461
                     const double path2 = (cx - L.source_x) * (cx - L.source_x) + (cy - L.source_y) * (cy - L.source_y) +
                                          L.source_z * L.source_z;
@@ -609,6 +619,26 @@ __global__ void nearfield_prepare_kernel(const __grid_constant__ mlb_lens_desc L
     }
 }
 
+// Per-ring float32 slices (mlb_nearfield_prepare): ring r's collection tables interpolated at the ring's grating period,
+// slice[o][iu][iv][slot] = (1 - t2) T[o][iu][iv][i2][slot] + t2 T[o][iu][iv][i2 + 1][slot]  (scipy RGI's linear rule along
+// the third axis, formed in float64, rounded once).  The complex64-output kernel then interpolates bilinearly.
+__global__ void nearfield_ring_tables_kernel(const __grid_constant__ mlb_lens_desc L) {
+    const int ring = blockIdx.y;
+    const RingAux &ra = reinterpret_cast<const RingAux *>(L.ring_aux)[ring];
+    if (ra.gc < 0 || ra.gc >= L.n_packs) return;
+    const mlb_table_pack &p = L.packs[ra.gc];
+    const int n = p.n_orders * p.n_ux * p.n_uy * 4;                  // complex entries of the slice
+    float2 *dst = reinterpret_cast<float2 *>(L.ring_tables + (size_t)ring * L.ring_table_stride);
+    const double2 *src = reinterpret_cast<const double2 *>(p.values);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int slot = e & 3, cellidx = e >> 2;                    // cellidx = (o * n_ux + iu) * n_uy + iv
+        const double2 a = src[((size_t)cellidx * p.n_g + ra.i2) * 4 + slot];
+        const double2 b = src[((size_t)cellidx * p.n_g + ra.i2 + 1) * 4 + slot];
+        const double w0 = 1.0 - ra.t2, w1 = ra.t2;
+        dst[e] = make_float2((float)(a.x * w0 + b.x * w1), (float)(a.y * w0 + b.y * w1));
+    }
+}
+
 __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n1, int n2,
                                   const double2 *__restrict__ values, const double *__restrict__ pts, int n,
                                   double2 *__restrict__ out) {
@@ -638,7 +668,7 @@ __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n
 }  // namespace mlb
 
 static int g_nf_lg_wy = 3;       // warp tile: 2^lg_wy samples along y times 32 / 2^lg_wy along x (mlb_nearfield_tune(100 + lg_wy)); 8 x 4 measured fastest
-static int g_nf_minblocks = 6;   // 80 registers, 6 blocks/SM: fastest on B200 (scripts/tune_nearfield.py)
+static int g_nf_minblocks = 8;   // 64 registers, 8 blocks/SM: fastest on B200 since the round-2 rework (scripts/tune_nearfield.py)
 /* tuning knob: minimum resident blocks per SM the complex64 kernel is compiled for (1, 5, 6 or 8) */
 extern "C" int mlb_nearfield_tune(int min_blocks) {
     if (min_blocks >= 102 && min_blocks <= 105) { g_nf_lg_wy = min_blocks - 100; return MLB_OK; }   // warp tile shape
@@ -678,7 +708,18 @@ static int check_desc(const mlb_lens_desc &L, const char *who) {
                 "%s: ring_aux / ring_aux_f32 / ring_lut buffers missing (see mlb_nearfield_prepare)", who);
     MLB_REQUIRE(mlb::aligned16(L.ring_aux) && mlb::aligned16(L.ring_aux_f32), "%s: ring_aux buffers not 16-byte aligned", who);
     MLB_REQUIRE(L.wavelength > 0 && L.n_glass > 0, "%s: bad wavelength / n_glass", who);
+    MLB_REQUIRE(L.ring_tables && L.ring_table_stride > 0, "%s: ring_tables missing (see mlb_nearfield_prepare)", who);
     return MLB_OK;
+}
+
+extern "C" long long mlb_nearfield_ring_table_floats(const mlb_lens_desc *h_desc) {
+    if (!h_desc) return 0;
+    long long need = 4;
+    for (int g = 0; g < h_desc->n_packs && g < MLB_MAX_PACKS; ++g) {
+        const long long v = 8LL * h_desc->packs[g].n_orders * h_desc->packs[g].n_ux * h_desc->packs[g].n_uy;
+        if (v > need) need = v;
+    }
+    return need;
 }
 
 extern "C" int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream) {
@@ -688,7 +729,17 @@ extern "C" int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream) 
     const double kvac = 2.0 * 3.14159265358979323846 / L.wavelength;
     const int n = (L.n_rings > L.n_lut + 1) ? L.n_rings : L.n_lut + 1;
     mlb::nearfield_prepare_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, kvac);
-    return mlb::check_launch("mlb_nearfield_prepare");
+    if (int rc = mlb::check_launch("mlb_nearfield_prepare")) return rc;
+    long long need = 0;
+    for (int g = 0; g < L.n_packs; ++g) {
+        const long long v = 8LL * L.packs[g].n_orders * L.packs[g].n_ux * L.packs[g].n_uy;
+        if (v > need) need = v;
+    }
+    MLB_REQUIRE(L.ring_tables && L.ring_table_stride >= need && L.ring_table_stride % 4 == 0 && mlb::aligned16(L.ring_tables),
+                "mlb_nearfield_prepare: ring_tables needs n_rings x %lld floats (see mlb_nearfield_ring_table_floats)", need);
+    const int per = (int)((need / 2 + 255) / 256);
+    mlb::nearfield_ring_tables_kernel<<<dim3(per > 16 ? 16 : (per < 1 ? 1 : per), L.n_rings), 256, 0, (cudaStream_t)stream>>>(L);
+    return mlb::check_launch("mlb_nearfield_prepare(ring tables)");
 }
 
 static int nearfield_launch(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *Hx, void *Hy, int ld, int out_is_double,

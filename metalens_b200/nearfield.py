@@ -48,7 +48,8 @@ class _LensC(C.Structure):
                 ("wavelength", C.c_double), ("n_glass", C.c_double), ("dipole_moment", C.c_double),
                 ("c0", C.c_double), ("Z0", C.c_double),
                 ("ring_aux", C.c_void_p), ("ring_aux_f32", C.c_void_p), ("ring_lut", C.c_void_p),
-                ("n_lut", C.c_int), ("_pad2", C.c_int), ("lut_r_max", C.c_double)]
+                ("n_lut", C.c_int), ("_pad2", C.c_int), ("lut_r_max", C.c_double),
+                ("ring_tables", C.c_void_p), ("ring_table_stride", C.c_longlong)]
 
 
 def good_fft_number(goal):
@@ -181,6 +182,11 @@ class NearfieldPlan:
             ring_aux=torch.zeros(self.n_rings * 8, dtype=torch.float64, device=dev),
             ring_aux_f32=torch.zeros(self.n_rings * 8, dtype=torch.float32, device=dev),
             ring_lut=torch.zeros(self.n_lut + 1, dtype=torch.int32, device=dev))
+        self._keep['ring_tables'] = None
+        self.ring_table_stride = 0
+        L = self._desc(self._keep['ring_boundary'], self._keep['ring_boundary'], 0.0, 0.0, -1.0, 'x', 1.0)
+        self.ring_table_stride = int(self.lib.mlb_nearfield_ring_table_floats(C.byref(L)))
+        self._keep['ring_tables'] = torch.zeros(self.n_rings * self.ring_table_stride, dtype=torch.float32, device=dev)
         L = self._desc(self._keep['ring_boundary'], self._keep['ring_boundary'], 0.0, 0.0, -1.0, 'x', 1.0)
         _lib.check(self.lib.mlb_nearfield_prepare(C.byref(L), _stream_ptr()), "mlb_nearfield_prepare")
 
@@ -225,6 +231,8 @@ class NearfieldPlan:
         L.c0, L.Z0 = c0, Z0
         L.ring_aux, L.ring_aux_f32 = k['ring_aux'].data_ptr(), k['ring_aux_f32'].data_ptr()
         L.ring_lut, L.n_lut, L.lut_r_max = k['ring_lut'].data_ptr(), self.n_lut, self.lens_max_r
+        if k.get('ring_tables') is not None:
+            L.ring_tables, L.ring_table_stride = k['ring_tables'].data_ptr(), self.ring_table_stride
         return L
 
     def default_grid(self):
