@@ -298,6 +298,12 @@ typedef struct mlb_lens_desc {
     int *ring_lut;
     int n_lut, _pad2;
     double lut_r_max;
+    /*   ring_tables  n_rings x ring_table_stride floats (16-byte aligned; stride = mlb_nearfield_ring_table_floats(), a
+     *                multiple of 4): per ring the complex64 slice [order][iu][iv][slot] of its collection's tables
+     *                interpolated at the ring's grating period (scipy's linear rule on the third axis, float64, rounded
+     *                once) -- the complex64-output kernel then needs 4 corners per order instead of 8 */
+    float *ring_tables;
+    long long ring_table_stride;
 } mlb_lens_desc;
 
 #define MLB_STATS_PER_ORDER 8   /* count, min/max ux, min/max uy, min/max third, pad (int64 each) */
@@ -318,6 +324,8 @@ int mlb_nearfield_blocks(int nx, int ny);
 /* Fills ring_aux / ring_aux_f32 / ring_lut of the descriptor (device buffers owned by the caller) from its ring
  * arrays and table axes; once per lens and wavelength, before the first mlb_nearfield_assemble(). */
 int mlb_nearfield_prepare(const mlb_lens_desc *h_desc, void *stream);
+/* floats per ring of mlb_lens_desc.ring_tables for this descriptor's packs (host only) */
+long long mlb_nearfield_ring_table_floats(const mlb_lens_desc *h_desc);
 /* tuning knob: register budget variant of the complex64 kernel (min resident blocks/SM: 1, 5, 6 or 8), or
  * 100 + lg: warp tile of 2^lg samples along y times 32 / 2^lg along x (lg 2..5; query mlb_nearfield_blocks after) */
 int mlb_nearfield_tune(int min_blocks);
