@@ -207,7 +207,8 @@ int mlb_get_option(const char *name);
  * components at the exact ux==uy==0 bin; P = k^2/(32 pi^2 Z) (...)/(uz+1e-5) * 2.
  * `amp_scale` multiplies every Fhat before use (dx*dy, and 1/len factors).
  * P is written as float (p_is_double=0) or double (1); adding 2 to p_is_double ACCUMULATES into P instead
- * (incoherent sum over sources / polarisations, nearfield.py:69-73).  If `block_sums` is not
+ * (incoherent sum over sources / polarisations, nearfield.py:69-73); adding 4 (float64 output only) says that h_Fhat
+ * holds complex128 aperture sums (pitch ldf in complex128 elements) -- the strict drop-in's inputs as they are.  If `block_sums` is not
  * NULL, each block writes the sum of its finite P values to block_sums[blockIdx]
  * (mlb_ff_epilogue_blocks() entries) for a deterministic total_P.
  */
@@ -371,16 +372,18 @@ int mlb_peer_flag_words(void);
 int mlb_peer_state_words(void);
 /* Row pass of ONE 2-D transform spread over `world` ranks, fused with the all-to-all that follows it: like mlb_fft_rows
  * (fold + fftshift rolls included) on this rank's n_rows folded rows -- input matrices [n_rows*s1][N*s2], folded row r
- * = sum over t1 of input rows r + t1*n_rows, i.e. the rank holds the s1 aliased copies of ITS rows one after the other
- * -- but output row r is row (out_row0 + r) mod n_rows_total of the distributed intermediate, and its column slab
+ * = sum over t1 of input rows r + t1*n_rows, i.e. the rank holds the s1 aliased copies of ITS rows one after the other.
+ * The rank's rows are blocks of row_block consecutive rows of the distributed intermediate, row_stride apart (blocks dealt
+ * round-robin to the ranks balance the work of a round lens; one block = a contiguous slab): output row r is row
+ * (out_row0 + (r / row_block) * row_stride + r % row_block) mod n_rows_total, and its column slab
  * [p*N/world, (p+1)*N/world) is stored straight into rank p's buffer h_out_peers[p*batch + f] (pitch ld_out >= N/world
  * complex) over NVLink while the next rows are still streaming in.  After a mlb_peer_barrier every rank holds all
  * n_rows_total rows of its N/world columns and runs mlb_fft_cols / mlb_fft_cols_power on them.
- * world must be a power of two <= MLB_MAX_PEERS dividing N; N in 256..2048 (the TMA-fed kernel), else
- * MLB_ERR_UNSUPPORTED. */
+ * world and row_block must be powers of two (world <= MLB_MAX_PEERS dividing N); N in 256..2048 (the TMA-fed kernel),
+ * else MLB_ERR_UNSUPPORTED. */
 int mlb_fft_rows_scatter(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out_peers, int ld_out, int n_rows,
                          int N, int s1, int s2, const mlb_c64 *tw, int in_roll_c, int out_roll, int out_row0,
-                         int n_rows_total, int world, int batch, void *stream);
+                         int row_block, int row_stride, int n_rows_total, int world, int batch, void *stream);
 /* Flag barrier across the ranks, in stream order: returns (on the device) once every rank's stream has reached its
  * matching mlb_peer_barrier -- all peer stores issued by earlier kernels of those streams are then visible. */
 int mlb_peer_barrier(void *const *h_flags, int rank, int world, void *local_state, void *stream);

@@ -76,7 +76,8 @@ SIGNATURES = {
     "mlb_peer_flag_words": (C.c_int, []),
     "mlb_peer_state_words": (C.c_int, []),
     "mlb_fft_rows_scatter": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]),
     "mlb_peer_barrier": (C.c_int, [_PP, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_peer_allgather": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, _PP, C.c_longlong, C.c_longlong,
                                      C.c_void_p, _PP, C.c_int, C.c_int, _PP, C.c_int, C.c_int, C.c_void_p, C.c_int,

@@ -3,6 +3,8 @@
 // float64 arithmetic; K^2 points x ~100 flop is negligible next to the aperture sum.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mlb {
@@ -33,7 +35,7 @@ __device__ __forceinline__ float fabs2(cfl a) { return a.re * a.re + a.im * a.im
 // F32: the float32-output flavour.  The evanescent mask and the DC test stay in float64 (bit-identical
 // to the reference); the polar projections and |.|^2 run in fp32 (relative error ~1e-7, the inputs are
 // complex64 anyway), which makes the kernel memory- instead of FP64-pipe-bound.
-template <bool F32>
+template <bool F32, bool IN64 = false>
 __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
     const long long n = (long long)blockIdx.x * EPI_THREADS + threadIdx.x;
     const long long total = (long long)a.Kx * a.Ky;
@@ -43,7 +45,10 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
         const int i = (int)(n / a.Ky), j = (int)(n % a.Ky);
         const double ux = a.ux[i], uy = a.uy[j];
         const size_t off = (size_t)i * a.ldf + j;
-        const float2 fex = a.F[0][off], fey = a.F[1][off], fhx = a.F[2][off], fhy = a.F[3][off];
+        // IN64: the caller's complex128 aperture sums as they are (the strict drop-in, nearfield_farfield.py:14)
+        using in_t = typename std::conditional<IN64, double2, float2>::type;
+        const in_t fex = reinterpret_cast<const in_t *>(a.F[0])[off], fey = reinterpret_cast<const in_t *>(a.F[1])[off];
+        const in_t fhx = reinterpret_cast<const in_t *>(a.F[2])[off], fhy = reinterpret_cast<const in_t *>(a.F[3])[off];
         const double s_ = a.amp_scale;
         // (8.15) J = n x H, M = -n x E with n = +z  (reference :135-138)
         const cd Nx = {-(double)fhy.x * s_, -(double)fhy.y * s_};
@@ -57,8 +62,8 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
         if (F32) {
             // raw aperture sums here; the common factor amp_scale^2 is applied in float64 at the end, so the
             // fp32 part never sees the (unit-system dependent) dx*dy scale
-            const cfl nx = {-fhy.x, -fhy.y}, ny = {fhx.x, fhx.y};
-            const cfl lx = {fey.x, fey.y}, ly = {-fex.x, -fex.y};
+            const cfl nx = {-(float)fhy.x, -(float)fhy.y}, ny = {(float)fhx.x, (float)fhx.y};
+            const cfl lx = {(float)fey.x, (float)fey.y}, ly = {-(float)fex.x, -(float)fex.y};
             cfl nth, nph, lth, lph;
             float uzf;
             if (uz2 < 0.0) {
@@ -271,7 +276,13 @@ extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const doub
     const double k = 2 * pi * n_glass / wavelength;
     a.pref = k * k / (32 * pi * pi * a.Z);                                  // :184
     a.ldf = ldf; a.ldp = ldp; a.Kx = Kx; a.Ky = Ky; a.p_is_double = p_is_double & 1; a.accumulate = (p_is_double >> 1) & 1;
+    const bool in64 = (p_is_double & 4) != 0;
+    MLB_REQUIRE(!in64 || (p_is_double & 1), "mlb_ff_epilogue: complex128 aperture sums need the float64 output");
     p_is_double &= 1;
+    if (in64) {
+        mlb::ff_epilogue_kernel<false, true><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
+        return mlb::check_launch("mlb_ff_epilogue(complex128)");
+    }
     bool x2 = !p_is_double && Ky % 2 == 0 && ldf % 2 == 0 && ldp % 2 == 0 && (reinterpret_cast<uintptr_t>(P) & 7u) == 0 &&
               mlb::aligned16(uy);
     for (int f = 0; f < 4; ++f) x2 = x2 && mlb::aligned16(a.F[f]);

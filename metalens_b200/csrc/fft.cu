@@ -111,6 +111,7 @@ struct FftArgs {
 struct RowScatter {
     float2 *out[MLB_MAX_PEERS][4];
     int world, lg_slab, out_row0, rows_total;
+    int lg_block, row_stride;         // local row r -> row out_row0 + (r >> lg_block) * row_stride + (r & (block - 1))
 };
 
 // folded, fftshift-rolled input sample(s) of row r at position n (VEC consecutive positions).
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
         if (sc.world) {
             // fused all-to-all: the row's column slabs go straight to their owners over NVLink (8-byte stores, a warp
             // covers 256 contiguous bytes of one peer's row), overlapped with the TMA stream of the next rows
-            int R = sc.out_row0 + r;
+            int R = sc.out_row0 + (r >> sc.lg_block) * sc.row_stride + (r & ((1 << sc.lg_block) - 1));
             if (R >= sc.rows_total) R -= sc.rows_total;
             const size_t row_off = (size_t)R * a.ld_out;
             const int slab_mask = (1 << sc.lg_slab) - 1;
@@ -1404,14 +1405,20 @@ extern "C" int mlb_fft_rows_ws(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *c
 
 extern "C" int mlb_fft_rows_scatter(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out_peers, int ld_out,
                                     int n_rows, int N, int s1, int s2, const mlb_c64 *tw, int in_roll_c, int out_roll,
-                                    int out_row0, int n_rows_total, int world, int batch, void *stream) {
+                                    int out_row0, int row_block, int row_stride, int n_rows_total, int world, int batch,
+                                    void *stream) {
     MLB_REQUIRE(h_out_peers && world >= 1 && world <= MLB_MAX_PEERS && (world & (world - 1)) == 0,
                 "mlb_fft_rows_scatter: world %d must be a power of two <= %d", world, MLB_MAX_PEERS);
     MLB_REQUIRE(batch >= 1 && batch <= 4 && N > 0 && N % world == 0, "mlb_fft_rows_scatter: bad batch %d / N %d", batch, N);
     MLB_REQUIRE(n_rows > 0 && n_rows <= n_rows_total && out_row0 >= 0 && out_row0 < n_rows_total,
                 "mlb_fft_rows_scatter: bad row window (%d rows at %d of %d)", n_rows, out_row0, n_rows_total);
+    MLB_REQUIRE(row_block >= 1 && (row_block & (row_block - 1)) == 0 && n_rows % row_block == 0 && row_stride >= row_block &&
+                    (long long)(n_rows / row_block - 1) * row_stride + row_block <= n_rows_total,
+                "mlb_fft_rows_scatter: bad row blocks (%d rows in blocks of %d, %d apart, of %d)", n_rows, row_block,
+                row_stride, n_rows_total);
     mlb::RowScatter sc = {};
     sc.world = world; sc.lg_slab = mlb::ilog2(N / world); sc.out_row0 = out_row0; sc.rows_total = n_rows_total;
+    sc.lg_block = mlb::ilog2(row_block); sc.row_stride = row_stride;
     for (int p = 0; p < world; ++p)
         for (int f = 0; f < 4; ++f) {
             const mlb_c64 *ptr = h_out_peers[p * batch + (f < batch ? f : 0)];

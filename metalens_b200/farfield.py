@@ -589,7 +589,8 @@ def farfield_from_nearfield(fftEx, fftEy, fftHx, fftHy, xp_list, yp_list, wavele
     (nearfield_farfield.py:14-75): same arguments (``fftEx = fft2(fftshift(Ex))`` ...),
     same return tuple ``(P_here_times_r2_over_uz, total_P, ux, uy, dux, duy)``, same
     AssertionErrors on shape / grid violations.  The power epilogue runs on the GPU in
-    float64; the reference's RAM chunk loop and its progress prints are not reproduced.
+    float64 on the caller's complex128 values (no down-cast); the reference's RAM chunk loop and
+    its progress prints are not reproduced.
     """
     dxp = xp_list[1] - xp_list[0]
     dyp = yp_list[1] - yp_list[0]
@@ -603,22 +604,23 @@ def farfield_from_nearfield(fftEx, fftEy, fftHx, fftHy, xp_list, yp_list, wavele
     dev = torch.device("cuda", torch.cuda.current_device())
     ux = fft_bin_direction_cosines(num_x, dxp, wavelength, n_glass)
     uy = fft_bin_direction_cosines(num_y, dyp, wavelength, n_glass)
-    # common power-of-two normalisation so complex64 cannot under/overflow for any unit system
-    peak = max(float(np.abs(a).max()) for a in (fftEx, fftEy, fftHx, fftHy))
-    norm = 2.0 ** math.floor(math.log2(peak)) if peak > 0 and math.isfinite(peak) else 1.0
-    F = []
-    for a in (fftEx, fftEy, fftHx, fftHy):
-        buf = _c64_buffer(num_x, num_y, dev)
-        buf[:, :num_y].copy_(torch.from_numpy(np.ascontiguousarray(a / norm).astype(np.complex64)))
-        F.append(buf)
+    # the caller's complex128 arrays as they are: the whole epilogue (:135-189) runs in float64 on float64 inputs
+    F = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)).to(dev) for a in (fftEx, fftEy, fftHx, fftHy)]
     d_ux, d_uy = torch.from_numpy(ux).to(dev), torch.from_numpy(uy).to(dev)
     P = torch.empty((num_x, num_y), dtype=torch.float64, device=dev)
     ux_s = np.fft.fftshift(ux)                                                           # :69
     uy_s = np.fft.fftshift(uy)                                                           # :70
     dux = ux_s[1] - ux_s[0]                                                              # :71
     duy = uy_s[1] - uy_s[0]                                                              # :72
-    total = _power_epilogue(lib, F, d_ux, d_uy, num_x, num_y, dxp * dyp * norm, wavelength, n_glass,
-                            P, dux * duy)                                                # :74
+    nblocks = lib.mlb_ff_epilogue_blocks(num_x, num_y)
+    block_sums = torch.empty(nblocks, dtype=torch.float64, device=dev)
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+    pf, _keep = _lib.ptr_array(F)
+    _lib.check(lib.mlb_ff_epilogue(pf, num_y, d_ux.data_ptr(), d_uy.data_ptr(), num_x, num_y, float(dxp * dyp),
+                                   float(wavelength), float(n_glass), Z0, P.data_ptr(), num_y, 1 + 4,
+                                   block_sums.data_ptr(), _stream_ptr()), "mlb_ff_epilogue")
+    _lib.check(lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, float(dux * duy), total.data_ptr(), _stream_ptr()),
+               "mlb_sum_f64")                                                            # :74
     P = torch.roll(P, shifts=(num_x // 2, num_y // 2), dims=(0, 1)).cpu().numpy()       # fftshift, :68
     ux2, uy2 = np.meshgrid(ux_s, uy_s, indexing="ij", sparse=True)                       # :73
     return P, float(total.cpu()[0]), ux2, uy2, dux, duy

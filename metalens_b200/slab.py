@@ -4,7 +4,8 @@ The reference computes disjoint uy chunks of one transform separately (nearfield
 disjoint y slabs of one assembly separately (nearfield.py:488-514).  Here the same independence is cut the
 other way round so that BOTH halves of the hot path shrink by 1/G and one small exchange remains:
 
-    rank g owns the folded rows r in [g K1/G, (g+1) K1/G) -- i.e. the aperture x-rows { r + t K1 } -- and
+    rank g owns every G-th block of 4 folded rows r (round-robin: equal work on a round lens) -- i.e. the aperture
+    x-rows { r + t K1 } -- and
       1. assembles only those rows of the aperture   (NearfieldPlan.run on x_pts[x_rows]),
       2. folds + row-transforms them                 (mlb_fft_rows_scatter), the kernel storing each row's column
          slab p straight into rank p's buffer over NVLink: the all-to-all of a distributed 2-D FFT, fused,
@@ -31,12 +32,25 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+ROW_BLOCK = 4      # rows per ownership block: the x extent of the assembly kernel's warp tile
+
+
+def _row_block(K1, world):
+    per = K1 // world
+    return ROW_BLOCK if per % ROW_BLOCK == 0 else 1
+
+
 def slab_rows(Mx, sx, rank, world):
     """Aperture x indices rank `rank` owns, in the order its local buffer holds them: the sx aliased copies of
-    its K1/world folded rows one after the other."""
+    its K1/world folded rows one after the other.  The folded rows are dealt to the ranks round-robin in blocks of
+    ROW_BLOCK (rank g owns rows 4(g + G b) .. 4(g + G b) + 3, b = 0, 1, ...): every rank then sees the same mix of
+    centre, ring and outside-the-lens samples of a round lens (contiguous slabs cost the edge ranks half as much)."""
     K1 = Mx // sx
     per = K1 // world
-    base = np.arange(rank * per, (rank + 1) * per)
+    blk = _row_block(K1, world)
+    b = np.arange(per // blk)
+    base = (blk * (rank + world * b))[:, None] + np.arange(blk)[None, :]
+    base = base.reshape(-1)
     return np.concatenate([base + t * K1 for t in range(sx)])
 
 
@@ -46,13 +60,16 @@ def slab_geometry(Mx, My, sx, sy, rank, world):
       folded row  G[r][p]  = sum_{t1,t2} J[r + t1 K1][((p - roll_c) mod K2) + t2 K2]      r = this rank's source rows
       row pass    W[R][(q + out_roll_rows) mod K2] = sum_p G[r][p] e^{-2 pi i q p / K2},   R = (r + h1) mod K1
       column pass F[(q + out_roll_cols) mod K1][c] = sum_R W[R][c] e^{-2 pi i q R / K1}
-    so that F is in the fftshifted order of ux[::sx], uy[::sy]."""
+    so that F is in the fftshifted order of ux[::sx], uy[::sy].  The rank's l-th local row is source row
+    row_block (rank + world (l // row_block)) + l % row_block, i.e. intermediate row
+    (out_row0 + (l // row_block) row_stride + l % row_block) mod K1."""
     K1, K2 = Mx // sx, My // sy
     h1, h2 = Mx // 2, My // 2
     per = K1 // world
+    blk = _row_block(K1, world)
     return dict(K1=K1, K2=K2, rows_per_rank=per, cols_per_rank=K2 // world, x_rows=slab_rows(Mx, sx, rank, world),
                 roll_c=h2 % K2, out_roll_rows=(h2 // sy) % K2, out_roll_cols=(h1 // sx) % K1,
-                out_row0=(rank * per + h1 % K1) % K1)
+                out_row0=(blk * rank + h1 % K1) % K1, row_block=blk, row_stride=blk * world)
 
 
 class SlabFarfield:
@@ -120,6 +137,7 @@ class SlabFarfield:
         geo = slab_geometry(self.Mx, self.My, self.sx, self.sy, self.rank, G)
         self.roll_c, self.out_roll_rows = geo["roll_c"], geo["out_roll_rows"]
         self.out_roll_cols, self.out_row0 = geo["out_roll_cols"], geo["out_row0"]
+        self.row_block, self.row_stride = geo["row_block"], geo["row_stride"]
         self._pw_all, self._k1 = _lib.ptr_array([p for peer in self._w_ptrs for p in peer])
         self._pw_mine, self._k2 = _lib.ptr_array(self._w_ptrs[self.rank])
 
@@ -135,7 +153,8 @@ class SlabFarfield:
         pin, keep = _lib.ptr_array(list(fields))
         _lib.check(lib.mlb_fft_rows_scatter(pin, ld, self._pw_all, self.ldw, self.rows_per_rank, self.K2, self.sx, self.sy,
                                             self.tw2.data_ptr(), self.roll_c, self.out_roll_rows, self.out_row0,
-                                            self.K1, self.world, 4, _stream_ptr()), "mlb_fft_rows_scatter")
+                                            self.row_block, self.row_stride, self.K1, self.world, 4, _stream_ptr()),
+                   "mlb_fft_rows_scatter")
 
     def _cols(self):
         col0 = self.rank * self.cols_per_rank

@@ -42,8 +42,9 @@ def test_dropin_farfield_from_nearfield(name, golden_dir):
     f = [np.fft.fft2(np.fft.fftshift(a.astype(complex))) for a in (Ex, Ey, Hx, Hy)]
     P, total, ux, uy, dux, duy = farfield_from_nearfield(f[0], f[1], f[2], f[3], list(x), list(y), WL, NG)
     assert P.dtype == np.float64 and P.shape == g["P"].shape
-    assert power_map_error(P, g["P"]) < FF_TOL
-    assert abs(total - g["total_P"]) <= FF_TOL * abs(g["total_P"])
+    # float64 epilogue on the caller's complex128 arrays: far below north_star's 1e-5
+    assert power_map_error(P, g["P"]) < 1e-11
+    assert abs(total - g["total_P"]) <= 1e-11 * abs(g["total_P"])
     assert ux.shape == (len(x), 1) and uy.shape == (1, len(y))
     np.testing.assert_array_equal(ux.ravel(), g["ux"])
     np.testing.assert_array_equal(uy.ravel(), g["uy"])

@@ -21,6 +21,7 @@ def test_distributed_fold_fft_equals_reference_bins(M, s, world):
         owned[rows] += 1
         local = J[rows]                                                       # what the rank assembles / holds
         n = g["rows_per_rank"]
+        assert np.array_equal(rows[:n] % K, rows[:n]) and np.array_equal(rows[n:2 * n], rows[:n] + K) or s == 1
         p = np.arange(K)
         for r in range(n):
             folded = np.zeros(K, complex)
@@ -28,7 +29,7 @@ def test_distributed_fold_fft_equals_reference_bins(M, s, world):
                 for t2 in range(s):
                     folded += local[r + t1 * n][((p - g["roll_c"]) % K) + t2 * K]
             row = np.roll(np.fft.fft(folded), g["out_roll_rows"])
-            R = (g["out_row0"] + r) % K
+            R = (g["out_row0"] + (r // g["row_block"]) * g["row_stride"] + r % g["row_block"]) % K
             for peer in range(world):
                 c0 = peer * g["cols_per_rank"]
                 W[peer][R] = row[c0:c0 + g["cols_per_rank"]]
@@ -38,5 +39,7 @@ def test_distributed_fold_fft_equals_reference_bins(M, s, world):
 
 
 def test_slab_rows_layout():
-    rows = slab_rows(32, 4, 1, 2)
-    assert rows.tolist() == [4, 5, 6, 7, 12, 13, 14, 15, 20, 21, 22, 23, 28, 29, 30, 31]
+    rows = slab_rows(64, 4, 1, 2)          # K1 = 16, 8 rows per rank in blocks of 4 dealt round-robin: rank 1 -> 4..7, 12..15
+    assert rows.tolist() == [4, 5, 6, 7, 12, 13, 14, 15, 20, 21, 22, 23, 28, 29, 30, 31,
+                             36, 37, 38, 39, 44, 45, 46, 47, 52, 53, 54, 55, 60, 61, 62, 63]
+    assert slab_rows(32, 4, 1, 2).tolist() == [4, 5, 6, 7, 12, 13, 14, 15, 20, 21, 22, 23, 28, 29, 30, 31]
