@@ -264,11 +264,17 @@ def bench_nearfield(M, torch, peaks, cpu_cols=384):
     R = M * (wl / 2.2) / 2
     f = R / math.tan(math.radians(44.0))
     spec = dict(bands=[(15.0, 25.0, 1000e-9, 0.3), (25.0, 45.0, 650e-9, 1.1)], source_distance=f, radius=R * 0.999)
-    t0 = time.perf_counter()
     collections, hgs = synth_lens.make_library(grating, lens_center, spec)
-    periph, center, _ = make_design(collections, f, spec["radius"], hgs)
+    make_design(collections, f, spec["radius"], hgs, device="cuda")           # first call: kernel loading
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    periph, center, _ = make_design(collections, f, spec["radius"], hgs, device="cuda")   # hex centre laid out on the GPU (N2)
+    torch.cuda.synchronize()
     t_design = time.perf_counter() - t0
+    t0 = time.perf_counter()
     plan = NearfieldPlan(wl, periph, center, hgs)
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter() - t0
     x = np.linspace(-R, R, M)
     out = torch.zeros((4, M, M), dtype=torch.complex64, device="cuda")
     for _ in range(2):
@@ -290,13 +296,15 @@ def bench_nearfield(M, torch, peaks, cpu_cols=384):
                              note="SURVEY 8(d): bytes_B = 32*M^2 written; the kernel is bound by instruction issue "
                                   "(float64 geometry), see profiles/"),
                note="one fused kernel launch incl. host packing of x/y and the violation read-back; "
-                    "algorithmic bytes = 32*M^2 written (4 complex64 fields)", design_seconds=t_design)
+                    "algorithmic bytes = 32*M^2 written (4 complex64 fields)", design_seconds=t_design,
+               plan_seconds=t_plan, design_note="make_design with the hex centre on the device (mlb_hex_count / mlb_hex_fill) and "
+                                                "NearfieldPlan (device binning, table packs, ring slices), wall clock")
     # CPU oracle on a strip of the same grid (off-centre so centre and rings are both represented)
     from oracle import nearfield_oracle as no
     j0 = M // 2 + M // 8
     ys = x[j0:j0 + cpu_cols]
     t0 = time.perf_counter()
-    no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center, hgs, x_pts=x, y_pts=ys)
+    no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center.cpu().numpy(), hgs, x_pts=x, y_pts=ys)
     tc = time.perf_counter() - t0
     res["cpu_baseline"] = dict(value=M * cpu_cols / tc, unit="aperture samples/s", cores=1, kind="port",
                                sample="%d x %d strip of the same grid, oracle/nearfield_oracle.py (numpy + scipy "
@@ -351,7 +359,7 @@ def cfg4_lens(M, wl=580e-9):
     spec = dict(bands=[(15.0, 25.0, 1000e-9, 0.3), (25.0, 45.0, 650e-9, 1.1), (45.0, 71.0, 300e-9, 2.3)],
                 source_distance=f, radius=R * 0.999)
     collections, hgs = synth_lens.make_library(grating, lens_center, spec)
-    periph, center, _ = make_design(collections, f, spec["radius"], hgs)
+    periph, center, _ = make_design(collections, f, spec["radius"], hgs, device="cuda")
     return periph, center, hgs, R, f
 
 
@@ -431,7 +439,7 @@ def bench_cfg4(torch, dist, rank, world, steps, warmup, M=8192, stride=4, check=
     if world > 1:
         dist.all_reduce(p_in, op=dist.ReduceOp.SUM)
     res = dict(workload=WORKLOADS["cfg4"]["name"], aperture=[M, M], far_field=[K, K], n_gpus=world,
-               rings=int(len(periph["r_min_list"])), hex_cells=int(len(center)), design_seconds=t_design,
+               rings=int(len(periph["r_min_list"])), hex_cells=int(center.shape[0]), design_seconds=t_design,
                ms_per_step=ms_step, ms_assembly=ms_nf, ms_farfield=ms_ff, steps=steps, warmup=warmup,
                far_field_points_per_s=K * K / ms_step * 1e3, aperture_samples_per_s=M * M / ms_step * 1e3,
                assembly_write_gbs=32.0 * M * M / world / ms_nf / 1e6,

@@ -355,6 +355,23 @@ int mlb_nearfield_fixup(const mlb_lens_desc *h_desc, void *Ex, void *Ey, void *H
 int mlb_table_eval(const double *axes, int n0, int n1, int n2, const double *values, const double *pts, int n,
                    double *out, void *stream);
 
+/* ---- N2: lens layout on the device (design_collimator.py:74-137, lens_center.py:175-186) ----------------------
+ * Hex-lattice centre of a design: lattice points n*(n2*sqrt(3)/2, n1 + n2/2) with x^2 + y^2 < radius^2 over the candidate
+ * ranges of design_collimator.hexagonal_grid (:85-103), in the reference's row order (n2 outer, n1 inner).
+ *   mlb_hex_count : counts[c] = cells of lattice column n2_lo + c                         (n2_hi - n2_lo + 1 ints)
+ *   mlb_hex_fill  : offsets = exclusive scan of counts (int64); writes cells[row] = (x, y, index), index = the
+ *                   HexGridSet entry picked by pick_from_phase(target_phase(r) + pi): argmax_k Im(x_amp[k] e^{-i phase});
+ *                   x_amp = n_amp complex128 values (re, im pairs)
+ * mlb_cells_bin : the bin grid the assembly kernel searches (mlb_lens_desc.cell_x / cell_y / cell_which / cell_orig /
+ *   bin_start) from device cells [n][3]: phase 0 adds the bin populations into count_or_cursor (nbx*nby ints, zeroed by
+ *   the caller), phase 1 scatters the cells with count_or_cursor = a copy of bin_start used as write cursors. */
+int mlb_hex_count(double pitch, double radius, int n1_lo, int n1_hi, int n2_lo, int n2_hi, int *counts, void *stream);
+int mlb_hex_fill(double pitch, double radius, int n1_lo, int n1_hi, int n2_lo, int n2_hi, const long long *offsets,
+                 double wavelength, double refractive_index, double source_distance, const double *x_amp, int n_amp,
+                 double *cells, void *stream);
+int mlb_cells_bin(const double *cells, int n, double x0, double y0, double bin_size, int nbx, int nby, int phase,
+                  int *count_or_cursor, double *cell_x, double *cell_y, int *cell_which, int *cell_orig, void *stream);
+
 /* ---- 8e: multi-GPU exchange steps ------------------------------------------------------------------------------
  * The reference is single-process; its independent units are the uy chunks of one transform
  * (nearfield_farfield.py:45-66) and the y slabs of one assembly (nearfield.py:488-514).  Two families:

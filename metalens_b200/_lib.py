@@ -72,6 +72,11 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_table_eval": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),
+    "mlb_hex_count": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_hex_fill": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double,
+                               C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_cells_bin": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     # 8e: multi-GPU exchange steps (peer memory over NVLink; NCCL wrappers)
     "mlb_peer_flag_words": (C.c_int, []),
     "mlb_peer_state_words": (C.c_int, []),

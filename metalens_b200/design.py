@@ -70,6 +70,44 @@ def design_center(hgs, source_distance, radius):
     return np.column_stack((xy, np.argmax(fom, axis=1).astype(float)))
 
 
+def _hex_ranges(n, radius):
+    """Candidate index ranges of hexagonal_grid(fourfold_symmetry=False) (design_collimator.py:85-103)."""
+    corners = [(radius, radius), (radius, -radius), (-radius, radius), (-radius, -radius)]
+    n1c = [y / n - x / (n * 3 ** 0.5) for x, y in corners]
+    n2c = [2 * x / (n * 3 ** 0.5) for x, y in corners]
+    return (int(min(n1c)) - 2, int(max(n1c)) + 2), (int(min(n2c)) - 2, int(max(n2c)) + 2)
+
+
+def design_center_device(hgs, source_distance, radius, device=None):
+    """design_center() on the GPU: the same rows [x, y, index] in the same order, as a CUDA float64 (n, 3)
+    tensor that NearfieldPlan consumes directly -- the ~10^6-cell lattice never exists on the host.  Three launches
+    (count per lattice column, scan, fill) through the C-ABI (csrc/design.cu)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
+    if not hasattr(hgs, 'x_amp_list'):
+        raise ValueError('Need to run characterize() first')                   # lens_center.py:178-179
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    (n1_lo, n1_hi), (n2_lo, n2_hi) = _hex_ranges(pitch, radius)
+    cols = n2_hi - n2_lo + 1
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    counts = torch.empty(cols, dtype=torch.int32, device=dev)
+    _lib.check(lib.mlb_hex_count(pitch, radius, n1_lo, n1_hi, n2_lo, n2_hi, counts.data_ptr(), stream), "mlb_hex_count")
+    ends = torch.cumsum(counts, dim=0, dtype=torch.int64)
+    offsets = ends - counts
+    n = int(ends[-1].item())
+    cells = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    if n:
+        amp = torch.from_numpy(np.ascontiguousarray(np.asarray(hgs.x_amp_list, dtype=np.complex128)).view(np.float64)).to(dev)
+        _lib.check(lib.mlb_hex_fill(pitch, radius, n1_lo, n1_hi, n2_lo, n2_hi, offsets.data_ptr(), wavelength,
+                                    float(refractive_index), source_distance, amp.data_ptr(), amp.numel() // 2,
+                                    cells.data_ptr(), stream), "mlb_hex_fill")
+    return cells
+
+
 def design_periphery(collections, source_distance, radius):
     """Ring layout of the grating periphery (design_collimator.py:148-228): one ring per 2-pi zone of
     the target phase beyond the switch radius, each assigned to the collection whose angle band
@@ -109,9 +147,11 @@ def design_periphery(collections, source_distance, radius):
             'num_around_circle_list': np.array([r[3] for r in rows])}
 
 
-def make_design(collections, source_distance, radius, hgs, make_xyrra_list=False):
+def make_design(collections, source_distance, radius, hgs, make_xyrra_list=False, device=None):
     """Full round-lens design (design_collimator.py:273-313): returns
-    (lens_periphery_summary, lens_center_summary, r_for_switch)."""
+    (lens_periphery_summary, lens_center_summary, r_for_switch).  device='cuda' (or a torch device) lays the hex centre
+    out on the GPU: lens_center_summary is then a CUDA (n, 3) tensor with the same rows, which NearfieldPlan /
+    build_nearfield take as is (the ring arrays are O(rings) and stay on the host)."""
     if make_xyrra_list:
         raise NotImplementedError("pillar lists for the CAD exporters are outside this engine")
     if len(collections) > 0:
@@ -124,5 +164,9 @@ def make_design(collections, source_distance, radius, hgs, make_xyrra_list=False
         assert r_for_switch < radius
     else:
         periphery, r_for_switch = None, radius
-    center = design_center(hgs, source_distance, r_for_switch - 300 * nm)
+    if device is not None:
+        center = design_center_device(hgs, source_distance, r_for_switch - 300 * nm,
+                                      None if device in ("cuda", True) else device)
+    else:
+        center = design_center(hgs, source_distance, r_for_switch - 300 * nm)
     return periphery, center, r_for_switch

@@ -144,37 +144,36 @@ class NearfieldPlan:
                                    up(p.order_array, np.int32), up(p.order_map, np.int32)))
         self.n_stats = slot
 
-        # centre cells -> uniform bin grid (replaces the reference's cKDTree, nearfield.py:363)
-        cells = np.asarray(lens_center_summary, dtype=np.float64).reshape(-1, 3)
-        self.n_cells = cells.shape[0]
-        if self.n_cells:
-            cx, cy = cells[:, 0], cells[:, 1]
-            span_x, span_y = cx.max() - cx.min(), cy.max() - cy.min()
-            area = max(span_x * span_y, 1e-300)
-            # about one cell per bin: with the exact reach test of the kernel a sample visits its own bin and the ring
-            # of eight around it (~9 cells) instead of 9 bins of ~4 cells
-            b = math.sqrt(area / self.n_cells) if area > 1e-300 else 1.0
-            b = max(b, 1e-12 * max(span_x, span_y, 1e-30))
-            self.bin_x0, self.bin_y0, self.bin_size = float(cx.min()), float(cy.min()), float(b)
-            self.nbx = int(math.floor(span_x / b)) + 1
-            self.nby = int(math.floor(span_y / b)) + 1
-            bx = np.minimum(np.floor((cx - self.bin_x0) / b).astype(np.int64), self.nbx - 1)
-            by = np.minimum(np.floor((cy - self.bin_y0) / b).astype(np.int64), self.nby - 1)
-            key = by * self.nbx + bx
-            order = np.argsort(key, kind="stable")
-            self._cells_host = cells[:, 0:2].copy()              # for the reference's tie choice (resolve_ties)
-            self._sorted_pos = np.empty(self.n_cells, dtype=np.int64)
-            self._sorted_pos[order] = np.arange(self.n_cells)
-            counts = np.bincount(key, minlength=self.nbx * self.nby)
-            self._keep.update(
-                cell_x=up(cx[order], np.float64), cell_y=up(cy[order], np.float64),
-                cell_which=up(cells[order, 2].astype(np.int64), np.int32),        # .astype(int), :367
-                cell_orig=up(order, np.int32),
-                bin_start=up(np.concatenate(([0], np.cumsum(counts))), np.int32))
+        # centre cells -> uniform bin grid (replaces the reference's cKDTree, nearfield.py:363).  About one cell per bin:
+        # with the exact reach test of the kernel a sample visits its own bin and the ring of eight around it (~9 cells)
+        self._cells_dev = None
+        if torch.is_tensor(lens_center_summary) and lens_center_summary.is_cuda:
+            self._bin_on_device(lens_center_summary.to(dev).reshape(-1, 3).contiguous(), up)
         else:
-            self.bin_x0 = self.bin_y0 = 0.0
-            self.bin_size = 1.0
-            self.nbx = self.nby = 1
+            cells = np.asarray(lens_center_summary.cpu() if torch.is_tensor(lens_center_summary) else lens_center_summary,
+                               dtype=np.float64).reshape(-1, 3)
+            self.n_cells = cells.shape[0]
+            if self.n_cells:
+                cx, cy = cells[:, 0], cells[:, 1]
+                self._bin_geometry(cx.min(), cx.max(), cy.min(), cy.max())
+                b = self.bin_size
+                bx = np.minimum(np.floor((cx - self.bin_x0) / b).astype(np.int64), self.nbx - 1)
+                by = np.minimum(np.floor((cy - self.bin_y0) / b).astype(np.int64), self.nby - 1)
+                key = by * self.nbx + bx
+                order = np.argsort(key, kind="stable")
+                self._cells_host = cells[:, 0:2].copy()              # for the reference's tie choice (_resolve_ties)
+                self._sorted_pos = np.empty(self.n_cells, dtype=np.int64)
+                self._sorted_pos[order] = np.arange(self.n_cells)
+                counts = np.bincount(key, minlength=self.nbx * self.nby)
+                self._keep.update(
+                    cell_x=up(cx[order], np.float64), cell_y=up(cy[order], np.float64),
+                    cell_which=up(cells[order, 2].astype(np.int64), np.int32),        # .astype(int), :367
+                    cell_orig=up(order, np.int32),
+                    bin_start=up(np.concatenate(([0], np.cumsum(counts))), np.int32))
+            else:
+                self.bin_x0 = self.bin_y0 = 0.0
+                self.bin_size = 1.0
+                self.nbx = self.nby = 1
 
         # per-lens derived data, filled on the device by mlb_nearfield_prepare (ring records, ring bin table)
         self.n_lut = max(16, 4 * self.n_rings)
@@ -191,6 +190,52 @@ class NearfieldPlan:
         _lib.check(self.lib.mlb_nearfield_prepare(C.byref(L), _stream_ptr()), "mlb_nearfield_prepare")
 
     # ------------------------------------------------------------------
+    def _bin_geometry(self, x_min, x_max, y_min, y_max):
+        span_x, span_y = float(x_max - x_min), float(y_max - y_min)
+        area = max(span_x * span_y, 1e-300)
+        b = math.sqrt(area / self.n_cells) if area > 1e-300 else 1.0
+        b = max(b, 1e-12 * max(span_x, span_y, 1e-30))
+        self.bin_x0, self.bin_y0, self.bin_size = float(x_min), float(y_min), float(b)
+        self.nbx = int(math.floor(span_x / b)) + 1
+        self.nby = int(math.floor(span_y / b)) + 1
+
+    def _bin_on_device(self, cells, up):
+        """Cells that already live on the GPU (design.design_center_device): bin them there (mlb_cells_bin: bin
+        populations, scan, scatter) -- no host sort, no upload."""
+        dev = self.device
+        self.n_cells = int(cells.shape[0])
+        self._cells_dev = cells
+        if not self.n_cells:
+            self.bin_x0 = self.bin_y0 = 0.0
+            self.bin_size = 1.0
+            self.nbx = self.nby = 1
+            return
+        lo = cells[:, :2].amin(dim=0).cpu().numpy()
+        hi = cells[:, :2].amax(dim=0).cpu().numpy()
+        self._bin_geometry(lo[0], hi[0], lo[1], hi[1])
+        nb = self.nbx * self.nby
+        counts = torch.zeros(nb, dtype=torch.int32, device=dev)
+        args = (cells.data_ptr(), self.n_cells, self.bin_x0, self.bin_y0, self.bin_size, self.nbx, self.nby)
+        _lib.check(self.lib.mlb_cells_bin(*args, 0, counts.data_ptr(), None, None, None, None, _stream_ptr()), "mlb_cells_bin")
+        bin_start = torch.zeros(nb + 1, dtype=torch.int32, device=dev)
+        bin_start[1:] = torch.cumsum(counts, dim=0, dtype=torch.int32)
+        cursor = bin_start[:-1].clone()
+        cx = torch.empty(self.n_cells, dtype=torch.float64, device=dev)
+        cy = torch.empty(self.n_cells, dtype=torch.float64, device=dev)
+        which = torch.empty(self.n_cells, dtype=torch.int32, device=dev)
+        orig = torch.empty(self.n_cells, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.mlb_cells_bin(*args, 1, cursor.data_ptr(), cx.data_ptr(), cy.data_ptr(), which.data_ptr(),
+                                          orig.data_ptr(), _stream_ptr()), "mlb_cells_bin")
+        self._keep.update(cell_x=cx, cell_y=cy, cell_which=which, cell_orig=orig, bin_start=bin_start)
+
+    def _tie_tables(self):
+        """Host copies needed only when exact nearest-cell ties are resolved the reference's way."""
+        if getattr(self, "_cells_host", None) is None:
+            self._cells_host = self._cells_dev[:, 0:2].cpu().numpy().copy()
+            orig = self._keep['cell_orig'].cpu().numpy().astype(np.int64)
+            self._sorted_pos = np.empty(self.n_cells, dtype=np.int64)
+            self._sorted_pos[orig] = np.arange(self.n_cells)
+
     def _pack_struct(self, pack, dev_arrays):
         s = _PackC()
         s.axes, s.values, s.values_f32, s.orders, s.order_map = (t.data_ptr() for t in dev_arrays)
@@ -352,6 +397,7 @@ class NearfieldPlan:
         self.last_tie_classes = (int(in_center.sum()), int((~in_center).sum()))
         if in_center.any():
             from scipy.spatial import cKDTree            # the reference's own dependency (nearfield.py:17)
+            self._tie_tables()
             if getattr(self, "_tree", None) is None:
                 self._tree = cKDTree(self._cells_host)
             winner = self._tree.query(np.stack((px[in_center], py[in_center]), axis=1))[1]      # original row numbers
