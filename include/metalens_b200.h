@@ -172,6 +172,15 @@ int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols,
                        const double *ux, const double *uy, double amp_scale, double wavelength, double n_glass,
                        double Z0, float *P, int ldp, int accumulate, double *block_sums,
                        mlb_c64 *const *h_Fhat, int ldf, void *stream);
+/* mlb_fft_cols_power + total_P in one call: total[0] = total_scale * (sum of the block sums), nearfield_farfield.py:74.
+ * Where the pass is a single launch of 256-thread CTAs (radix-16 engine, 1024..2048-point columns) its last CTA adds the
+ * block sums itself -- same fixed order as mlb_sum_f64, one launch less on the critical path of a pipelined step --,
+ * otherwise mlb_sum_f64 follows.  done_counter: one zeroed uint32 of device memory per concurrently running call (left
+ * zero again). */
+int mlb_fft_cols_power_total(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw, int out_roll,
+                             const double *ux, const double *uy, double amp_scale, double wavelength, double n_glass,
+                             double Z0, float *P, int ldp, int accumulate, double *block_sums, double *total,
+                             double total_scale, void *done_counter, void *stream);
 /* Named integer tuning options (defaults are the B200-tuned values):
  *   rows_ctas_per_sm     resident CTAs per SM of the TMA-fed row pass, 0 = as many as fit (default)
  *   rows_l2_evict_first  1 (default) = stream the aperture through L2 with an evict-first policy

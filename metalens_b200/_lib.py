@@ -49,6 +49,9 @@ SIGNATURES = {
     "mlb_fft_cols_power": (C.c_int, [_PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, _PP, C.c_int, C.c_void_p]),
+    "mlb_fft_cols_power_total": (C.c_int, [_PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "mlb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "mlb_get_option": (C.c_int, [C.c_char_p]),
     "mlb_ff_epilogue_blocks": (C.c_int, [C.c_int, C.c_int]),

@@ -45,6 +45,24 @@ __device__ __forceinline__ T pick4(T const (&p)[4], unsigned i) {
     return i == 0 ? p[0] : (i == 1 ? p[1] : (i == 2 ? p[2] : p[3]));
 }
 
+// Sum of n doubles in ONE fixed order by a 256-thread block (thread t takes in[t], in[t + 256], ...; xor-shuffle tree per
+// warp; the 8 warp sums added in order).  Shared by mlb_sum_f64 and by the kernels that finish total_P themselves, so a
+// total does not depend on which of them formed it.  ws: 8 doubles of shared memory.  Result valid in thread 0.
+__device__ __forceinline__ double ordered_sum_256(const double *__restrict__ in, int n, double *ws) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) v += __ldcg(in + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += ws[w];
+    }
+    return s;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- mbarrier / bulk-copy (1-D TMA) PTX wrappers ---------------------------

@@ -234,21 +234,11 @@ __global__ void __launch_bounds__(EPI_THREADS) cone_power_kernel(const T *__rest
     }
 }
 
-__global__ void __launch_bounds__(1024) sum_f64_kernel(const double *__restrict__ in, int n, double scale,
-                                                       double *__restrict__ out) {
-    __shared__ double ws[32];
-    double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) v += in[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        v = ws[threadIdx.x];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) out[0] = v * scale;
-    }
+__global__ void __launch_bounds__(256) sum_f64_kernel(const double *__restrict__ in, int n, double scale,
+                                                      double *__restrict__ out) {
+    __shared__ double ws[8];
+    const double s = ordered_sum_256(in, n, ws);
+    if (threadIdx.x == 0) out[0] = s * scale;
 }
 
 }  // namespace mlb
@@ -311,6 +301,6 @@ extern "C" int mlb_cone_power(const void *P, int ldp, int p_is_double, const dou
 
 extern "C" int mlb_sum_f64(const double *in, int n, double scale, double *out, void *stream) {
     MLB_REQUIRE(in && out && n >= 0, "mlb_sum_f64: bad arguments");
-    mlb::sum_f64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, n, scale, out);
+    mlb::sum_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(in, n, scale, out);
     return mlb::check_launch("mlb_sum_f64");
 }

@@ -1693,10 +1693,12 @@ extern "C" int mlb_fft_cols_power_blocks(int N, int n_cols) {
     return cl ? (n_cols + cl - 1) / cl : 0;
 }
 
-extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw,
-                                  int out_roll, const double *ux, const double *uy, double amp_scale,
-                                  double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
-                                  double *block_sums, mlb_c64 *const *h_Fhat, int ldf, void *stream) {
+static int fft_cols_power_impl(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw,
+                               int out_roll, const double *ux, const double *uy, double amp_scale,
+                               double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
+                               double *block_sums, mlb_c64 *const *h_Fhat, int ldf, void *stream,
+                               double *total, double total_scale, unsigned int *done, bool *total_done) {
+    if (total_done) *total_done = false;
     MLB_REQUIRE(h_in && tw && ux && uy && P, "mlb_fft_cols_power: NULL pointer");
     if (mlb::g_cols_engine == 1 && !h_Fhat && N >= (1 << mlb::g_r16_min_lg)) {
         int lgSub, cl16, groups;
@@ -1718,8 +1720,13 @@ extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, 
         r.roll = out_roll;
         const int xblocks = (n_cols + cl16 - 1) / cl16;
         r.bs_stride = xblocks; r.bs_off = 0;
+        r.total = nullptr; r.total_scale = 0.0; r.done = nullptr; r.n_sums = 0;
         if (groups == 1) {
             r.in_gs = 0; r.in_rs = 1; r.out_gs = 0; r.out_rs = 1;
+            if (total && done && block_sums) {                      // the last CTA finishes total_P (256-thread CTAs)
+                r.total = total; r.total_scale = total_scale; r.done = done; r.n_sums = xblocks;
+                if (total_done) *total_done = true;
+            }
             return mlb::r16_cols_power_dispatch(lgSub, r, 1, st16);
         }
         // 16 x B decomposition, strip by strip: the first pass of every strip writes into the first strip of the
@@ -1795,4 +1802,27 @@ extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, 
     }
 #undef MLB_CP_LAUNCH
     return mlb::check_launch("mlb_fft_cols_power");
+}
+
+extern "C" int mlb_fft_cols_power(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw,
+                                  int out_roll, const double *ux, const double *uy, double amp_scale,
+                                  double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
+                                  double *block_sums, mlb_c64 *const *h_Fhat, int ldf, void *stream) {
+    return fft_cols_power_impl(h_in, ld_in, N, n_cols, tw, out_roll, ux, uy, amp_scale, wavelength, n_glass, Z0, P, ldp,
+                               accumulate, block_sums, h_Fhat, ldf, stream, nullptr, 0.0, nullptr, nullptr);
+}
+
+extern "C" int mlb_fft_cols_power_total(const mlb_c64 *const *h_in, int ld_in, int N, int n_cols, const mlb_c64 *tw,
+                                        int out_roll, const double *ux, const double *uy, double amp_scale,
+                                        double wavelength, double n_glass, double Z0, float *P, int ldp, int accumulate,
+                                        double *block_sums, double *total, double total_scale, void *done_counter,
+                                        void *stream) {
+    MLB_REQUIRE(block_sums && total && done_counter, "mlb_fft_cols_power_total: NULL block_sums / total / counter");
+    bool fused = false;
+    if (int rc = fft_cols_power_impl(h_in, ld_in, N, n_cols, tw, out_roll, ux, uy, amp_scale, wavelength, n_glass, Z0, P,
+                                     ldp, accumulate, block_sums, nullptr, 0, stream, total, total_scale,
+                                     reinterpret_cast<unsigned int *>(done_counter), &fused))
+        return rc;
+    if (fused) return MLB_OK;
+    return mlb_sum_f64(block_sums, mlb_fft_cols_power_blocks(N, n_cols), total_scale, total, stream);
 }

@@ -304,6 +304,13 @@ struct R16PowerArgs {
     int ld_in, ldp, n_cols, lgNtot, accumulate;
     int in_gs, in_rs, out_gs, out_rs, roll;
     int bs_stride, bs_off;            // block_sums[blockIdx.y * bs_stride + bs_off + blockIdx.x] (column strips)
+    // total != NULL (single-launch shapes only): the last CTA to finish sums the n_sums block sums in the fixed order of
+    // ordered_sum_256 and writes total[0] = sum * total_scale -- total_P (:74) without a second launch.  done: zeroed
+    // device counter, left zero again.
+    double *total;
+    double total_scale;
+    unsigned int *done;
+    int n_sums;
 };
 
 template <int LGN, int CL>
@@ -378,7 +385,8 @@ __global__ void __launch_bounds__(CL * (1 << (LGN - 4)), 2) fft16_cols_power_ker
     if (a.block_sums) {                                            // :74 total_P over finite bins
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        __shared__ double ws[T / 32];
+        __shared__ double ws[T / 32 < 8 ? 8 : T / 32];
+        __shared__ int is_last;
         if ((tid & 31) == 0) ws[tid >> 5] = sum;
         __syncthreads();
         if (tid == 0) {
@@ -386,6 +394,22 @@ __global__ void __launch_bounds__(CL * (1 << (LGN - 4)), 2) fft16_cols_power_ker
 #pragma unroll
             for (int w = 0; w < T / 32; ++w) s += ws[w];
             a.block_sums[(size_t)blockIdx.y * a.bs_stride + a.bs_off + blockIdx.x] = s;
+            is_last = 0;
+            if (a.total) {
+                __threadfence();
+                is_last = (atomicAdd(a.done, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+            }
+        }
+        if constexpr (T == 256) {
+            __syncthreads();
+            if (is_last) {                                         // every block sum is visible: finish total_P here
+                __threadfence();
+                const double s = ordered_sum_256(a.block_sums, a.n_sums, ws);
+                if (tid == 0) {
+                    a.total[0] = s * a.total_scale;
+                    *a.done = 0u;
+                }
+            }
         }
     }
 }

@@ -200,7 +200,8 @@ class FarfieldPlan:
             for t, n in ((self.tw1, K1), (self.tw2, K2)):
                 _lib.check(self.lib.mlb_fft_twiddle(n, t.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
             self.AxT = self.Ay = None
-            self.work_counter = torch.zeros(2, dtype=torch.int32, device=dev)     # dynamic row distribution (mlb_fft_rows_ws)
+            # [0:2] dynamic row distribution (mlb_fft_rows_ws), [2] finished-CTA counter of the fused column+power pass
+            self.work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
             # fused column pass + power: measured faster than column pass + epilogue up to 1024-point columns
             # (above that the fused kernel's register footprint costs more than the saved round trip)
             self.fused = bool(self._want_fused and not self.two_pass_t and self.p_dtype == torch.float32
@@ -399,16 +400,14 @@ class FarfieldPlan:
             out.append(("fold_fft_rows" if (self.sx > 1 or self.sy > 1) else "fft_rows", rows,
                         32 * (self.Mx * self.My + Rx * Ry), 4 * 5.0 * Rx * Ry * math.log2(Ry)))
             if fused:
-                def cols_power(keep=k4, accumulate=accumulate):   # column pass + radiated power in one kernel
-                    nb = lib.mlb_fft_cols_power_blocks(Rx, Ry)
-                    _lib.check(lib.mlb_fft_cols_power(pw, ldw, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx,
-                                                      self.d_ux.data_ptr(), self.d_uy.data_ptr(), self.dxp * self.dyp,
-                                                      self.wavelength, self.n_glass, Z0, self.P.data_ptr(),
-                                                      self.P.shape[1], 1 if accumulate else 0,
-                                                      self.block_sums.data_ptr(), None, 0, _stream_ptr()),
-                               "mlb_fft_cols_power")
-                    _lib.check(lib.mlb_sum_f64(self.block_sums.data_ptr(), nb, self.dux * self.duy,
-                                               self.total.data_ptr(), _stream_ptr()), "mlb_sum_f64")
+                def cols_power(keep=k4, accumulate=accumulate):   # column pass + radiated power + total_P in one call
+                    _lib.check(lib.mlb_fft_cols_power_total(pw, ldw, Rx, Ry, self.tw1.data_ptr(), (h1 // self.sx) % Rx,
+                                                            self.d_ux.data_ptr(), self.d_uy.data_ptr(), self.dxp * self.dyp,
+                                                            self.wavelength, self.n_glass, Z0, self.P.data_ptr(),
+                                                            self.P.shape[1], 1 if accumulate else 0,
+                                                            self.block_sums.data_ptr(), self.total.data_ptr(),
+                                                            self.dux * self.duy, self.work_counter.data_ptr() + 8,
+                                                            _stream_ptr()), "mlb_fft_cols_power_total")
                     return self.P, self.total
                 out.append(("fft_cols_power", cols_power, (32 + 4) * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))
                 return out
