@@ -76,11 +76,13 @@ class SlabFarfield:
     """Far field of one (Mx, My) aperture on the every-`stride`-th-FFT-bin grid, computed by `world` ranks.
 
     peers : a SymmetricPeers (one process per GPU) or a VirtualPeers.view(rank) (virtual ranks on one device).
+    gather_ctas: CTAs of the pushed all-gather of P; it is on the critical path with nothing else running, so it gets
+    most of the SMs (the tile exchange of sharding.py, which runs under an HBM-bound kernel, uses few).
     run(fields) takes THIS rank's rows of the four fields -- complex64 (len(x_rows), My) each, row order
     ``self.x_rows`` -- and returns (P (K1, K2) float32 complete on every rank, total_P device scalar).
     """
 
-    def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride, peers, name="slab", gather_ctas=0):
+    def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride, peers, name="slab", gather_ctas=128):
         self.lib = lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
