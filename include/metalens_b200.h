@@ -141,14 +141,6 @@ int mlb_fft_rows_can_transpose(int N);
 int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
                  int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
                  int batch, void *stream);
-/* mlb_fft_rows with an 8-byte device work area owned by the caller (two uint32 counters, zero before the FIRST call;
- * the kernel leaves them zero again; one area per concurrently running call): the TMA-fed persistent kernel then
- * hands rows to its CTAs dynamically instead of by a fixed stride, so CTAs that start late (SMs still busy with
- * another stream's kernels) do not delay the pass.
- * NULL, or a path other than the TMA-fed kernel, behaves exactly like mlb_fft_rows. */
-int mlb_fft_rows_ws(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows, int N,
-                    int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll, int transpose_out,
-                    int batch, void *work_counter, void *stream);
 /* Same along columns:  out_b[(q + out_roll) % N][c] = sum_p in_b[p][c] e^{-2 pi i q p / N}.  In-place allowed
  * for power-of-two N <= 2048 and every other length; for power-of-two N >= 4096 the transform is a two-pass
  * decomposition that uses the INPUT buffer as scratch (it is overwritten) and needs out != in; for other lengths
@@ -191,16 +183,13 @@ int mlb_fft_cols_power_total(const mlb_c64 *const *h_in, int ld_in, int N, int n
  *                        points) everywhere, 2 (default) = radix-16 without a fold, TMA-fed fold+FFT kernel with one
  *   cols_engine          0 = radix-4 column kernels, 1 (default) = radix-16 register kernels (256..8192 points; 4096 and
  *                        8192 as 16 x 256/512 in two passes, the first in place on the INPUT buffer)
- *   mixed_engine         non-power-of-two lengths (the good_fft_number() sizes): 1 (default) = big-radix engine (radices
- *                        up to 16 in registers, long columns as A x B in two passes, the first in place on the INPUT
- *                        buffer unless the call is in place), 0 = radix 2..5 shared-memory kernels
- *   mixed_registers      1 (default) = one-butterfly-per-thread register kernels of that engine where they pay (long
+ *   mixed_registers      non-power-of-two lengths (the good_fft_number() sizes; big-radix engine: radices up to 16 in registers,
+ *                        long columns as A x B in two passes, the first in place on the INPUT buffer unless the call is
+ *                        in place): 1 (default) = one-butterfly-per-thread register kernels where they pay (long
  *                        transforms that keep >= 80 % of a CTA's threads busy), 2 = wherever they apply, 0 = never
  *   mixed_occupancy      resident CTAs per SM those kernels are compiled for: 0 (default: rows 2, columns 4), 2..4
  *   cols_strip_mb        two-pass (>= 4096-point) column transforms run strip by strip, strips of this many MB of all
  *                        fields (intermediate stays in L2); 0 (default) = one strip
- *   rows_dynamic         1 = mlb_fft_rows_ws uses its work counter (kernel alone +2.5 %, pipelined items -12 %: measured),
- *                        0 (default) = fixed stride
  *   r16_min_lg           the radix-16 kernels serve lengths from 2^this up (default 10; 8..13), the radix-4 ones below
  *   r16_occupancy        resident CTAs per SM the radix-16 kernels are compiled for: 0 (default: rows 4, columns 3), 2..4
  * mlb_get_option returns -1 for an unknown name. */

@@ -41,8 +41,6 @@ SIGNATURES = {
     "mlb_fft_rows": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mlb_fft_mixed_plan": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
-    "mlb_fft_rows_ws": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_fft_cols": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p]),
     "mlb_fft_cols_power_blocks": (C.c_int, [C.c_int, C.c_int]),

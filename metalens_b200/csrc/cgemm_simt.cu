@@ -150,10 +150,10 @@ template <int TM, int TN, int BK, int STAGES>
 static int launch_cgemm(const CgemmArgs &a, int batch, cudaStream_t stream) {
     using Cfg = CgemmCfg<TM, TN, BK, STAGES>;
     auto kern = cgemm_tn_kernel<TM, TN, BK, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0; const unsigned long long devbit_ = mlb::device_bit();
+    if (!(attr_set & devbit_)) {
         MLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
+        attr_set |= devbit_;
     }
     dim3 grid((a.cols + Cfg::BN - 1) / Cfg::BN, (a.rows + Cfg::BM - 1) / Cfg::BM, batch);
     kern<<<grid, 256, Cfg::SMEM, stream>>>(a);

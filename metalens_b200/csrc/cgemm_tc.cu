@@ -333,10 +333,10 @@ extern "C" int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, 
         a.out_hi[b] = h_out_hi[s];
         a.out_lo[b] = (mode == 1) ? h_out_lo[s] : nullptr;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0; const unsigned long long devbit_ = mlb::device_bit();
+    if (!(attr_set & devbit_)) {
         MLB_CUDA(cudaFuncSetAttribute(mlb::cgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlb::TC_SMEM));
-        attr_set = true;
+        attr_set |= devbit_;
     }
     a.ldo = ldo; a.rows = rows; a.cols_c = cols_c;
     a.k_blocks = (K + mlb::TC_BK - 1) / mlb::TC_BK; a.mode = mode;

@@ -63,6 +63,14 @@ __device__ __forceinline__ double ordered_sum_256(const double *__restrict__ in,
     return s;
 }
 
+// one bit per CUDA device: the "function attribute already set" flags are kept per device, not per process (a process
+// that uses several GPUs must raise the dynamic shared-memory limit of a kernel on each of them)
+inline unsigned long long device_bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ULL << (dev & 63);
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- mbarrier / bulk-copy (1-D TMA) PTX wrappers ---------------------------

@@ -15,8 +15,8 @@
 //   * fftshift of input and output is index arithmetic ("rolls") at load/store time;
 //   * twiddles come from tables built with float64 phases, re-ordered per Stockham stage so that the
 //     shared-memory reads are conflict-free.
-// The kernels of this file serve powers of two (index math is shifts and masks) plus the first-generation
-// radix 2..5 kernels kept behind the option mixed_engine = 0.
+// The kernels of this file serve powers of two (index math is shifts and masks); the first-generation radix 2..5
+// mixed kernels and the counter-driven row distribution of round 1 were measured slower and have been removed.
 #include <math_constants.h>
 
 #include <string>
@@ -103,7 +103,6 @@ struct FftArgs {
     float2 *out[4];
     const float2 *tw;
     int ld_in, ld_out, lgN, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2, plain_loader, transpose_out, evict_first;
-    unsigned int *work_counter;       // TMA-fed row pass: two zeroed device counters (next item, finished CTAs) or NULL
 };
 
 // Distributed 2-D transform (mlb_fft_rows_scatter): output row r of this rank is row (out_row0 + r) mod rows_total of
@@ -213,10 +212,10 @@ __device__ __forceinline__ int fft_ct(float2 *buf0, float2 *buf1, const float2 *
 // mbarrier transaction counts); 256 consumer threads add the segments into registers as they land, then run
 // the row FFT and store the row.  The producer keeps prefetching the next rows while the consumers are in
 // their butterfly stages, so loads stay in flight all the time (the thread-issued loader loses ~20 % of the
-// HBM bandwidth to that phase alternation).  CTAs are persistent; the producer draws (field, row) work items
-// from a device counter when the caller provides one (a CTA that starts late -- its SM still busy with the
-// previous item's column pass on another stream -- then simply takes fewer rows), else strides over them; it
-// hands the item number to the consumers through the slot of the item's first segment (-1 = no more work).
+// HBM bandwidth to that phase alternation).  CTAs are persistent and stride over the (field, row) work items
+// (drawing them from a device counter was built in round 1 and measured slower in the pipelined step: removed);
+// the producer hands the item number to the consumers through the slot of the item's first segment (-1 = no
+// more work).
 constexpr int TMA_CONSUMERS = 256;
 
 template <int LGN, int RING_KB = 64>
@@ -256,15 +255,8 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1) fft_rows_tma_kernel(con
             long long g = 0;
             const uint64_t pol = l2_evict_first_policy();
             for (int seq = 0;; ++seq) {
-                int w = a.work_counter ? (int)atomicAdd(a.work_counter, 1u) : blockIdx.x + seq * (int)gridDim.x;
-                if (w >= work) {
-                    w = -1;
-                    // every CTA draws exactly one number >= work; the last one to do so re-arms the two counters
-                    if (a.work_counter && atomicAdd(a.work_counter + 1, 1u) == gridDim.x - 1) {
-                        a.work_counter[0] = 0u;
-                        a.work_counter[1] = 0u;
-                    }
-                }
+                int w = blockIdx.x + seq * (int)gridDim.x;
+                if (w >= work) w = -1;
                 const int f = w < 0 ? 0 : w / a.other, r = w < 0 ? 0 : w - f * a.other;
                 int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
                 const float2 *src = pick4(a.in, f);
@@ -770,20 +762,7 @@ __global__ void __launch_bounds__(256) fft_cols_sub_kernel(const FftSubArgs a) {
     }
 }
 
-// ---- mixed-radix passes: any length N = 2^a 3^b 5^c <= 8192 ---------------------------------------------
-// The reference sizes its aperture with good_fft_number() (nearfield.py:30-36: only factors 2, 3, 5), so
-// the typical grid is NOT a power of two (e.g. 675 = 3^3 5^2).  These kernels run the same Stockham
-// autosort scheme with radix-4/2/3/5 stages chosen at run time; index math is integer division instead
-// of shifts, which is why the power-of-two kernels above stay separate.
-struct MixArgs {
-    const float2 *in[4];
-    float2 *out[4];
-    const float2 *tw;                 // plain table W_N^t, t < N
-    int ld_in, ld_out, N, other, lanes, in_roll_r, in_roll_c, out_roll, s1, s2;
-    int nstage;
-    int radix[16];
-};
-
+// ---- small in-register DFTs shared with the big-radix mixed engine (fftmix.cuh) ----------------------------------
 template <int R>
 __device__ __forceinline__ void dft_small(float2 (&v)[R]) {
     if (R == 2) {
@@ -814,110 +793,6 @@ __device__ __forceinline__ void dft_small(float2 (&v)[R]) {
         v[4] = csubf(m1, n1);
         v[2] = caddf(m2, n2);
         v[3] = csubf(m2, n2);
-    }
-}
-
-// one Stockham stage, radix R, sub-length Ns, `lanes` transforms at lane*pitch
-template <int R>
-__device__ __forceinline__ void mixed_stage(const float2 *__restrict__ x, float2 *__restrict__ y, int N, int Ns, int lanes,
-                                            int pitch, const float2 *__restrict__ tw) {
-    const int per = N / R, total = per * lanes, tstep = N / (Ns * R);
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int lane = idx / per, j = idx - lane * per;
-        const int k = j % Ns;
-        const int base_out = (j - k) * R + k;
-        const float2 *xl = x + lane * pitch;
-        float2 *yl = y + lane * pitch;
-        float2 v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            v[r] = xl[j + r * per];
-            if (r > 0 && Ns > 1) v[r] = cmulf(v[r], __ldg(tw + r * k * tstep));
-        }
-        dft_small<R>(v);
-#pragma unroll
-        for (int r = 0; r < R; ++r) yl[base_out + r * Ns] = v[r];
-    }
-}
-
-__device__ __forceinline__ int mixed_fft(float2 *buf0, float2 *buf1, const MixArgs &a, int lanes, int pitch) {
-    int cur = 0, Ns = 1;
-    for (int s = 0; s < a.nstage; ++s) {
-        __syncthreads();
-        const float2 *x = cur ? buf1 : buf0;
-        float2 *y = cur ? buf0 : buf1;
-        switch (a.radix[s]) {
-            case 2: mixed_stage<2>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
-            case 3: mixed_stage<3>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
-            case 4: mixed_stage<4>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
-            default: mixed_stage<5>(x, y, a.N, Ns, lanes, pitch, a.tw); break;
-        }
-        Ns *= a.radix[s];
-        cur ^= 1;
-    }
-    __syncthreads();
-    return cur;
-}
-
-// rows: `lanes` rows per CTA; loader folds s1 x s2 aliased copies and applies the input fftshift
-__global__ void __launch_bounds__(256) fft_rows_mixed_kernel(const MixArgs a) {
-    extern __shared__ __align__(16) float2 fsm[];
-    const int N = a.N, L = a.lanes;
-    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * N;
-    const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
-    float2 *__restrict__ out = pick4(a.out, blockIdx.y);
-    const int row0 = blockIdx.x * L, total = L * N;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int lane = idx / N, n = idx - lane * N;
-        const int r = row0 + lane;
-        float re = 0.f, im = 0.f;
-        if (r < a.other) {
-            int rs = r - a.in_roll_r; if (rs < 0) rs += a.other;
-            int cs = n - a.in_roll_c; if (cs < 0) cs += N;
-            for (int t1 = 0; t1 < a.s1; ++t1) {
-                const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in + cs;
-                for (int t2 = 0; t2 < a.s2; ++t2) {
-                    const float2 v = __ldcs(row + (size_t)t2 * N);
-                    re += v.x; im += v.y;
-                }
-            }
-        }
-        buf0[idx] = make_float2(re, im);
-    }
-    const int cur = mixed_fft(buf0, buf1, a, L, N);
-    const float2 *res = cur ? buf1 : buf0;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int lane = idx / N, n = idx - lane * N;
-        const int r = row0 + lane;
-        if (r < a.other) {
-            int q = n - a.out_roll; if (q < 0) q += N;
-            out[(size_t)r * a.ld_out + n] = res[lane * N + q];
-        }
-    }
-}
-
-// columns: `lanes` adjacent columns per CTA, transposed into [lane][n] shared-memory rows
-__global__ void __launch_bounds__(256) fft_cols_mixed_kernel(const MixArgs a) {
-    extern __shared__ __align__(16) float2 fsm[];
-    const int N = a.N, L = a.lanes, P = N + 1;
-    float2 *buf0 = fsm, *buf1 = fsm + (size_t)L * P;
-    const float2 *__restrict__ in = pick4(a.in, blockIdx.y);
-    float2 *__restrict__ out = pick4(a.out, blockIdx.y);
-    const int c0 = blockIdx.x * L, total = L * N;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int n = idx / L, lane = idx - n * L;
-        const int c = c0 + lane;
-        buf0[lane * P + n] = (c < a.other) ? in[(size_t)n * a.ld_in + c] : make_float2(0.f, 0.f);
-    }
-    const int cur = mixed_fft(buf0, buf1, a, L, P);
-    const float2 *res = cur ? buf1 : buf0;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int n = idx / L, lane = idx - n * L;
-        const int c = c0 + lane;
-        if (c < a.other) {
-            int q = n - a.out_roll; if (q < 0) q += N;
-            out[(size_t)n * a.ld_out + c] = res[lane * P + q];
-        }
     }
 }
 
@@ -965,15 +840,11 @@ static int g_rows_evict_first = 1;     // TMA row pass: stream the aperture thro
 static int g_cols_strip_mb = 0;        // two-pass column transforms (>= 4096 points): run them strip by strip, strips of this many MB (so the
                                        // intermediate stays in L2); 0 = one strip (default: measured faster on B200, the per-strip launches cost
                                        // more than the saved HBM round trip)
-static int g_rows_dynamic = 0;         // TMA row pass: 1 = draw rows from the caller's work counter (mlb_fft_rows_ws).  Measured on B200
-                                       // (scripts/ab_rows_dynamic.py): the kernel alone gains 2.5 % (90.4 vs 93.0 us at cfg3), but the two-stream
-                                       // item pipeline loses 12 % (371 vs 331 us per step) -- default off
 static int g_r16_min_lg = 10;          // radix-16 kernels from 2^this points up (8..13): below 1024 points the radix-4 kernels launch more
                                        // CTAs and measure faster on B200 (cfg2 / the 256-point sweep of bench.py)
 static int g_mixed_occ = 0;            // register kernels of the big-radix engine: resident CTAs per SM they are compiled for
                                        // (2..4; 0 = default: rows 2, columns 4 -- measured on B200, scripts/allbins_kernels.py)
 static int g_mixed_reg = 1;            // big-radix engine: use the one-butterfly-per-thread register kernels where they apply
-static int g_mixed_engine = 1;         // non-power-of-two lengths: 0 = radix 2..5 shared-memory kernels, 1 = big-radix engine (fftmix.cuh; default)
 static int g_cols_power_wide = -1;     // fused column+power pass: 1 = 4096-point tiles / 1024 threads, 0 = 2048 / 512,
                                        // -1 = by length (wide from 1024 points up: measured faster on B200)
 static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
@@ -987,13 +858,6 @@ static int factor_235(int n, int *radix) {
     while (n % 3 == 0) { radix[ns++] = 3; n /= 3; }
     while (n % 5 == 0) { radix[ns++] = 5; n /= 5; }
     return (n == 1 && ns <= 16) ? ns : 0;
-}
-template <typename A>
-static int fill_mixed(MixArgs &m, const A &a, int N) {
-    for (int b = 0; b < 4; ++b) { m.in[b] = a.in[b]; m.out[b] = a.out[b]; }
-    m.N = N;
-    m.nstage = factor_235(N, m.radix);
-    return m.nstage;
 }
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 constexpr int FFT_MAX_N = 8192;                     // 2 x 8192 x 8 B = 128 KB of shared memory
@@ -1039,14 +903,12 @@ extern "C" int mlb_set_option(const char *name, int value) {
     else if (n == "rows_l2_evict_first") mlb::g_rows_evict_first = value ? 1 : 0;
     else if (n == "rows_engine") { MLB_REQUIRE(value >= 0 && value <= 2, "rows_engine: 0..2"); mlb::g_rows_engine = value; }
     else if (n == "r16_occupancy") { MLB_REQUIRE(value == 0 || (value >= 2 && value <= 4), "r16_occupancy: 0, 2..4"); mlb::g_r16_occ = value; }
-    else if (n == "rows_dynamic") mlb::g_rows_dynamic = value ? 1 : 0;
     else if (n == "r16_min_lg") { MLB_REQUIRE(value >= 8 && value <= 13, "r16_min_lg: 8..13"); mlb::g_r16_min_lg = value; }
     else if (n == "cols_engine") { MLB_REQUIRE(value >= 0 && value <= 1, "cols_engine: 0..1"); mlb::g_cols_engine = value; }
     else if (n == "rows_ring_kb") { MLB_REQUIRE(value == 64 || value == 128, "rows_ring_kb: 64 or 128"); mlb::g_rows_ring_kb = value; }
     else if (n == "cols_power_wide") mlb::g_cols_power_wide = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "mixed_registers") { MLB_REQUIRE(value >= 0 && value <= 2, "mixed_registers: 0..2"); mlb::g_mixed_reg = value; }
     else if (n == "mixed_occupancy") { MLB_REQUIRE(value == 0 || (value >= 2 && value <= 4), "mixed_occupancy: 0, 2..4"); mlb::g_mixed_occ = value; }
-    else if (n == "mixed_engine") { MLB_REQUIRE(value >= 0 && value <= 1, "mixed_engine: 0..1"); mlb::g_mixed_engine = value; }
     else if (n == "cols_strip_mb") { MLB_REQUIRE(value >= 0 && value <= 4096, "cols_strip_mb: 0..4096"); mlb::g_cols_strip_mb = value; }
     else MLB_REQUIRE(false, "mlb_set_option: unknown option '%s'", name);
     return MLB_OK;
@@ -1061,11 +923,9 @@ extern "C" int mlb_get_option(const char *name) {
     if (n == "rows_engine") return mlb::g_rows_engine;
     if (n == "cols_engine") return mlb::g_cols_engine;
     if (n == "r16_min_lg") return mlb::g_r16_min_lg;
-    if (n == "rows_dynamic") return mlb::g_rows_dynamic;
     if (n == "r16_occupancy") return mlb::g_r16_occ;
     if (n == "cols_power_wide") return mlb::g_cols_power_wide;
     if (n == "cols_strip_mb") return mlb::g_cols_strip_mb;
-    if (n == "mixed_engine") return mlb::g_mixed_engine;
     if (n == "mixed_registers") return mlb::g_mixed_reg;
     if (n == "mixed_occupancy") return mlb::g_mixed_occ;
     return -1;
@@ -1110,8 +970,8 @@ static int mix2_plan(Mix2Args &m, int N) {
 static size_t mix2_smem(int N, int lanes) { return 2 * (size_t)lanes * (mixpad(N, 4) + 1) * sizeof(float2); }
 constexpr size_t MIX2_SMEM_MAX = 2 * (size_t)(FFT_MAX_N + (FFT_MAX_N >> 4) + 1) * sizeof(float2);   // one 8192-point transform
 static int mix2_set_smem() {
-    static bool set_ = false;
-    if (!set_) {
+    static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();
+    if (!(set_ & devbit_)) {
         MLB_CUDA(cudaFuncSetAttribute(mix2_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX));
         MLB_CUDA(cudaFuncSetAttribute(mix2_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX));
         MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
@@ -1120,7 +980,7 @@ static int mix2_set_smem() {
         MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
         MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
         MLB_CUDA(cudaFuncSetAttribute(mix2_reg_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MIX2_SMEM_MAX / 2));
-        set_ = true;
+        set_ |= devbit_;
     }
     return MLB_OK;
 }
@@ -1178,12 +1038,10 @@ extern "C" int mlb_fft_rows_can_transpose(int N) {
 
 static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
                          int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
-                         int transpose_out, int batch, unsigned int *work_counter, void *stream,
-                         const mlb::RowScatter *scatter = nullptr) {
+                         int transpose_out, int batch, void *stream, const mlb::RowScatter *scatter = nullptr) {
     mlb::FftArgs a;
     static const mlb::RowScatter no_scatter = {};
     const mlb::RowScatter &sc = scatter ? *scatter : no_scatter;
-    a.work_counter = nullptr;
     if (int rc = mlb::fill_args(a, h_in, h_out, batch, "mlb_fft_rows")) return rc;
     int radix_probe[16];
     MLB_REQUIRE(N >= 2 && N <= mlb::FFT_MAX_N && mlb::factor_235(N, radix_probe) > 0,
@@ -1204,50 +1062,32 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
     }
     if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
         MLB_REQUIRE(!transpose_out, "mlb_fft_rows: transposed output needs a power-of-two length");
-        if (mlb::g_mixed_engine == 1) {
-            mlb::Mix2Args m2;
-            MLB_REQUIRE(mlb::mix2_plan(m2, N) > 0, "mlb_fft_rows: cannot factor %d", N);
-            for (int b = 0; b < 4; ++b) { m2.in[b] = a.in[b]; m2.out[b] = a.out[b]; }
-            m2.tw = a.tw; m2.ld_in = ld_in; m2.ld_out = ld_out; m2.other = n_rows; m2.tw_mul = 1; m2.Ntot = N;
-            m2.in_roll_r = in_roll_r; m2.in_roll_c = in_roll_c; m2.out_roll = out_roll; m2.s1 = s1; m2.s2 = s2;
-            m2.in_gs = m2.in_rs = m2.out_gs = m2.out_rs = m2.roll = 0;
-            int lanes = 1;                           // rows per CTA: ~one butterfly per thread and stage, <= 64 KB
-            while (lanes < 16 && mlb::mix2_smem(N, lanes * 2) <= 64 * 1024 && lanes * 2 <= n_rows && lanes * N < 4096) lanes *= 2;
-            if (int rc = mlb::mix2_set_smem()) return rc;
-            const int mp = mlb::mix2_max_per(m2);
-            int rl = mp <= 256 ? 256 / mp : 0;
-            if (rl > 16) rl = 16;
-            if (rl > n_rows) rl = n_rows;
-            // one butterfly per thread and stage (register variant): long rows that keep >= 80 % of the threads busy
-            if (mlb::g_mixed_reg && rl >= 1 && (mlb::g_mixed_reg == 2 || (N >= 2048 && rl * mp >= 205))) {
-                m2.lanes = rl; m2.lg_lanes = 0;
-                dim3 grid((n_rows + rl - 1) / rl, batch);
-                const size_t sm2 = mlb::mix2_smem(N, rl) / 2;
-                if (mlb::g_mixed_occ == 4) mlb::mix2_reg_kernel<false, 4><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
-                else if (mlb::g_mixed_occ == 3) mlb::mix2_reg_kernel<false, 3><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
-                else mlb::mix2_reg_kernel<false, 2><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
-                return mlb::check_launch("mlb_fft_rows(mixed radix, registers)");
-            }
-            m2.lanes = lanes; m2.lg_lanes = 0;
-            dim3 grid((n_rows + lanes - 1) / lanes, batch);
-            mlb::mix2_rows_kernel<<<grid, 256, mlb::mix2_smem(N, lanes), (cudaStream_t)stream>>>(m2);
-            return mlb::check_launch("mlb_fft_rows(mixed radix)");
+        mlb::Mix2Args m2;
+        MLB_REQUIRE(mlb::mix2_plan(m2, N) > 0, "mlb_fft_rows: cannot factor %d", N);
+        for (int b = 0; b < 4; ++b) { m2.in[b] = a.in[b]; m2.out[b] = a.out[b]; }
+        m2.tw = a.tw; m2.ld_in = ld_in; m2.ld_out = ld_out; m2.other = n_rows; m2.tw_mul = 1; m2.Ntot = N;
+        m2.in_roll_r = in_roll_r; m2.in_roll_c = in_roll_c; m2.out_roll = out_roll; m2.s1 = s1; m2.s2 = s2;
+        m2.in_gs = m2.in_rs = m2.out_gs = m2.out_rs = m2.roll = 0;
+        int lanes = 1;                           // rows per CTA: ~one butterfly per thread and stage, <= 64 KB
+        while (lanes < 16 && mlb::mix2_smem(N, lanes * 2) <= 64 * 1024 && lanes * 2 <= n_rows && lanes * N < 4096) lanes *= 2;
+        if (int rc = mlb::mix2_set_smem()) return rc;
+        const int mp = mlb::mix2_max_per(m2);
+        int rl = mp <= 256 ? 256 / mp : 0;
+        if (rl > 16) rl = 16;
+        if (rl > n_rows) rl = n_rows;
+        // one butterfly per thread and stage (register variant): long rows that keep >= 80 % of the threads busy
+        if (mlb::g_mixed_reg && rl >= 1 && (mlb::g_mixed_reg == 2 || (N >= 2048 && rl * mp >= 205))) {
+            m2.lanes = rl; m2.lg_lanes = 0;
+            dim3 grid((n_rows + rl - 1) / rl, batch);
+            const size_t sm2 = mlb::mix2_smem(N, rl) / 2;
+            if (mlb::g_mixed_occ == 4) mlb::mix2_reg_kernel<false, 4><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+            else if (mlb::g_mixed_occ == 3) mlb::mix2_reg_kernel<false, 3><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+            else mlb::mix2_reg_kernel<false, 2><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+            return mlb::check_launch("mlb_fft_rows(mixed radix, registers)");
         }
-        mlb::MixArgs m;
-        mlb::fill_mixed(m, a, N);
-        m.tw = a.tw; m.ld_in = ld_in; m.ld_out = ld_out; m.other = n_rows;
-        m.in_roll_r = in_roll_r; m.in_roll_c = in_roll_c; m.out_roll = out_roll; m.s1 = s1; m.s2 = s2;
-        int lanes = 1;
-        while (lanes * 2 * N <= 1024 && lanes * 2 <= n_rows) lanes *= 2;
-        m.lanes = lanes;
-        const size_t smem = 2 * (size_t)lanes * N * sizeof(float2);
-        static bool set_ = false;
-        if (!set_) {
-            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * mlb::FFT_MAX_N * 8));
-            set_ = true;
-        }
+        m2.lanes = lanes; m2.lg_lanes = 0;
         dim3 grid((n_rows + lanes - 1) / lanes, batch);
-        mlb::fft_rows_mixed_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(m);
+        mlb::mix2_rows_kernel<<<grid, 256, mlb::mix2_smem(N, lanes), (cudaStream_t)stream>>>(m2);
         return mlb::check_launch("mlb_fft_rows(mixed radix)");
     }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_rows;
@@ -1277,27 +1117,27 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
         constexpr int T = mlb::R16Threads<LG>::value, TR = (1 << LG) >> 4, L = T / TR;                               \
         constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 1;                                                      \
         const size_t smem16 = (size_t)L * PITCH * sizeof(float2);                                                    \
-        static bool set_ = false;                                                                                    \
-        if (!set_) {                                                                                                 \
+        static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();                                                                                    \
+        if (!(set_ & devbit_)) {                                                                                                 \
             MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_rows_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                           (int)smem16));                                                             \
-            set_ = true;                                                                                             \
+            set_ |= devbit_;                                                                                             \
         }                                                                                                            \
         dim3 g16((n_rows + L - 1) / L, batch);                                                                       \
-        static bool set3_ = false, set4_ = false;                                                                    \
+        static unsigned long long set3_ = 0, set4_ = 0;                                                                    \
         if (mlb::g_r16_occ == 3 || ((mlb::g_r16_occ == 2 || mlb::g_r16_occ == 0) && LG == 13)) {                                              \
             constexpr int MB = (LG == 13) ? 2 : 3;                                                                   \
-            if (!set3_) {                                                                                            \
+            if (!(set3_ & devbit_)) {                                                                                            \
                 MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_rows_kernel<LG, MB>,                                        \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
-                set3_ = true;                                                                                        \
+                set3_ |= devbit_;                                                                                        \
             }                                                                                                        \
             mlb::fft16_rows_kernel<LG, MB><<<g16, T, smem16, st>>>(r);                                               \
         } else if ((mlb::g_r16_occ == 4 || mlb::g_r16_occ == 0) && LG < 13) {                                                                 \
-            if (!set4_) {                                                                                            \
+            if (!(set4_ & devbit_)) {                                                                                            \
                 MLB_CUDA(cudaFuncSetAttribute(mlb::fft16_rows_kernel<LG, 4>,                                         \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));            \
-                set4_ = true;                                                                                        \
+                set4_ |= devbit_;                                                                                        \
             }                                                                                                        \
             mlb::fft16_rows_kernel<LG, 4><<<g16, T, smem16, st>>>(r);                                                \
         } else {                                                                                                     \
@@ -1323,11 +1163,11 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
 #define MLB_ROWS_TMA_RING(LG, KB)                                                                                     \
     {                                                                                                                \
         using Cfg = mlb::RowsTmaCfg<LG, KB>;                                                                         \
-        static bool set_ = false;                                                                                    \
-        if (!set_) {                                                                                                 \
+        static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();                                                                                    \
+        if (!(set_ & devbit_)) {                                                                                                 \
             MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_tma_kernel<LG, KB>,                                          \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));             \
-            set_ = true;                                                                                             \
+            set_ |= devbit_;                                                                                             \
         }                                                                                                            \
         int per_sm = (int)((220 * 1024) / (Cfg::SMEM + 1024));                                                       \
         if (per_sm > 3) per_sm = 3;                                                                                  \
@@ -1335,7 +1175,6 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
         if (per_sm < 1) per_sm = 1;                                                                                  \
         int grid = n_sm * per_sm;                                                                                    \
         if (grid > n_rows * batch) grid = n_rows * batch;                                                            \
-        a.work_counter = work_counter;                                                                               \
         mlb::fft_rows_tma_kernel<LG, KB><<<grid, mlb::TMA_CONSUMERS + 32, Cfg::SMEM, st>>>(a, batch, sc);            \
         return mlb::check_launch("mlb_fft_rows(tma)");                                                               \
     }
@@ -1363,11 +1202,11 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
     const int smem_max = 3 * mlb::FFT_MAX_N * 8;
 #define MLB_ROWS_LAUNCH(V, LG)                                                                                      \
     do {                                                                                                            \
-        static bool set_ = false;                                                                                   \
-        if (!set_) {                                                                                                \
+        static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();                                                                                   \
+        if (!(set_ & devbit_)) {                                                                                                \
             MLB_CUDA(cudaFuncSetAttribute(mlb::fft_rows_kernel<V, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           smem_max));                                                               \
-            set_ = true;                                                                                            \
+            set_ |= devbit_;                                                                                            \
         }                                                                                                           \
         mlb::fft_rows_kernel<V, LG><<<grid, (LG >= 12) ? 1024 : mlb::g_rows_threads, smem, st>>>(a);                                    \
     } while (0)
@@ -1393,14 +1232,7 @@ extern "C" int mlb_fft_rows(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
                             int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
                             int transpose_out, int batch, void *stream) {
     return fft_rows_impl(h_in, ld_in, h_out, ld_out, n_rows, N, s1, s2, tw, in_roll_r, in_roll_c, out_roll, transpose_out,
-                         batch, nullptr, stream);
-}
-
-extern "C" int mlb_fft_rows_ws(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int n_rows,
-                               int N, int s1, int s2, const mlb_c64 *tw, int in_roll_r, int in_roll_c, int out_roll,
-                               int transpose_out, int batch, void *work_counter, void *stream) {
-    return fft_rows_impl(h_in, ld_in, h_out, ld_out, n_rows, N, s1, s2, tw, in_roll_r, in_roll_c, out_roll, transpose_out,
-                         batch, mlb::g_rows_dynamic ? reinterpret_cast<unsigned int *>(work_counter) : nullptr, stream);
+                         batch, stream);
 }
 
 extern "C" int mlb_fft_rows_scatter(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out_peers, int ld_out,
@@ -1425,8 +1257,8 @@ extern "C" int mlb_fft_rows_scatter(const mlb_c64 *const *h_in, int ld_in, mlb_c
             MLB_REQUIRE(ptr != nullptr, "mlb_fft_rows_scatter: NULL output (peer %d, field %d)", p, f);
             sc.out[p][f] = reinterpret_cast<float2 *>(const_cast<mlb_c64 *>(ptr));
         }
-    return fft_rows_impl(h_in, ld_in, h_out_peers, ld_out, n_rows, N, s1, s2, tw, 0, in_roll_c, out_roll, 0, batch,
-                         nullptr, stream, &sc);
+    return fft_rows_impl(h_in, ld_in, h_out_peers, ld_out, n_rows, N, s1, s2, tw, 0, in_roll_c, out_roll, 0, batch, stream,
+                         &sc);
 }
 
 namespace mlb {
@@ -1434,24 +1266,24 @@ template <int LG, int CL>
 static int launch_r16_cols(const R16ColArgs &r, int groups, int batch, cudaStream_t st) {
     constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);
     const size_t smem16 = (size_t)CL * PITCH * sizeof(float2);
-    static bool set_ = false, set3_ = false, set4_ = false;
+    static unsigned long long set_ = 0, set3_ = 0, set4_ = 0; const unsigned long long devbit_ = mlb::device_bit();
     dim3 gc((r.n_cols + CL - 1) / CL, groups, batch);
     if ((g_r16_occ == 3 || g_r16_occ == 0) && T <= 256) {
-        if (!set3_) {
+        if (!(set3_ & devbit_)) {
             MLB_CUDA(cudaFuncSetAttribute(fft16_cols_kernel<LG, CL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            set3_ = true;
+            set3_ |= devbit_;
         }
         fft16_cols_kernel<LG, CL, 3><<<gc, T, smem16, st>>>(r);
     } else if (g_r16_occ == 4 && T <= 256) {
-        if (!set4_) {
+        if (!(set4_ & devbit_)) {
             MLB_CUDA(cudaFuncSetAttribute(fft16_cols_kernel<LG, CL, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            set4_ = true;
+            set4_ |= devbit_;
         }
         fft16_cols_kernel<LG, CL, 4><<<gc, T, smem16, st>>>(r);
     } else {
-        if (!set_) {
+        if (!(set_ & devbit_)) {
             MLB_CUDA(cudaFuncSetAttribute(fft16_cols_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-            set_ = true;
+            set_ |= devbit_;
         }
         fft16_cols_kernel<LG, CL><<<gc, T, smem16, st>>>(r);
     }
@@ -1481,10 +1313,10 @@ template <int LG, int CL>
 static int launch_r16_cols_power(const R16PowerArgs &r, int groups, cudaStream_t st) {
     constexpr int PITCH = (1 << LG) + ((1 << LG) >> 4) + 32 / CL, T = CL * ((1 << LG) >> 4);
     const size_t smem16 = (size_t)CL * PITCH * sizeof(float2) + (size_t)16 * T * (sizeof(float2) + sizeof(float));
-    static bool set_ = false;
-    if (!set_) {
+    static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();
+    if (!(set_ & devbit_)) {
         MLB_CUDA(cudaFuncSetAttribute(fft16_cols_power_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-        set_ = true;
+        set_ |= devbit_;
     }
     dim3 gc((r.n_cols + CL - 1) / CL, groups);
     fft16_cols_power_kernel<LG, CL><<<gc, T, smem16, st>>>(r);
@@ -1512,7 +1344,7 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     MLB_REQUIRE(tw && n_cols > 0 && ld_in >= n_cols && ld_out >= n_cols, "mlb_fft_cols: bad sizes");
     MLB_REQUIRE(out_roll >= 0 && out_roll < N, "mlb_fft_cols: roll out of range");
     a.tw = reinterpret_cast<const float2 *>(tw);
-    if (!mlb::is_pow2(N) && mlb::g_mixed_engine == 1) {
+    if (!mlb::is_pow2(N)) {
         // big-radix engine: direct while >= 16 columns per CTA fit, else N = A x B in two passes (the first in place
         // on the INPUT buffer, which is then scratch; in-place calls fall back to the direct pass)
         cudaStream_t st = (cudaStream_t)stream;
@@ -1556,24 +1388,6 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
         m2.lanes = lanes; m2.lg_lanes = mlb::ilog2(lanes);
         dim3 grid((n_cols + lanes - 1) / lanes, A, batch);
         mlb::mix2_cols_kernel<<<grid, 256, mlb::mix2_smem(B, lanes), st>>>(m2);
-        return mlb::check_launch("mlb_fft_cols(mixed radix)");
-    }
-    if (!mlb::is_pow2(N)) {                        // mixed radix (good_fft_number sizes)
-        mlb::MixArgs m;
-        mlb::fill_mixed(m, a, N);
-        m.tw = a.tw; m.ld_in = ld_in; m.ld_out = ld_out; m.other = n_cols;
-        m.in_roll_r = m.in_roll_c = 0; m.out_roll = out_roll; m.s1 = m.s2 = 1;
-        int lanes = 1;
-        while (lanes < 16 && 2 * (size_t)(lanes * 2) * (N + 1) * sizeof(float2) <= 96 * 1024 && lanes * 2 <= n_cols) lanes *= 2;
-        m.lanes = lanes;
-        const size_t smem = 2 * (size_t)lanes * (N + 1) * sizeof(float2);
-        static bool set_ = false;
-        if (!set_) {
-            MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (mlb::FFT_MAX_N + 1) * 8));
-            set_ = true;
-        }
-        dim3 grid((n_cols + lanes - 1) / lanes, batch);
-        mlb::fft_cols_mixed_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(m);
         return mlb::check_launch("mlb_fft_cols(mixed radix)");
     }
     a.ld_in = ld_in; a.ld_out = ld_out; a.lgN = mlb::ilog2(N); a.other = n_cols;
@@ -1642,11 +1456,11 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
     const int smem_max = (3 * mlb::FFT_MAX_N + 8) * 8;
 #define MLB_COLS_LAUNCH(LG, CL)                                                                                      \
     do {                                                                                                             \
-        static bool set_ = false;                                                                                    \
-        if (!set_) {                                                                                                 \
+        static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();                                                                                    \
+        if (!(set_ & devbit_)) {                                                                                                 \
             MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_kernel<LG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           smem_max));                                                                \
-            set_ = true;                                                                                             \
+            set_ |= devbit_;                                                                                             \
         }                                                                                                            \
         dim3 grid((n_cols + lanes - 1) / lanes, batch);                                                              \
         mlb::fft_cols_kernel<LG, CL><<<grid, (LG >= 12) ? 1024 : 256, smem, st>>>(a);                                                    \
@@ -1777,11 +1591,11 @@ static int fft_cols_power_impl(const mlb_c64 *const *h_in, int ld_in, int N, int
     cudaStream_t st = (cudaStream_t)stream;
 #define MLB_CP_LAUNCH(LG, CL, T)                                                                                      \
     do {                                                                                                              \
-        static bool set_ = false;                                                                                     \
-        if (!set_) {                                                                                                  \
+        static unsigned long long set_ = 0; const unsigned long long devbit_ = mlb::device_bit();                                                                                     \
+        if (!(set_ & devbit_)) {                                                                                                  \
             MLB_CUDA(cudaFuncSetAttribute(mlb::fft_cols_power_kernel<LG, CL, T>,                                      \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-            set_ = true;                                                                                              \
+            set_ |= devbit_;                                                                                              \
         }                                                                                                             \
         mlb::fft_cols_power_kernel<LG, CL, T><<<grid, T, smem, st>>>(a);                                              \
     } while (0)

@@ -200,8 +200,7 @@ class FarfieldPlan:
             for t, n in ((self.tw1, K1), (self.tw2, K2)):
                 _lib.check(self.lib.mlb_fft_twiddle(n, t.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
             self.AxT = self.Ay = None
-            # [0:2] dynamic row distribution (mlb_fft_rows_ws), [2] finished-CTA counter of the fused column+power pass
-            self.work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.done_counter = torch.zeros(2, dtype=torch.int32, device=dev)     # finished-CTA counter of the fused column+power pass
             # fused column pass + power: measured faster than column pass + epilogue up to 1024-point columns
             # (above that the fused kernel's register footprint costs more than the saved round trip)
             self.fused = bool(self._want_fused and not self.two_pass_t and self.p_dtype == torch.float32
@@ -386,9 +385,8 @@ class FarfieldPlan:
             tr = 1 if self.two_pass_t else 0
 
             def rows(pi_=pi_, ld=ld, keep=(k3, k4)):      # along y; stored transposed (W[qy][p1]) in two-pass mode
-                _lib.check(lib.mlb_fft_rows_ws(pi_, ld, pw, ldw, Rx, Ry, self.sx, self.sy, self.tw2.data_ptr(),
-                                               roll_r, roll_c, (h2 // self.sy) % Ry, tr, 4,
-                                               self.work_counter.data_ptr(), _stream_ptr()), "mlb_fft_rows_ws")
+                _lib.check(lib.mlb_fft_rows(pi_, ld, pw, ldw, Rx, Ry, self.sx, self.sy, self.tw2.data_ptr(),
+                                            roll_r, roll_c, (h2 // self.sy) % Ry, tr, 4, _stream_ptr()), "mlb_fft_rows")
 
             def cols(keep=k5):                            # along x
                 if tr:                                    # rows of W = fixed qy, contiguous p1 -> Fhat[qx][qy]
@@ -406,7 +404,7 @@ class FarfieldPlan:
                                                             self.wavelength, self.n_glass, Z0, self.P.data_ptr(),
                                                             self.P.shape[1], 1 if accumulate else 0,
                                                             self.block_sums.data_ptr(), self.total.data_ptr(),
-                                                            self.dux * self.duy, self.work_counter.data_ptr() + 8,
+                                                            self.dux * self.duy, self.done_counter.data_ptr(),
                                                             _stream_ptr()), "mlb_fft_cols_power_total")
                     return self.P, self.total
                 out.append(("fft_cols_power", cols_power, (32 + 4) * Rx * Ry, 4 * 5.0 * Rx * Ry * math.log2(Rx)))

@@ -264,15 +264,13 @@ def test_fft_passes_match_numpy(fft_engines):
     pb, k4 = _lib.ptr_array([bad])
     assert lib.mlb_fft_rows(pb, 14, pb, 14, 4, 14, 1, 1, bad.data_ptr(), 0, 0, 0, 0, 1, None) != 0   # 14 = 2*7: not 5-smooth
     # mixed radix (good_fft_number sizes): rows with fold + rolls, and columns
-    # engine 1 = big-radix kernels (fftmix.cuh; long columns in two passes when >= 8 columns), 0 = radix 2..5 kernels
+    # engine 1 = big-radix kernels (fftmix.cuh; long columns in two passes when >= 8 columns)
     cases = [(1, c) for c in ((6, 5, 1, 1), (12, 7, 2, 3), (45, 9, 1, 2), (100, 4, 3, 1), (675, 3, 1, 1), (720, 5, 2, 2),
                               (1000, 2, 1, 1), (6000, 2, 1, 1), (3375, 37, 1, 1), (450, 20, 2, 1), (8100, 9, 1, 1),
                               (2187, 12, 1, 1), (3125, 8, 1, 1), (1536, 16, 1, 2), (3600, 40, 1, 1), (20, 33, 1, 1))]
-    cases += [(0, c) for c in ((12, 7, 2, 3), (675, 3, 1, 1), (720, 5, 2, 2), (6000, 2, 1, 1))]
     # engine 2 here = big-radix engine with the register (one butterfly per thread) kernels switched off
     cases += [(2, c) for c in ((12, 7, 2, 3), (675, 3, 1, 1), (3375, 37, 1, 1), (450, 20, 2, 1), (3600, 40, 1, 1))]
     for engine, (N, other, s1, s2) in cases:
-        lib.mlb_set_option(b"mixed_engine", min(engine, 1))
         lib.mlb_set_option(b"mixed_registers", 0 if engine == 2 else 2)      # 2: register kernels wherever they apply
         big = (rng.standard_normal((other * s1, N * s2)) + 1j * rng.standard_normal((other * s1, N * s2))).astype(np.complex64)
         ldi = N * s2 + 3
@@ -300,7 +298,6 @@ def test_fft_passes_match_numpy(fft_engines):
         refc = np.roll(np.fft.fft(folded.T.astype(np.complex64).astype(complex), axis=0), ro, axis=0)
         assert field_error(dco[0][:, :other].cpu().numpy(), refc) < 3e-6, ("mixed cols", N)
         assert float(dco[0][:, other:].abs().max()) == 0.0                       # pitch padding untouched
-    lib.mlb_set_option(b"mixed_engine", 1)
     lib.mlb_set_option(b"mixed_registers", 1)
     # fused fold: [n_rows*s1][N*s2] input, summed over the aliased copies while loading
     n_rows, N, s1, s2 = 6, 64, 3, 4
@@ -797,28 +794,6 @@ def test_radix16_column_kernels_match_numpy():
         lib.mlb_set_option(b"r16_min_lg", 10)
 
 
-def test_dynamic_row_distribution_is_bit_identical():
-    """mlb_fft_rows_ws: the TMA-fed row pass drawing its rows from a self-re-arming device counter gives the same
-    bits as the fixed-stride distribution, call after call (the counters are left zero)."""
-    from metalens_b200 import _lib
-    from metalens_b200.farfield import FarfieldPlan
-    lib = _lib.load()
-    Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(1024, 5, WL)
-    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
-    plan = FarfieldPlan((1024, 1024), x[1] - x[0], y[1] - y[0], WL, NG, stride=2)
-    assert plan.method == "fft"
-    P0 = plan.run(dev)[0].clone()
-    lib.mlb_set_option(b"rows_dynamic", 1)
-    try:
-        for _ in range(3):
-            P1 = plan.run(dev)[0]
-            assert _same(P0, P1)
-            assert int(plan.work_counter.abs().sum().item()) == 0
-    finally:
-        lib.mlb_set_option(b"rows_dynamic", 0)
-
-
-@pytest.mark.parametrize("M", [3375, 2700])
 def test_reference_default_grid_full_size_properties(M):
     """The reference's own usage at full size: a good_fft_number() aperture (3375 = 3^3 5^3, 2700 = 2^2 3^3 5^2),
     ALL FFT bins, through the big-radix mixed engine.  Size-independent properties: a sample of bins against the
