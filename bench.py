@@ -674,7 +674,7 @@ def ours(args):
     # ---- the other formulations on the same workload (device-resident, fewer steps), for context
     paths = {plans[0].method: value}
     if world == 1 and not args.no_paths:
-        for m in ("fft", "fold", "tc", "dense"):
+        for m in ("fft", "fold", "czt", "tc", "dense"):
             if m in paths:
                 continue
             try:

@@ -196,6 +196,20 @@ int mlb_fft_cols_power_total(const mlb_c64 *const *h_in, int ld_in, int N, int n
 int mlb_set_option(const char *name, int value);
 int mlb_get_option(const char *name);
 
+/* ---- A4 on a uniform "zoomed" grid: chirp-z (Bluestein) aperture sum on the FFT passes -----------------------
+ * For ux_i = u0 + i du (any u0, du) and x_m = (m - origin) d the sum of nearfield_farfield.py:97-120 along one axis is
+ *     F[i] = post[i] . conj( FFT_L( conj( FFT_L(pad(J . pre)) . FFT_L(kern) ) ) )[i + origin]        (L >= M + K - 1)
+ * mlb_czt_chirps builds pre[M], kern[L] (the wrapped chirp e^{+i pi tq n^2/2}; its FFT is taken once with mlb_fft_rows) and
+ * post[K] (includes 1/L) from t_lin = 2 n d u0 / lambda, t_quad = 2 n d du / lambda with float64 phases.
+ * mlb_czt_pointwise is the pointwise step between the FFT passes (pad, multiply, conjugate, crop), batch <= 4 fields:
+ *   out_b[r][c] = conj_out?( conj_in?(in_b[r + row_off][c + col_off]) . row_tab[r] . col_tab[c] ),  r < rows_valid and
+ *   c < cols_valid, 0 elsewhere (r < rows_out, c < cols_out); row_tab / col_tab may be NULL. */
+int mlb_czt_chirps(int M, int origin, int K, int L, double t_lin, double t_quad, mlb_c64 *pre, mlb_c64 *kern,
+                   mlb_c64 *post, void *stream);
+int mlb_czt_pointwise(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *h_out, int ld_out, int rows_out, int cols_out,
+                      int rows_valid, int cols_valid, int row_off, int col_off, const mlb_c64 *row_tab,
+                      const mlb_c64 *col_tab, int conj_in, int conj_out, int batch, void *stream);
+
 /* ---- A2/A3: radiated power ------------------------------------------------ */
 /*
  * Fhat (4 x Kx x Ky c64: Ex,Ey,Hx,Hy aperture sums) -> P (Kx x Ky) following

@@ -52,6 +52,10 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "mlb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "mlb_get_option": (C.c_int, [C.c_char_p]),
+    "mlb_czt_chirps": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "mlb_czt_pointwise": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mlb_ff_epilogue_blocks": (C.c_int, [C.c_int, C.c_int]),
     "mlb_ff_epilogue": (C.c_int, [_PP, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_double, C.c_double,

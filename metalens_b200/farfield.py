@@ -71,8 +71,11 @@ class FarfieldPlan:
     stride : int or (sx, sy) -- far-field grid = every stride-th bin of the reference's
         fftshifted FFT-bin grid (stride 1 = the reference grid itself)
     ux, uy : explicit direction-cosine lists (arbitrary grid); excludes `stride`
-    method : 'auto' | 'dense' | 'fold' | 'fft'
+    method : 'auto' | 'dense' | 'fold' | 'fft' | 'czt' | 'tc'
         dense -- two-stage separable tiled complex reduction over the full aperture
+        czt   -- chirp-z (Bluestein) aperture sum for UNIFORM ux / uy lists that are not FFT bins (a "zoomed" far field):
+                 the sum along each axis becomes a convolution with a chirp, run on the FFT passes at a power-of-two
+                 length L >= M + K - 1 <= 8192 (csrc/czt.cu); float32-exact like 'dense' at a small fraction of its work
         fold  -- exact aperture fold (HBM-bound) followed by the dense reduction on the
                  folded (Mx/sx x My/sy) aperture; needs an FFT-bin-stride grid with
                  sx | Mx//2 and sy | My//2
@@ -83,7 +86,7 @@ class FarfieldPlan:
                  kernels (TMA-fed row pass), other sizes the mixed-radix ones
         tc    -- the dense separable reduction on the tensor cores: tcgen05 UMMA (TF32 operands split
                  hi/lo, three products per term -> fp32-class accuracy), TMEM accumulators, TMA-fed
-        auto  -- fft if eligible, else fold, else dense
+        auto  -- fft if eligible, else fold, else (explicit uniform ux / uy) czt, else dense
     p_dtype : torch.float32 (north-star output type) or torch.float64
     rows : optional (row0, row1): compute only that slab of far-field rows (ux indices) -- the
         multi-GPU tile of metalens_b200/sharding.py.  Supported by 'dense' and 'fold', whose work
@@ -147,14 +150,29 @@ class FarfieldPlan:
             if method == "fft":
                 raise ValueError("row slabs need method 'dense' or 'fold' (the FFT passes yield all rows)")
             can_fft = False
+        def uniform(u):
+            d = np.diff(u)
+            return bool(u.size >= 2 and d[0] != 0 and np.all(np.abs(d - d[0]) <= 1e-9 * abs(d[0])))
+
+        def czt_len(m, k):
+            n = 1
+            while n < m + k - 1:
+                n *= 2
+            return n
+        self.czt_L = (czt_len(self.Mx, self.Kx), czt_len(self.My, self.Ky))
+        nmax_czt = self.lib.mlb_fft_max_length()
+        can_czt = (uniform(self.ux) and uniform(self.uy) and min(self.czt_L) >= 16 and max(self.czt_L) <= nmax_czt
+                   and max(self.czt_L) <= 65535)
         if method == "auto":
-            method = "fft" if can_fft else ("fold" if can_fold else "dense")
+            method = "fft" if can_fft else ("fold" if can_fold else ("czt" if (can_czt and not self.fft_bin_grid) else "dense"))
+        if method == "czt" and not can_czt:
+            raise ValueError("czt needs uniformly spaced ux and uy lists and M + K - 1 <= %d per axis" % nmax_czt)
         if method == "fold" and not can_fold:
             raise ValueError("fold needs an FFT-bin-stride grid with stride dividing M and M//2")
         if method == "fft" and not can_fft:
             raise ValueError("fft needs an FFT-bin(-stride) grid whose folded sizes are 2^a 3^b 5^c and <= %d"
                              % self.lib.mlb_fft_max_length())
-        assert method in ("dense", "fold", "fft", "tc")
+        assert method in ("dense", "fold", "fft", "tc", "czt")
         self.method = method
         self._build()
 
@@ -183,6 +201,8 @@ class FarfieldPlan:
             self.G = None
         elif self.method == "tc":
             self._build_tc()
+        elif self.method == "czt":
+            self._build_czt()
         elif self.method == "fft":
             K1, K2 = Mx // self.sx, My // self.sy
             assert K1 == Kx and K2 == Ky
@@ -235,6 +255,70 @@ class FarfieldPlan:
         self.duy = float(self.uy[1] - self.uy[0]) if Ky > 1 else float("nan")
         self._staging = None
         self._pinned = None
+
+    def _build_czt(self):
+        """Chirp tables, their transforms and the work buffers of method 'czt' (csrc/czt.cu)."""
+        dev, lib = self.device, self.lib
+        self.Rx, self.Ry = self.Mx, self.My
+        self.G = None
+        self.AxT = self.Ay = None
+        self.czt = {}
+        for axis, (M, K, L, d, u) in {"x": (self.Mx, self.Kx, self.czt_L[0], self.dxp, self.ux),
+                                      "y": (self.My, self.Ky, self.czt_L[1], self.dyp, self.uy)}.items():
+            o = M - M // 2                                    # the sample fftshift() moves to index 0 (SURVEY Q4)
+            du = float(u[1] - u[0])
+            t_lin = 2.0 * self.n_glass * d * float(u[0]) / self.wavelength
+            t_quad = 2.0 * self.n_glass * d * du / self.wavelength
+            pre = torch.empty(M + (M & 1), dtype=torch.complex64, device=dev)
+            kern = torch.empty((1, L), dtype=torch.complex64, device=dev)
+            post = torch.empty(K + (K & 1), dtype=torch.complex64, device=dev)
+            _lib.check(lib.mlb_czt_chirps(M, o, K, L, t_lin, t_quad, pre.data_ptr(), kern.data_ptr(), post.data_ptr(),
+                                          _stream_ptr()), "mlb_czt_chirps")
+            tw = torch.empty(2 * L, dtype=torch.complex64, device=dev)
+            _lib.check(lib.mlb_fft_twiddle(L, tw.data_ptr(), _stream_ptr()), "mlb_fft_twiddle")
+            khat = torch.empty((1, L), dtype=torch.complex64, device=dev)
+            pk, k1 = _lib.ptr_array([kern])
+            ph, k2 = _lib.ptr_array([khat])
+            _lib.check(lib.mlb_fft_rows(pk, L, ph, L, 1, L, 1, 1, tw.data_ptr(), 0, 0, 0, 0, 1, _stream_ptr()), "mlb_fft_rows(chirp)")
+            self.czt[axis] = dict(o=o, L=L, pre=pre, post=post, khat=khat, tw=tw)
+        Lx, Ly = self.czt_L
+        self.czt_R = [torch.empty((self.Mx, Ly), dtype=torch.complex64, device=dev) for _ in range(4)]
+        kyp = _even(self.Ky)
+        self.czt_C = [[torch.empty((Lx, kyp), dtype=torch.complex64, device=dev) for _ in range(4)] for _ in range(2)]
+
+    def _steps_czt(self, ops, ld):
+        lib = self.lib
+        Mx, My, Kx, Ky = self.Mx, self.My, self.Kx, self.Ky
+        Lx, Ly = self.czt_L
+        X, Y = self.czt["x"], self.czt["y"]
+        pin, k0 = _lib.ptr_array(ops)
+        pR, k1 = _lib.ptr_array(self.czt_R)
+        pC0, k2 = _lib.ptr_array(self.czt_C[0])
+        pC1, k3 = _lib.ptr_array(self.czt_C[1])
+        pF, k4 = _lib.ptr_array(self.Fhat)
+        ldc, ldf = self.czt_C[0][0].shape[1], self.Fhat[0].shape[1]
+
+        def pw(i, ldi, o, ldo, rows_out, cols_out, rows_valid, cols_valid, roff, coff, rtab, ctab, cin, cout):
+            _lib.check(lib.mlb_czt_pointwise(i, ldi, o, ldo, rows_out, cols_out, rows_valid, cols_valid, roff, coff,
+                                             None if rtab is None else rtab.data_ptr(),
+                                             None if ctab is None else ctab.data_ptr(), cin, cout, 4, _stream_ptr()),
+                       "mlb_czt_pointwise")
+
+        def rows(keep=(k0, k1)):            # along y: pad . pre -> FFT -> . FFT(chirp), conj -> FFT -> (crop in cols())
+            pw(pin, ld, pR, Ly, Mx, Ly, Mx, My, 0, 0, None, Y["pre"], 0, 0)
+            _lib.check(lib.mlb_fft_rows(pR, Ly, pR, Ly, Mx, Ly, 1, 1, Y["tw"].data_ptr(), 0, 0, 0, 0, 4, _stream_ptr()), "mlb_fft_rows(czt)")
+            pw(pR, Ly, pR, Ly, Mx, Ly, Mx, Ly, 0, 0, None, Y["khat"], 0, 1)
+            _lib.check(lib.mlb_fft_rows(pR, Ly, pR, Ly, Mx, Ly, 1, 1, Y["tw"].data_ptr(), 0, 0, 0, 0, 4, _stream_ptr()), "mlb_fft_rows(czt)")
+
+        def cols(keep=(k2, k3, k4)):        # crop . post_y . pre_x, zero-padded to Lx rows -> the same along x -> crop . post_x
+            pw(pR, Ly, pC0, ldc, Lx, Ky, Mx, Ky, 0, Y["o"], X["pre"], Y["post"], 1, 0)
+            _lib.check(lib.mlb_fft_cols(pC0, ldc, pC1, ldc, Lx, Ky, X["tw"].data_ptr(), 0, 4, _stream_ptr()), "mlb_fft_cols(czt)")
+            pw(pC1, ldc, pC1, ldc, Lx, Ky, Lx, Ky, 0, 0, X["khat"], None, 0, 1)
+            _lib.check(lib.mlb_fft_cols(pC1, ldc, pC0, ldc, Lx, Ky, X["tw"].data_ptr(), 0, 4, _stream_ptr()), "mlb_fft_cols(czt)")
+            pw(pC0, ldc, pF, ldf, Kx, Ky, Kx, Ky, X["o"], 0, X["post"], None, 1, 0)
+        import math as _m
+        return [("czt_rows", rows, 4 * 8 * (Mx * My + 5 * Mx * Ly), 4 * 2 * 5.0 * Mx * Ly * _m.log2(Ly)),
+                ("czt_cols", cols, 4 * 8 * (Mx * Ly + 5 * Lx * Ky + Kx * Ky), 4 * 2 * 5.0 * Lx * Ky * _m.log2(Lx))]
 
     def _build_tc(self):
         """Operands of the tensor-core path (csrc/cgemm_tc.cu): y-first contraction
@@ -355,6 +439,8 @@ class FarfieldPlan:
         out = []
         if self.method == "tc":
             return self._steps_tc(ops, ld) + [("epilogue", self.power, 36 * Kx * Ky, 0.0)]
+        if self.method == "czt":
+            return self._steps_czt(ops, ld) + [("epilogue", self.power, 36 * Kx * Ky, 0.0)]
         if self.method == "fold":
             pj, k1 = _lib.ptr_array(ops)
             pg, k2 = _lib.ptr_array(self.G)
@@ -574,7 +660,8 @@ def farfield_from_fields(Ex, Ey, Hx, Hy, xp_list, yp_list, wavelength, n_glass, 
     _check_axis(xp_list, wavelength)
     _check_axis(yp_list, wavelength)
     if ux is not None:
-        plan = FarfieldPlan((nx, ny), dxp, dyp, wavelength, n_glass, ux=ux, uy=uy, method="dense", p_dtype=p_dtype)
+        plan = FarfieldPlan((nx, ny), dxp, dyp, wavelength, n_glass, ux=ux, uy=uy,
+                            method=method if method in ("dense", "czt", "tc") else "auto", p_dtype=p_dtype)
     else:
         plan = FarfieldPlan((nx, ny), dxp, dyp, wavelength, n_glass, stride=stride, method=method, p_dtype=p_dtype)
     P, total = plan.run_host(Ex, Ey, Hx, Hy)

@@ -99,6 +99,61 @@ def test_arbitrary_direction_cosine_grid():
     assert power_map_error(P, P_ref) < FF_TOL
 
 
+@pytest.mark.parametrize("shape,kx,ky,span", [((96, 70), 53, 38, (-0.83, 0.91, -0.5, 0.77)),       # wide, non-square
+                                              ((128, 128), 64, 64, (-0.06, 0.06, -0.05, 0.07)),    # zoom around the axis
+                                              ((45, 27), 30, 9, (0.2, -0.3, 0.1, 0.4)),            # odd sizes, descending ux
+                                              ((1024, 1024), 300, 301, (-0.02, 0.02, -0.02, 0.02))])
+def test_chirp_z_uniform_zoom_grids(shape, kx, ky, span):
+    """A4 on a UNIFORM grid that is not a set of FFT bins: method 'czt' (chirp-z on the FFT passes) against the float64
+    direct sum, and against the tiled reduction it replaces; 'auto' picks it for explicit uniform grids."""
+    from oracle import farfield_oracle as fo
+    from metalens_b200.farfield import FarfieldPlan
+    Mx, My = shape
+    if Mx >= 1024:
+        Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(Mx, 21, WL, NG, na=0.3)
+    else:
+        Ex, Ey, Hx, Hy, x, y = apertures.gaussian_random(Mx, 21, WL, My=My)
+    ux = np.linspace(span[0], span[1], kx)
+    uy = np.linspace(span[2], span[3], ky)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Ex, Ey, Hx, Hy)]
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    plan = FarfieldPlan((Mx, My), dx, dy, WL, NG, ux=ux, uy=uy)
+    assert plan.method == "czt"
+    P, total = plan.run(dev)
+    P = P.cpu().numpy()
+    P_ref, F_ref = fo.farfield_dense(Ex, Ey, Hx, Hy, dx, dy, ux, uy, WL, NG)
+    assert power_map_error(P, P_ref) < FF_TOL
+    amps = plan.amplitudes().cpu().numpy()
+    for k in range(4):
+        assert field_error(amps[k], F_ref[k]) < 3e-6
+    dense = FarfieldPlan((Mx, My), dx, dy, WL, NG, ux=ux, uy=uy, method="dense")
+    Pd, td = dense.run(dev)
+    assert power_map_error(Pd.cpu().numpy(), P_ref) < FF_TOL
+    assert abs(total.item() - td.item()) <= FF_TOL * abs(td.item())
+    # a slab of far-field rows (multi-GPU tile) is still a uniform grid
+    slab = FarfieldPlan((Mx, My), dx, dy, WL, NG, ux=ux, uy=uy, rows=(kx // 3, kx // 3 + 7))
+    assert slab.method == "czt"
+    Ps = slab.run(dev)[0].cpu().numpy()
+    assert power_map_error(Ps, P_ref[kx // 3:kx // 3 + 7]) < FF_TOL * max(1.0, np.nanmax(P_ref) / np.nanmax(P_ref[kx // 3:kx // 3 + 7]))
+
+
+def test_chirp_z_on_the_strided_bin_grid():
+    """The every-4th-bin grid of BASELINE cfg 2/3 is uniform too: 'czt' must agree with the fold + FFT path there."""
+    from metalens_b200.farfield import FarfieldPlan
+    M, s = 512, 4
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(M, 5, WL, NG)
+    dev = [torch.from_numpy(a).cuda() for a in (Ex, Ey, Hx, Hy)]
+    d = x[1] - x[0]
+    a = FarfieldPlan((M, M), d, d, WL, NG, stride=s, method="fft")
+    b = FarfieldPlan((M, M), d, d, WL, NG, stride=s, method="czt")
+    Pa, ta = a.run(dev)
+    Pb, tb = b.run(dev)
+    assert power_map_error(Pb.cpu().numpy(), Pa.cpu().numpy()) < FF_TOL
+    assert abs(ta.item() - tb.item()) <= FF_TOL * abs(ta.item())
+    with pytest.raises(ValueError):
+        FarfieldPlan((8192, 8192), d, d, WL, NG, stride=4, method="czt")          # M + K - 1 > 8192
+
+
 def test_complex_amplitudes_match_fft():
     """The aperture sums themselves (not only P) equal fft2(fftshift(.)) -- phase origin (Q4)."""
     from metalens_b200.farfield import FarfieldPlan
