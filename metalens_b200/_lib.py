@@ -34,6 +34,8 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "mlb_cgemm_tc": (C.c_int, [_PP, _PP, C.c_int, _PP, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                _PP, _PP, C.c_int, C.c_int, C.c_void_p]),
+    "mlb_cgemm_tc_split": (C.c_int, [_PP, _PP, C.c_int, _PP, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     _PP, _PP, C.c_int, C.c_int, _PP, C.c_int, C.c_void_p]),
     "mlb_fft_twiddle": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "mlb_fft_max_length": (C.c_int, []),
     "mlb_fft_tune": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -14,6 +14,11 @@
 //   large main term and the 2^-11-times-smaller correction term get SEPARATE TMEM accumulators
 //   (2 x 256 columns = all of TMEM) and are summed in fp32 by the epilogue: the correction products no
 //   longer cost a truncation of the big accumulator each (3x fewer biased roundings).
+//   Truncation is a BIAS (toward zero, ~2^-24 of the accumulator per 8-deep step) that does not average out in a
+//   coherent sum such as the focus of a lens: ~1e-4 at depth 4096.  The contraction is therefore split into chunks
+//   of TC_CHUNK_BLOCKS k-blocks (64 accumulation steps): every launch starts its TMEM accumulators at zero and its
+//   epilogue ADDS the chunk into the fp32 result in memory with round-to-nearest (unbiased) -- the in-chunk bias is
+//   bounded (~2e-6) whatever the aperture size, at the price of one read-modify-write of the output per chunk.
 //
 // Kernel anatomy (one 128 x 256 real output tile per CTA, 192 threads):
 //   warp 0 : TMA producer  (cp.async.bulk.tensor 2-D, 4 operand tiles per k-block, mbarrier tx)
@@ -34,6 +39,7 @@ constexpr int TC_BM = 128;       // real rows of D per CTA  (= UMMA M)
 constexpr int TC_BN = 256;       // real cols of D per CTA  (= UMMA N) = 128 complex columns
 constexpr int TC_BK = 32;        // tf32 elements per k-block = 128 bytes = one swizzle span
 constexpr int TC_STAGES = 2;
+constexpr int TC_CHUNK_BLOCKS = 16;   // k-blocks per launch (512 real depth = 64 truncating accumulation steps)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;        // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // Ah, Al, Bh, Bl = 96 KB
@@ -110,8 +116,9 @@ struct TcArgs {
     float *out_hi[4], *out_lo[4];   // mode 1: embedded operand hi / lo;  mode 2: out_hi = complex64 result
     int ldo;                  // floats (mode 1) or complex elements (mode 2)
     int rows, cols_c;         // valid output rows (real M) and complex columns (N/2)
-    int k_blocks;
-    int mode;
+    int kb0, k_blocks;        // this launch contracts k-blocks [kb0, kb0 + k_blocks)
+    int mode;                 // 1: embedded hi/lo operand of the next stage, 2: complex64 result, 3: complex64 partial sum
+    int accumulate;           // modes 2 / 3: add to what is in memory (round-to-nearest) instead of overwriting
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -148,7 +155,7 @@ cgemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
                 if (kb >= TC_STAGES) mbar_wait(&empty[s], (uint32_t)(((kb / TC_STAGES) - 1) & 1));
                 unsigned char *st = base + s * TC_STAGE_BYTES;
                 mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-                const int k0 = kb * TC_BK;
+                const int k0 = (a.kb0 + kb) * TC_BK;
                 tma_load_2d(st, mapAh, k0, m0, &full[s]);
                 tma_load_2d(st + TC_A_BYTES, mapAl, k0, m0, &full[s]);
                 tma_load_2d(st + 2 * TC_A_BYTES, mapBh, k0, n0, &full[s]);
@@ -206,7 +213,13 @@ cgemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs a) {
                         *reinterpret_cast<float2 *>(out_lo + o0) = make_float2(rl, -il);
                         *reinterpret_cast<float2 *>(out_lo + o1) = make_float2(il, rl);
                     } else {
-                        reinterpret_cast<float2 *>(out_hi)[(size_t)row * a.ldo + jc] = make_float2(re, im);
+                        float2 *dst = reinterpret_cast<float2 *>(out_hi) + (size_t)row * a.ldo + jc;
+                        if (a.accumulate) {                           // chunk sums are added with round-to-nearest
+                            const float2 old = *dst;
+                            *dst = make_float2(old.x + re, old.y + im);
+                        } else {
+                            *dst = make_float2(re, im);
+                        }
                     }
                 }
             }
@@ -227,6 +240,24 @@ __global__ void tf32_split_kernel(const float *__restrict__ in, size_t ld_in, fl
     split_tf32(in[(size_t)r * ld_in + c], h, l);
     hi[(size_t)r * ld_out + c] = h;
     lo[(size_t)r * ld_out + c] = l;
+}
+
+// complex64 T[row][j] (pitch ld_in complex) -> the hi / lo operand embedding of the next stage (what the mode-1 epilogue
+// writes directly when the contraction is a single chunk): rows 2j, 2j+1 of [2*cols_c][ldo], columns 2*row, 2*row+1
+__global__ void tc_embed_kernel(const float2 *__restrict__ in, size_t ld_in, float *__restrict__ hi, float *__restrict__ lo,
+                                size_t ldo, int rows, int cols_c) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;       // fast index = output column pair
+    const int jc = blockIdx.y;
+    if (row >= rows || jc >= cols_c) return;
+    const float2 v = in[(size_t)row * ld_in + jc];
+    float rh, rl, ih, il;
+    split_tf32(v.x, rh, rl);
+    split_tf32(v.y, ih, il);
+    const size_t o0 = (size_t)(2 * jc) * ldo + 2 * row, o1 = o0 + ldo;
+    *reinterpret_cast<float2 *>(hi + o0) = make_float2(rh, -ih);
+    *reinterpret_cast<float2 *>(hi + o1) = make_float2(ih, rh);
+    *reinterpret_cast<float2 *>(lo + o0) = make_float2(rl, -il);
+    *reinterpret_cast<float2 *>(lo + o1) = make_float2(il, rl);
 }
 
 // twiddle w(u_i, x_m) = exp(i*pi*scale*coord[m]*u[i]) in float64, written hi/lo as
@@ -307,9 +338,10 @@ extern "C" int mlb_twiddle_tf32(const double *coord, int n_coord, const double *
     return mlb::check_launch("mlb_twiddle_tf32");
 }
 
-extern "C" int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,
-                            const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
-                            float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream) {
+static int cgemm_tc_impl(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,
+                         const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
+                         float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, mlb_c64 *const *h_scratch,
+                         int ld_scratch, void *stream) {
     MLB_REQUIRE(h_Ah && h_Al && h_Bh && h_Bl && h_out_hi, "mlb_cgemm_tc: NULL pointer");
     MLB_REQUIRE(batch >= 1 && batch <= 4, "mlb_cgemm_tc: batch %d not in 1..4", batch);
     MLB_REQUIRE(mode == 1 || mode == 2, "mlb_cgemm_tc: mode must be 1 (embedded hi/lo output) or 2 (complex64 output)");
@@ -338,9 +370,62 @@ extern "C" int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, 
         MLB_CUDA(cudaFuncSetAttribute(mlb::cgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlb::TC_SMEM));
         attr_set |= devbit_;
     }
-    a.ldo = ldo; a.rows = rows; a.cols_c = cols_c;
-    a.k_blocks = (K + mlb::TC_BK - 1) / mlb::TC_BK; a.mode = mode;
+    a.rows = rows; a.cols_c = cols_c;
+    const int k_blocks = (K + mlb::TC_BK - 1) / mlb::TC_BK;
     dim3 grid((2 * cols_c + mlb::TC_BN - 1) / mlb::TC_BN, (rows + mlb::TC_BM - 1) / mlb::TC_BM, batch);
-    mlb::cgemm_tc_kernel<<<grid, mlb::TC_THREADS, mlb::TC_SMEM, (cudaStream_t)stream>>>(maps, a);
-    return mlb::check_launch("mlb_cgemm_tc");
+    const cudaStream_t st = (cudaStream_t)stream;
+    const bool chunked = h_scratch != nullptr && k_blocks > mlb::TC_CHUNK_BLOCKS;
+    if (!chunked) {                                       // short contraction (or no scratch): one launch, as before
+        a.ldo = ldo; a.kb0 = 0; a.k_blocks = k_blocks; a.mode = mode; a.accumulate = 0;
+        mlb::cgemm_tc_kernel<<<grid, mlb::TC_THREADS, mlb::TC_SMEM, st>>>(maps, a);
+        return mlb::check_launch("mlb_cgemm_tc");
+    }
+    // chunked: every launch contracts TC_CHUNK_BLOCKS k-blocks from zero and adds its partial sum to the complex64
+    // result in memory (round-to-nearest); mode 1 accumulates in the scratch and embeds it for the next stage at the end
+    mlb::TcArgs c = a;
+    if (mode == 1) {
+        MLB_REQUIRE(ld_scratch >= cols_c, "mlb_cgemm_tc_split: scratch pitch too small");
+        for (int b = 0; b < 4; ++b) {
+            const int s = b < batch ? b : 0;
+            MLB_REQUIRE(h_scratch[s] != nullptr, "mlb_cgemm_tc_split: NULL scratch %d", s);
+            c.out_hi[b] = reinterpret_cast<float *>(const_cast<mlb_c64 *>(h_scratch[s]));
+            c.out_lo[b] = nullptr;
+        }
+        c.ldo = ld_scratch; c.mode = 3;
+    } else {
+        c.ldo = ldo; c.mode = 2;
+    }
+    for (int kb0 = 0; kb0 < k_blocks; kb0 += mlb::TC_CHUNK_BLOCKS) {
+        c.kb0 = kb0;
+        c.k_blocks = (k_blocks - kb0 < mlb::TC_CHUNK_BLOCKS) ? k_blocks - kb0 : mlb::TC_CHUNK_BLOCKS;
+        c.accumulate = kb0 > 0;
+        mlb::cgemm_tc_kernel<<<grid, mlb::TC_THREADS, mlb::TC_SMEM, st>>>(maps, c);
+        if (int rc = mlb::check_launch("mlb_cgemm_tc(chunk)")) return rc;
+    }
+    if (mode == 1) {
+        for (int b = 0; b < batch; ++b) {
+            dim3 ge((rows + 127) / 128, cols_c);
+            mlb::tc_embed_kernel<<<ge, 128, 0, st>>>(reinterpret_cast<const float2 *>(h_scratch[b]), (size_t)ld_scratch,
+                                                     h_out_hi[b], h_out_lo[b], (size_t)ldo, rows, cols_c);
+            if (int rc = mlb::check_launch("mlb_cgemm_tc(embed)")) return rc;
+        }
+    }
+    return MLB_OK;
+}
+
+extern "C" int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,
+                            const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
+                            float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream) {
+    return cgemm_tc_impl(h_Ah, h_Al, lda, h_Bh, h_Bl, ldb, rows, cols_c, depth_c, mode, h_out_hi, h_out_lo, ldo, batch,
+                         nullptr, 0, stream);
+}
+
+extern "C" int mlb_cgemm_tc_split(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,
+                                  const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
+                                  float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch,
+                                  mlb_c64 *const *h_scratch, int ld_scratch, void *stream) {
+    MLB_REQUIRE(mode == 2 || h_scratch, "mlb_cgemm_tc_split: mode 1 needs a complex64 scratch per batch item");
+    static mlb_c64 *const dummy[4] = {nullptr, nullptr, nullptr, nullptr};
+    return cgemm_tc_impl(h_Ah, h_Al, lda, h_Bh, h_Bl, ldb, rows, cols_c, depth_c, mode, h_out_hi, h_out_lo, ldo, batch,
+                         h_scratch ? h_scratch : dummy, ld_scratch, stream);
 }

@@ -351,6 +351,8 @@ class FarfieldPlan:
         self.Jl = [f32(Mx, 2 * My) for _ in range(4)]
         self.TBh = [f32(2 * Ky, 2 * Mx) for _ in range(4)]
         self.TBl = [f32(2 * Ky, 2 * Mx) for _ in range(4)]
+        # partial sums of the chunked stage 1 (mlb_cgemm_tc_split): complex64 [Mx][Ky]
+        self.tc_scratch = [_c64_buffer(Mx, Ky, dev) for _ in range(4)]
         self.AxT = self.Ay = None
 
     def _steps_tc(self, ops, ld):
@@ -372,15 +374,19 @@ class FarfieldPlan:
         pAxh, k7 = _lib.ptr_array([self.AxA[0]] * 4)
         pAxl, k8 = _lib.ptr_array([self.AxA[1]] * 4)
         pF, k9 = _lib.ptr_array(self.Fhat)
+        pS, k10 = _lib.ptr_array(self.tc_scratch)
 
-        def stage1(keep=(k1, k2, k3, k4, k5, k6)):       # all four fields in one launch
-            _lib.check(lib.mlb_cgemm_tc(pJh, pJl, ldj, pAyh, pAyl, self.AyB[0].shape[1], Mx, Ky, My, 1,
-                                        pTh, pTl, self.TBh[0].shape[1], 4, _stream_ptr()), "mlb_cgemm_tc(stage 1)")
+        # both stages with the contraction split into 512-deep chunks whose partial sums are added with round-to-nearest
+        # (the tensor core's truncating accumulation is a bias that grows with the depth of a coherent sum)
+        def stage1(keep=(k1, k2, k3, k4, k5, k6, k10)):  # all four fields in one launch per chunk
+            _lib.check(lib.mlb_cgemm_tc_split(pJh, pJl, ldj, pAyh, pAyl, self.AyB[0].shape[1], Mx, Ky, My, 1,
+                                              pTh, pTl, self.TBh[0].shape[1], 4, pS, self.tc_scratch[0].shape[1],
+                                              _stream_ptr()), "mlb_cgemm_tc_split(stage 1)")
 
         def stage2(keep=(k7, k8, k9)):
-            _lib.check(lib.mlb_cgemm_tc(pAxh, pAxl, self.AxA[0].shape[1], pTh, pTl, self.TBh[0].shape[1],
-                                        Kx, Ky, Mx, 2, pF, None, self.Fhat[0].shape[1], 4, _stream_ptr()),
-                       "mlb_cgemm_tc(stage 2)")
+            _lib.check(lib.mlb_cgemm_tc_split(pAxh, pAxl, self.AxA[0].shape[1], pTh, pTl, self.TBh[0].shape[1],
+                                              Kx, Ky, Mx, 2, pF, None, self.Fhat[0].shape[1], 4, None, 0, _stream_ptr()),
+                       "mlb_cgemm_tc_split(stage 2)")
         return [("tf32_split", split, 4 * 24 * Mx * My, 0.0),
                 ("tc_stage1", stage1, 4 * (16 * Mx * My + 32 * Ky * Mx) + 16 * Ky * My, 32.0 * Mx * My * Ky),
                 ("tc_stage2", stage2, 4 * (32 * Ky * Mx + 8 * Kx * Ky) + 16 * Kx * Mx, 32.0 * Kx * Mx * Ky)]
