@@ -439,6 +439,9 @@ int mlb_peer_allgather(const void *src, long long src_pitch, int rows, long long
 /* Wait (on the device, in stream order) until every peer's pushes of the latest mlb_peer_allgather this rank ran have
  * landed in this rank's destination.  my_flags = this rank's flag block. */
 int mlb_peer_wait(const void *my_flags, int world, void *local_state, void *stream);
+/* mlb_peer_wait followed by mlb_sum_f64(in, n, scale, out) in one launch (total_P of the gathered block sums) */
+int mlb_peer_wait_sum(const void *my_flags, int world, void *local_state, const double *in, int n, double scale,
+                      double *out, void *stream);
 
 /* NCCL wrappers (libnccl resolved at run time; MLB_ERR_UNSUPPORTED if it cannot be found).  mlb_comm_unique_id on one
  * rank, ship the MLB_COMM_ID_BYTES bytes to the others by any means (the launcher's store, MPI, a file), then

@@ -95,6 +95,7 @@ SIGNATURES = {
                                      C.c_void_p, _PP, C.c_int, C.c_int, _PP, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                      C.c_void_p]),
     "mlb_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_peer_wait_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "mlb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "mlb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mlb_comm_destroy": (C.c_int, [C.c_void_p]),

@@ -145,6 +145,20 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const unsigned int *__res
         atomicExch(state + ST_ERROR, 1u);
 }
 
+// mlb_peer_wait followed by mlb_sum_f64 in one launch: the pushes have landed (block sums included), so total_P can be
+// finished right here -- one kernel less on the critical path of the one-aperture step
+__global__ void __launch_bounds__(256) peer_wait_sum_kernel(const unsigned int *__restrict__ my_flags, int world,
+                                                            unsigned int *__restrict__ state, const double *__restrict__ in,
+                                                            int n, double scale, double *__restrict__ out) {
+    __shared__ double ws[8];
+    const unsigned int e = state[ST_GATHER_EPOCH];
+    if ((int)threadIdx.x < world && !wait_flag(my_flags + FLAG_DONE * MLB_MAX_PEERS + threadIdx.x, e))
+        atomicExch(state + ST_ERROR, 1u);
+    __syncthreads();
+    const double s = ordered_sum_256(in, n, ws);
+    if (threadIdx.x == 0) out[0] = s * scale;
+}
+
 static int fill_ptrs(PeerPtrs &out, void *const *h, int world, const char *who) {
     MLB_REQUIRE(h != nullptr && world >= 1 && world <= MLB_MAX_PEERS, "%s: world %d (1..%d)", who, world, MLB_MAX_PEERS);
     for (int p = 0; p < MLB_MAX_PEERS; ++p) out.p[p] = nullptr;
@@ -165,6 +179,7 @@ static void preload_kernels() {
     cudaFuncGetAttributes(&fa, peer_barrier_kernel);
     cudaFuncGetAttributes(&fa, peer_allgather_kernel);
     cudaFuncGetAttributes(&fa, peer_wait_kernel);
+    cudaFuncGetAttributes(&fa, peer_wait_sum_kernel);
     done = true;
 }
 
@@ -221,4 +236,13 @@ extern "C" int mlb_peer_wait(const void *my_flags, int world, void *local_state,
     mlb::peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned int *>(my_flags), world,
                                                              reinterpret_cast<unsigned int *>(local_state));
     return mlb::check_launch("mlb_peer_wait");
+}
+
+extern "C" int mlb_peer_wait_sum(const void *my_flags, int world, void *local_state, const double *in, int n, double scale,
+                                 double *out, void *stream) {
+    MLB_REQUIRE(my_flags && local_state && world >= 1 && world <= MLB_MAX_PEERS && in && out && n >= 0,
+                "mlb_peer_wait_sum: bad arguments");
+    mlb::peer_wait_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned int *>(my_flags), world,
+                                                                  reinterpret_cast<unsigned int *>(local_state), in, n, scale, out);
+    return mlb::check_launch("mlb_peer_wait_sum");
 }

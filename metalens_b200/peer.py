@@ -129,6 +129,11 @@ class PeerChannel:
         _lib.check(self.lib.mlb_peer_wait(self.flags.data_ptr(), self.world, self.state.data_ptr(), _stream_ptr()),
                    "mlb_peer_wait")
 
+    def wait_sum(self, block_sums, n, scale, out):
+        """wait() and out[0] = scale * sum(block_sums[:n]) in one launch (same fixed order as mlb_sum_f64)."""
+        _lib.check(self.lib.mlb_peer_wait_sum(self.flags.data_ptr(), self.world, self.state.data_ptr(), block_sums.data_ptr(),
+                                              n, scale, out.data_ptr(), _stream_ptr()), "mlb_peer_wait_sum")
+
     def check(self):
         """Raise if any wait of this channel ever timed out (synchronises the device)."""
         if int(self.state[3].item()) != 0:

@@ -203,8 +203,9 @@ class SlabFarfield:
     def finish(self):
         """Every rank's slab of P (and block sums) has arrived; total_P summed in the single-GPU order."""
         if self.world > 1:
-            self.chan.wait()
-        self._sum()
+            self.chan.wait_sum(self.block_sums, self.nb_local * self.world, self.dux * self.duy, self.total)
+        else:
+            self._sum()
         return self.P, self.total
 
 
