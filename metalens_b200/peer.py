@@ -78,6 +78,7 @@ class VirtualPeers:
         class _View:
             world = outer.world
             device = outer.device
+            virtual = True           # every rank's waiting kernels share ONE GPU: exchanges must use few CTAs
 
             def __init__(self):
                 self.rank = rank

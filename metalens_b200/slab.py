@@ -76,13 +76,13 @@ class SlabFarfield:
     """Far field of one (Mx, My) aperture on the every-`stride`-th-FFT-bin grid, computed by `world` ranks.
 
     peers : a SymmetricPeers (one process per GPU) or a VirtualPeers.view(rank) (virtual ranks on one device).
-    gather_ctas: CTAs of the pushed all-gather of P; it is on the critical path with nothing else running, so it gets
-    most of the SMs (the tile exchange of sharding.py, which runs under an HBM-bound kernel, uses few).
+    gather_ctas: CTAs of the pushed all-gather of P (default 128 across real GPUs: it is on the critical path with nothing
+    else running, so it gets most of the SMs; 8 for virtual ranks, whose waiting kernels share one GPU).
     run(fields) takes THIS rank's rows of the four fields -- complex64 (len(x_rows), My) each, row order
     ``self.x_rows`` -- and returns (P (K1, K2) float32 complete on every rank, total_P device scalar).
     """
 
-    def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride, peers, name="slab", gather_ctas=128):
+    def __init__(self, shape, dxp, dyp, wavelength, n_glass, stride, peers, name="slab", gather_ctas=None):
         self.lib = lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
@@ -133,6 +133,8 @@ class SlabFarfield:
         self.block_sums = self._bs[:8 * self.nb_local * G].view(torch.float64)
         self.total = torch.zeros(1, dtype=torch.float64, device=dev)
         self.chan = PeerChannel(peers, name + ".chan")
+        if gather_ctas is None:          # virtual ranks share one GPU: their spinning CTAs must leave room for each other
+            gather_ctas = 8 if getattr(peers, "virtual", False) else 128
         self.gather_ctas = gather_ctas
         peers.sync()
         # fftshift bookkeeping of nearfield_farfield.py:18-20, :68 as index rolls
