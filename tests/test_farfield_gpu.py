@@ -866,6 +866,7 @@ def test_radix16_column_kernels_match_numpy():
         lib.mlb_set_option(b"r16_min_lg", 10)
 
 
+@pytest.mark.parametrize("M", [3375, 2700])
 def test_reference_default_grid_full_size_properties(M):
     """The reference's own usage at full size: a good_fft_number() aperture (3375 = 3^3 5^3, 2700 = 2^2 3^3 5^2),
     ALL FFT bins, through the big-radix mixed engine.  Size-independent properties: a sample of bins against the
