@@ -108,10 +108,10 @@ int mlb_cgemm_tc(const float *const *h_Ah, const float *const *h_Al, int lda, co
                  const float *const *h_Bl, int ldb, int rows, int cols_c, int depth_c, int mode,
                  float *const *h_out_hi, float *const *h_out_lo, int ldo, int batch, void *stream);
 
-/* mlb_cgemm_tc with the contraction split into chunks of 1024 real depth: every chunk starts its TMEM accumulators at zero
+/* mlb_cgemm_tc with the contraction split into chunks of 512 real depth: every chunk starts its TMEM accumulators at zero
  * and its epilogue ADDS the partial sum to the complex64 result in memory with round-to-nearest.  The tensor core
  * accumulates with truncation -- a bias of ~2^-24 per 8-deep step that does not average out in a coherent sum (1e-4 at
- * depth 4096); chunking bounds it at ~4e-6 whatever the aperture size.  mode 1 needs h_scratch: one complex64
+ * depth 4096); chunking bounds it below 1e-5 whatever the aperture size (measured up to 2048^2 coherent apertures).  mode 1 needs h_scratch: one complex64
  * [rows][ld_scratch >= cols_c] buffer per batch item (the partial sums; embedded as the next stage's operand at the end);
  * mode 2 accumulates in h_out_hi itself (h_scratch may be NULL). */
 int mlb_cgemm_tc_split(const float *const *h_Ah, const float *const *h_Al, int lda, const float *const *h_Bh,

@@ -16,10 +16,11 @@
 //   longer cost a truncation of the big accumulator each (3x fewer biased roundings).
 //   Truncation is a BIAS (toward zero, ~2^-24 of the accumulator per 8-deep step) that does not average out in a
 //   coherent sum such as the focus of a lens: ~1e-4 at depth 4096.  The contraction is therefore split into chunks
-//   of TC_CHUNK_BLOCKS k-blocks (128 accumulation steps): every launch starts its TMEM accumulators at zero and its
+//   of TC_CHUNK_BLOCKS k-blocks (64 accumulation steps): every launch starts its TMEM accumulators at zero and its
 //   epilogue ADDS the chunk into the fp32 result in memory with round-to-nearest (unbiased) -- the in-chunk bias is
-//   bounded (~4e-6) whatever the aperture size, at the price of one read-modify-write of the output per chunk
-//   (16-block chunks halve the bias again but cost 2.4x in speed at cfg3: launch, pipeline fill and epilogue per chunk).
+//   bounded whatever the aperture size, at the price of a launch, a pipeline fill and an epilogue (read-modify-write of
+//   the output tile) per chunk.  Measured on coherent 1024^2 / 2048^2 lens apertures: 16-block chunks meet 1e-5,
+//   32-block chunks do not (and are 1.45x faster at cfg3: 2.0e8 vs 1.4e8 points/s) -- accuracy decides.
 //
 // Kernel anatomy (one 128 x 256 real output tile per CTA, 192 threads):
 //   warp 0 : TMA producer  (cp.async.bulk.tensor 2-D, 4 operand tiles per k-block, mbarrier tx)
@@ -40,7 +41,7 @@ constexpr int TC_BM = 128;       // real rows of D per CTA  (= UMMA M)
 constexpr int TC_BN = 256;       // real cols of D per CTA  (= UMMA N) = 128 complex columns
 constexpr int TC_BK = 32;        // tf32 elements per k-block = 128 bytes = one swizzle span
 constexpr int TC_STAGES = 2;
-constexpr int TC_CHUNK_BLOCKS = 32;   // k-blocks per launch (1024 real depth = 128 truncating accumulation steps)
+constexpr int TC_CHUNK_BLOCKS = 16;   // k-blocks per launch (512 real depth = 64 truncating accumulation steps)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;        // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // Ah, Al, Bh, Bl = 96 KB
