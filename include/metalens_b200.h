@@ -283,6 +283,13 @@ typedef struct mlb_table_pack {
     double u0_first, u0_inv_step, u1_first, u1_inv_step;
 } mlb_table_pack;
 
+/* Device-side packing of one collection's tables (SURVEY 8b "mlb_table_pack"; the name is taken by the struct): raw = the interpolators' value arrays as the
+ * reference holds them (grating.py:1227-1229, lens_center.py:222-223), complex128 [order][slot][iu][iv][ig] with slot =
+ * 2*pol + amp -> values (complex128) and values_f32 (complex64), both [order][iu][iv][ig][slot] as mlb_table_pack.values
+ * / values_f32 expect. */
+int mlb_table_pack_build(const double *raw, int n_orders, int n_ux, int n_uy, int n_g, double *values, float *values_f32,
+                   void *stream);
+
 /* Everything build_nearfield (nearfield.py:66-480) reads, as device arrays + scalars. */
 typedef struct mlb_lens_desc {
     const double *x_pts, *y_pts;          /* sample coordinates, nx and ny entries          */

@@ -639,6 +639,22 @@ __global__ void nearfield_ring_tables_kernel(const __grid_constant__ mlb_lens_de
     }
 }
 
+// mlb_table_pack_build: the interpolator value arrays as the reference holds them -- one (n_ux, n_uy, n_g) complex128 array per
+// (order, slot), stacked [order][slot][iu][iv][ig] -- into the layout the assembly kernel gathers from,
+// [order][iu][iv][ig][slot] (the four values a corner needs adjacent), as complex128 and as complex64.
+__global__ void table_pack_kernel(const double2 *__restrict__ raw, int n_orders, int cells, double2 *__restrict__ values,
+                                  float2 *__restrict__ values_f32) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // output index
+    const long long total = (long long)n_orders * cells * 4;
+    if (e >= total) return;
+    const int slot = (int)(e & 3);
+    const long long oc = e >> 2;                                               // order * cells + cell
+    const long long o = oc / cells, cell = oc - o * cells;
+    const double2 v = raw[(o * 4 + slot) * cells + cell];
+    values[e] = v;
+    values_f32[e] = make_float2((float)v.x, (float)v.y);
+}
+
 __global__ void table_eval_kernel(const double *__restrict__ axes, int n0, int n1, int n2,
                                   const double2 *__restrict__ values, const double *__restrict__ pts, int n,
                                   double2 *__restrict__ out) {
@@ -824,6 +840,20 @@ extern "C" int mlb_nearfield_fixup(const mlb_lens_desc *h_desc, void *Ex, void *
     MLB_REQUIRE(fix_samples && fix_cells && n_fix > 0, "mlb_nearfield_fixup: empty fix-up list");
     return nearfield_launch(h_desc, Ex, Ey, Hx, Hy, ld, out_is_double, nullptr, nullptr, 0, violation, nullptr, nullptr, 0,
                             fix_samples, fix_cells, n_fix, stream, "mlb_nearfield_fixup");
+}
+
+extern "C" int mlb_table_pack_build(const double *raw, int n_orders, int n_ux, int n_uy, int n_g, double *values,
+                              float *values_f32, void *stream) {
+    MLB_REQUIRE(raw && values && values_f32 && n_orders >= 0 && n_ux >= 2 && n_uy >= 2 && n_g >= 2,
+                "mlb_table_pack_build: bad arguments");
+    MLB_REQUIRE(mlb::aligned16(raw) && mlb::aligned16(values) && mlb::aligned16(values_f32), "mlb_table_pack_build: buffers not 16-byte aligned");
+    if (n_orders == 0) return MLB_OK;
+    const int cells = n_ux * n_uy * n_g;
+    const long long total = (long long)n_orders * cells * 4;
+    mlb::table_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2 *>(raw), n_orders, cells, reinterpret_cast<double2 *>(values),
+        reinterpret_cast<float2 *>(values_f32));
+    return mlb::check_launch("mlb_table_pack_build");
 }
 
 extern "C" int mlb_table_eval(const double *axes, int n0, int n1, int n2, const double *values, const double *pts,

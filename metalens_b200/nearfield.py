@@ -138,9 +138,13 @@ class NearfieldPlan:
         for p in self.packs + [self.hex_pack]:
             p.stats_slot = slot
             slot += len(p.orders)
-            flat = p.values.reshape(-1)
-            self._pack_dev.append((up(p.axes, np.float64), up(flat.view(np.float64), np.float64),
-                                   up(flat.astype(np.complex64).view(np.float32), np.float32),
+            # upload the interpolators' arrays as they are; the gather layout (and its complex64 copy) is made on the device
+            raw = up(p.raw.reshape(-1).view(np.float64), np.float64)
+            vals = torch.empty(raw.numel(), dtype=torch.float64, device=dev)
+            vals32 = torch.empty(raw.numel(), dtype=torch.float32, device=dev)
+            _lib.check(self.lib.mlb_table_pack_build(raw.data_ptr(), len(p.orders), p.n[0], p.n[1], p.n[2], vals.data_ptr(),
+                                               vals32.data_ptr(), _stream_ptr()), "mlb_table_pack_build")
+            self._pack_dev.append((up(p.axes, np.float64), vals, vals32,
                                    up(p.order_array, np.int32), up(p.order_map, np.int32)))
         self.n_stats = slot
 

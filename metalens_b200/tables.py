@@ -98,10 +98,13 @@ class TablePack:
                 else:
                     assert all(np.array_equal(a, b) for a, b in zip(grid, g)), "tables of one collection share axes"
                 slot_vals.append(np.asarray(f.values, dtype=np.complex128))
-            blocks.append(np.stack(slot_vals, axis=-1))            # [iu][iv][ig][slot]
+            blocks.append(np.stack(slot_vals, axis=0))             # [slot][iu][iv][ig]: the arrays as the reference holds them
         self.grid = grid
         self.n = tuple(a.size for a in grid)
-        self.values = np.ascontiguousarray(np.stack(blocks, axis=0))   # [order][iu][iv][ig][slot]
+        # raw: what is uploaded; the interleaved layout [order][iu][iv][ig][slot] the kernel gathers from is made on the
+        # device by mlb_table_pack_build (NearfieldPlan).  `values` is the same interleaving on the host, for tests / the oracle.
+        self.raw = np.ascontiguousarray(np.stack(blocks, axis=0)) if blocks else np.zeros((0, 4) + tuple(a.size for a in grid), complex)
+        self.values = np.ascontiguousarray(np.moveaxis(self.raw, 1, -1))   # [order][iu][iv][ig][slot]
         self.bounds = tuple(float(b) for b in owner.interpolator_bounds)
         self.axes = np.concatenate(grid)
         # uniformly spaced ux / uy axes (what characterize() produces): the kernel may locate cells arithmetically
