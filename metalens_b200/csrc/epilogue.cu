@@ -134,19 +134,23 @@ __global__ void __launch_bounds__(EPI_THREADS) ff_epilogue_kernel(EpiArgs a) {
     }
 }
 
-// Two adjacent far-field points per thread (16-byte loads of the four aperture sums, 8-byte store of P): the
-// float32-output flavour for even row lengths.  Same arithmetic as ff_epilogue_kernel<true> except that
+// Two adjacent far-field points per thread (16-byte loads of the four aperture sums, 8-byte store of P where the
+// pitch of P allows): the float32-output flavour for even-pitched aperture sums, any row length.  Same arithmetic as ff_epilogue_kernel<true> except that
 // sin(theta) and the final quotient are formed in fp32 (relative error ~1e-7); the evanescent mask, the DC test
-// and the unit-system dependent scale stay in float64.  128 threads x 2 points keeps the block count (and the
-// block_sums layout) of mlb_ff_epilogue_blocks().
-__global__ void __launch_bounds__(EPI_THREADS / 2) ff_epilogue_x2_kernel(EpiArgs a) {
-    const long long n = ((long long)blockIdx.x * (EPI_THREADS / 2) + threadIdx.x) * 2;
-    const long long total = (long long)a.Kx * a.Ky;
+// and the unit-system dependent scale stay in float64.  128 threads x 2 points per block: mlb_ff_epilogue_blocks()
+// counts pairs per row, so every flavour launches (and fills block_sums for) the same number of blocks.
+__global__ void __launch_bounds__(EPI_THREADS / 2) ff_epilogue_x2_kernel(EpiArgs a, int vec_store) {
+    // pair n covers points (i, j) and (i, j + 1), j even; an odd row length leaves the last pair of a row half empty
+    // (the loads still hit the even-pitched buffers, the second point is neither stored nor summed)
+    const int ppr = (a.Ky + 1) >> 1;
+    const long long n = (long long)blockIdx.x * (EPI_THREADS / 2) + threadIdx.x;
+    const long long total = (long long)a.Kx * ppr;
     double sum = 0.0;
     if (n < total) {
-        const int i = (int)(n / a.Ky), j = (int)(n % a.Ky);
+        const int i = (int)(n / ppr), j = (int)(n % ppr) * 2;
+        const bool second = j + 1 < a.Ky;
         const double ux = a.ux[i];
-        const double2 uy2v = *reinterpret_cast<const double2 *>(a.uy + j);
+        const double2 uy2v = make_double2(a.uy[j], second ? a.uy[j + 1] : 0.0);
         const size_t off = (size_t)i * a.ldf + j;
         const float4 fex = *reinterpret_cast<const float4 *>(a.F[0] + off), fey = *reinterpret_cast<const float4 *>(a.F[1] + off);
         const float4 fhx = *reinterpret_cast<const float4 *>(a.F[2] + off), fhy = *reinterpret_cast<const float4 *>(a.F[3] + off);
@@ -177,10 +181,16 @@ __global__ void __launch_bounds__(EPI_THREADS / 2) ff_epilogue_x2_kernel(EpiArgs
             const float qf = (fabs2(t1) + fabs2(t2)) / (uzf + 1e-5f);
             const double p = scale * (double)qf;
             pf[q] = (float)p;
+            if (q == 1 && !second) break;
             if (a.accumulate) pf[q] += dst[q];
             if (isfinite(pf[q])) sum += p;
         }
-        *reinterpret_cast<float2 *>(dst) = make_float2(pf[0], pf[1]);
+        if (second && vec_store) {
+            *reinterpret_cast<float2 *>(dst) = make_float2(pf[0], pf[1]);
+        } else {
+            dst[0] = pf[0];
+            if (second) dst[1] = pf[1];
+        }
     }
     if (a.block_sums) {
 #pragma unroll
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(256) sum_f64_kernel(const double *__restrict__
 }  // namespace mlb
 
 extern "C" int mlb_ff_epilogue_blocks(int Kx, int Ky) {
-    long long t = (long long)Kx * Ky;
+    long long t = (long long)Kx * ((Ky + 1) / 2) * 2;          // whole pairs per row (odd rows end in a half pair)
     return (int)((t + mlb::EPI_THREADS - 1) / mlb::EPI_THREADS);
 }
 
@@ -273,11 +283,11 @@ extern "C" int mlb_ff_epilogue(const mlb_c64 *const *h_Fhat, int ldf, const doub
         mlb::ff_epilogue_kernel<false, true><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
         return mlb::check_launch("mlb_ff_epilogue(complex128)");
     }
-    bool x2 = !p_is_double && Ky % 2 == 0 && ldf % 2 == 0 && ldp % 2 == 0 && (reinterpret_cast<uintptr_t>(P) & 7u) == 0 &&
-              mlb::aligned16(uy);
+    bool x2 = !p_is_double && ldf % 2 == 0;
     for (int f = 0; f < 4; ++f) x2 = x2 && mlb::aligned16(a.F[f]);
+    const int vec_store = (ldp % 2 == 0 && (reinterpret_cast<uintptr_t>(P) & 7u) == 0) ? 1 : 0;
     if (p_is_double) mlb::ff_epilogue_kernel<false><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
-    else if (x2) mlb::ff_epilogue_x2_kernel<<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS / 2, 0, (cudaStream_t)stream>>>(a);
+    else if (x2) mlb::ff_epilogue_x2_kernel<<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS / 2, 0, (cudaStream_t)stream>>>(a, vec_store);
     else mlb::ff_epilogue_kernel<true><<<mlb_ff_epilogue_blocks(Kx, Ky), mlb::EPI_THREADS, 0, (cudaStream_t)stream>>>(a);
     return mlb::check_launch("mlb_ff_epilogue");
 }
