@@ -119,8 +119,8 @@ __device__ __forceinline__ void gather4(const mlb_table_pack &p, int order, cons
 }
 
 // e^{i x}: float64 sincos for the complex128 output; for the complex64 output the argument is reduced
-// to [-1/2, 1/2] turns in float64 (exact to ~1e-16 turns) and the sine/cosine taken in fp32 (abs. error
-// ~1e-7, below the output's own rounding).
+// to [-1/2, 1/2] turns in float64 (exact to ~1e-16 turns) and the sine/cosine taken by the special-function unit
+// (abs. error 4e-7, well inside the complex64 tolerance of the path).
 struct cf { float re, im; };
 __device__ __forceinline__ cf operator+(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
 __device__ __forceinline__ cf operator*(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
@@ -140,27 +140,6 @@ __device__ __forceinline__ double rsqrt_fast(double v) {
 __device__ __forceinline__ cplx expi(double x) {
     double s, c;
     sincos(x, &s, &c);
-    return {c, s};
-}
-// (cos, sin)(pi r) for |r| <= 1: quadrant q = rint(2r), Taylor polynomials on |z| = |r - q/2| <= 1/4 (truncation
-// < 3e-8, below the fp32 rounding); the library sincospif spends a third of its instructions on arguments
-// that cannot occur here
-__device__ __forceinline__ cf cospi_sinpi_unit(float r) {
-    const float q = rintf(r + r);
-    const float z = fmaf(q, -0.5f, r), z2 = z * z;
-    float sp = fmaf(z2, 0.0821458866f, -0.599264529f);        // pi^9/9!, -pi^7/7!
-    sp = fmaf(sp, z2, 2.55016404f);                           // pi^5/5!
-    sp = fmaf(sp, z2, -5.16771278f);                          // -pi^3/3!
-    sp = fmaf(sp, z2, 3.14159265f);
-    const float s0 = sp * z;
-    float cp = fmaf(z2, 0.235330630f, -1.33526277f);          // pi^8/8!, -pi^6/6!
-    cp = fmaf(cp, z2, 4.05871213f);                           // pi^4/4!
-    cp = fmaf(cp, z2, -4.93480220f);                          // -pi^2/2
-    const float c0 = fmaf(cp, z2, 1.0f);
-    const int iq = (int)q;                                    // -2..2
-    float s = (iq & 1) ? c0 : s0, c = (iq & 1) ? s0 : c0;
-    if (iq & 2) s = -s;
-    if (((iq >> 1) ^ iq) & 1) c = -c;
     return {c, s};
 }
 __device__ __forceinline__ cf expi_fast(double x) {
