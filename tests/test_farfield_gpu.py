@@ -51,6 +51,30 @@ def test_dropin_farfield_from_nearfield(name, golden_dir):
     assert dux == g["dux"] and duy == g["duy"]
 
 
+@pytest.mark.parametrize("name,rot", [("lens675_seed9", False), ("lens675_seed9_rot", True)])
+def test_reference_default_size_675_against_reference(name, rot, golden_dir):
+    """675 x 675 (the reference's own typical grid: good_fft_number, odd, 3^3 5^2 -> mixed-radix FFT passes, odd-row
+    epilogue) against a sampled subset of the UNMODIFIED reference's map; and the strict drop-in on the same case."""
+    from metalens_b200.farfield import farfield_from_fields, farfield_from_nearfield
+    g = golden(golden_dir, name)
+    wl, ng = float(g["wavelength"]), float(g["n_glass"])
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(675, 9, wl, ng, rotate=rot)
+    P, total, ux, uy, dux, duy = farfield_from_fields(Ex, Ey, Hx, Hy, x, y, wl, ng, stride=1, method="fft",
+                                                      p_dtype=torch.float32)
+    got = P.ravel()[g["index"]]
+    assert np.array_equal(np.isnan(got), np.isnan(g["P"])) and int(np.isnan(P).sum()) == int(g["nan_count"])
+    fin = np.isfinite(g["P"])
+    assert np.abs(got - g["P"])[fin].max() / float(g["P_max"]) < FF_TOL
+    assert abs(total - float(g["total_P"])) <= FF_TOL * abs(float(g["total_P"]))
+    np.testing.assert_array_equal(ux.ravel(), g["ux"])
+    f = [np.fft.fft2(np.fft.fftshift(a.astype(complex))) for a in (Ex, Ey, Hx, Hy)]
+    P2, total2, *_ = farfield_from_nearfield(f[0], f[1], f[2], f[3], list(x), list(y), wl, ng)
+    got2 = P2.ravel()[g["index"]]
+    assert np.array_equal(np.isnan(got2), np.isnan(g["P"]))
+    assert np.abs(got2 - g["P"])[fin].max() / float(g["P_max"]) < 1e-11
+    assert abs(total2 - float(g["total_P"])) <= 1e-11 * abs(float(g["total_P"]))
+
+
 @pytest.mark.parametrize("method", ["auto", "dense"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_fields_to_farfield_all_bins(name, method, golden_dir):

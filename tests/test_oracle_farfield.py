@@ -36,6 +36,22 @@ def test_reference_path_matches_golden(name, golden_dir):
     assert dux == g["dux"] and duy == g["duy"]
 
 
+@pytest.mark.parametrize("name,rot", [("lens675_seed9", False), ("lens675_seed9_rot", True)])
+def test_reference_path_matches_mid_golden(name, rot, golden_dir):
+    """675 x 675: the reference's own typical default grid size (good_fft_number, odd, 3^3 5^2), sampled subset of the
+    UNMODIFIED reference's map (tests/golden/make_farfield_mid_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "farfield_%s.npz" % name))
+    wl, ng = float(g["wavelength"]), float(g["n_glass"])
+    Ex, Ey, Hx, Hy, x, y = apertures.focusing_lens(675, 9, wl, ng, rotate=rot)
+    P, total, ux, uy, dux, duy = fo.farfield_reference_path(Ex, Ey, Hx, Hy, x, y, wl, ng)
+    got = P.ravel()[g["index"]]
+    assert np.array_equal(np.isnan(got), np.isnan(g["P"])) and int(np.isnan(P).sum()) == int(g["nan_count"])
+    fin = np.isfinite(g["P"])
+    assert np.abs(got - g["P"])[fin].max() / float(g["P_max"]) < 1e-12
+    assert abs(total - float(g["total_P"])) <= 1e-12 * abs(float(g["total_P"]))
+    np.testing.assert_allclose(ux.ravel(), g["ux"], rtol=0, atol=1e-15)
+
+
 def test_known_answers(golden_dir):
     """SURVEY KAT-1..3: energy conservation of the transform."""
     g = np.load(os.path.join(golden_dir, "farfield_kat1_uniform.npz"))
