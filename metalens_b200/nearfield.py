@@ -503,17 +503,22 @@ def build_nearfield(source_x, source_y, source_z, source_pol, wavelength,
     """
     assert source_z < 0                                                        # :84
     assert source_pol in ('x', 'y', 'z')                                       # :85
-    plan = _plan_for(wavelength, lens_periphery_summary, lens_center_summary, hexgridset)
-    if x_pts is None:
-        x_pts = plan.default_grid()                                            # :95-99
-    if y_pts is None:
-        y_pts = plan.default_grid()                                            # :100-104
-    for l in (x_pts, y_pts):                                                   # :106-109
+    def check_axis(l):                                                         # :106-109
         steps = np.diff(np.asarray(l, dtype=float))
         assert 0 < steps[0] < wavelength / 2
         assert steps.max() - steps.min() <= 1e-9 * np.abs(steps).max()
+    for l in (x_pts, y_pts):               # the caller's axes are judged before any device work, like the reference
+        if l is not None:
+            check_axis(l)
     if source_z == -inf:
         assert source_pol != 'z'                                               # :224
+    plan = _plan_for(wavelength, lens_periphery_summary, lens_center_summary, hexgridset)
+    if x_pts is None:
+        x_pts = plan.default_grid()                                            # :95-99
+        check_axis(x_pts)
+    if y_pts is None:
+        y_pts = plan.default_grid()                                            # :100-104
+        check_axis(y_pts)
     out, power = plan.run(source_x, source_y, source_z, source_pol, x_pts, y_pts, dipole_moment=dipole_moment,
                           out_dtype=torch.complex128, verbose=verbose, ties="reference")
     ny = len(y_pts)
