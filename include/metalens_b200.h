@@ -198,7 +198,11 @@ int mlb_fft_cols_power_total(const mlb_c64 *const *h_in, int ld_in, int N, int n
  *                        long columns as A x B in two passes, the first in place on the INPUT buffer unless the call is
  *                        in place): 1 (default) = one-butterfly-per-thread register kernels where they pay (long
  *                        transforms that keep >= 80 % of a CTA's threads busy), 2 = wherever they apply, 0 = never
- *   mixed_occupancy      resident CTAs per SM those kernels are compiled for: 0 (default: rows 2, columns 4), 2..4
+ *   mixed_compiled       1 (default) = those register kernels run the instantiation compiled for the plan (radices,
+ *                        sub-lengths, lanes and padding as constants: no spills, half the registers; every plan the
+ *                        dispatch sends there has one), 0 = the generic kernels that read the plan at run time
+ *   mixed_occupancy      resident CTAs per SM those kernels are compiled for: 0 (default: compiled plans 4; generic rows
+ *                        2, columns 4), 2..4 (compiled plans: 3 or 4)
  *   cols_strip_mb        two-pass (>= 4096-point) column transforms run strip by strip, strips of this many MB of all
  *                        fields (intermediate stays in L2); 0 (default) = one strip
  *   r16_min_lg           the radix-16 kernels serve lengths from 2^this up (default 10; 8..13), the radix-4 ones below

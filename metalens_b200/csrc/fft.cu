@@ -845,6 +845,7 @@ static int g_r16_min_lg = 10;          // radix-16 kernels from 2^this points up
 static int g_mixed_occ = 0;            // register kernels of the big-radix engine: resident CTAs per SM they are compiled for
                                        // (2..4; 0 = default: rows 2, columns 4 -- measured on B200, scripts/allbins_kernels.py)
 static int g_mixed_reg = 1;            // big-radix engine: use the one-butterfly-per-thread register kernels where they apply
+static int g_mixed_ct = 1;             // register kernels of the big-radix engine: 1 = the instantiation compiled for the plan (default), 0 = generic
 static int g_cols_power_wide = -1;     // fused column+power pass: 1 = 4096-point tiles / 1024 threads, 0 = 2048 / 512,
                                        // -1 = by length (wide from 1024 points up: measured faster on B200)
 static int g_rows_plain = 1, g_rows_points = 1024, g_rows_threads = 256, g_rows_vec = 2, g_rows_tma = 1, g_cols_half = 0;
@@ -908,6 +909,7 @@ extern "C" int mlb_set_option(const char *name, int value) {
     else if (n == "rows_ring_kb") { MLB_REQUIRE(value == 64 || value == 128, "rows_ring_kb: 64 or 128"); mlb::g_rows_ring_kb = value; }
     else if (n == "cols_power_wide") mlb::g_cols_power_wide = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "mixed_registers") { MLB_REQUIRE(value >= 0 && value <= 2, "mixed_registers: 0..2"); mlb::g_mixed_reg = value; }
+    else if (n == "mixed_compiled") mlb::g_mixed_ct = value ? 1 : 0;
     else if (n == "mixed_occupancy") { MLB_REQUIRE(value == 0 || (value >= 2 && value <= 4), "mixed_occupancy: 0, 2..4"); mlb::g_mixed_occ = value; }
     else if (n == "cols_strip_mb") { MLB_REQUIRE(value >= 0 && value <= 4096, "cols_strip_mb: 0..4096"); mlb::g_cols_strip_mb = value; }
     else MLB_REQUIRE(false, "mlb_set_option: unknown option '%s'", name);
@@ -928,6 +930,7 @@ extern "C" int mlb_get_option(const char *name) {
     if (n == "cols_strip_mb") return mlb::g_cols_strip_mb;
     if (n == "mixed_registers") return mlb::g_mixed_reg;
     if (n == "mixed_occupancy") return mlb::g_mixed_occ;
+    if (n == "mixed_compiled") return mlb::g_mixed_ct;
     return -1;
 }
 
@@ -996,6 +999,33 @@ static int mix2_max_per(const Mix2Args &m) {
     for (int s = 0; s < m.nstage; ++s) mx = (m.N / m.radix[s] > mx) ? m.N / m.radix[s] : mx;
     return mx;
 }
+// compile-time plans of the register kernels (fftmix.cuh): every plan the dispatch below sends there
+typedef void (*Mix2Kernel)(const Mix2Args);
+struct Mix2CtEntry { int r0, r1, r2; Mix2Kernel fn[2]; };
+#define MIX2_CT_ROW(r0, r1, r2) {r0, r1, r2, {mix2_ct_kernel<false, 3, r0, r1, r2>, mix2_ct_kernel<false, 4, r0, r1, r2>}}
+#define MIX2_CT_COL(r0, r1) {r0, r1, 1, {mix2_ct_kernel<true, 3, r0, r1, 1>, mix2_ct_kernel<true, 4, r0, r1, 1>}}
+static const Mix2CtEntry mix2_ct_rows[] = {         // N = 2160, 2250, 2304, 2400, 2560, 2700, 2880, 3072, 3375, 3600, 3840
+    MIX2_CT_ROW(15, 9, 16), MIX2_CT_ROW(15, 15, 10), MIX2_CT_ROW(9, 16, 16), MIX2_CT_ROW(15, 10, 16), MIX2_CT_ROW(10, 16, 16),
+    MIX2_CT_ROW(15, 15, 12), MIX2_CT_ROW(15, 12, 16), MIX2_CT_ROW(12, 16, 16), MIX2_CT_ROW(15, 15, 15), MIX2_CT_ROW(15, 15, 16),
+    MIX2_CT_ROW(15, 16, 16)};
+static const Mix2CtEntry mix2_ct_cols[] = {         // B = 30 .. 240: the second pass of N = A B columns (and short direct columns)
+    MIX2_CT_COL(15, 2), MIX2_CT_COL(15, 3), MIX2_CT_COL(15, 4), MIX2_CT_COL(15, 5), MIX2_CT_COL(15, 6), MIX2_CT_COL(15, 8),
+    MIX2_CT_COL(15, 9), MIX2_CT_COL(9, 16), MIX2_CT_COL(15, 10), MIX2_CT_COL(10, 16), MIX2_CT_COL(15, 12), MIX2_CT_COL(12, 16),
+    MIX2_CT_COL(15, 15), MIX2_CT_COL(15, 16)};
+#undef MIX2_CT_ROW
+#undef MIX2_CT_COL
+// the instantiation for plan m (lanes, padding and radices must all match), or NULL; occ = resident CTAs it is compiled for
+template <size_t NE>
+static Mix2Kernel mix2_ct_find(const Mix2CtEntry (&tab)[NE], const Mix2Args &m, int lanes, int occ) {
+    if (!g_mixed_ct || m.lanes != lanes || (m.nstage != 2 && m.nstage != 3)) return nullptr;
+    const int r2 = (m.nstage == 3) ? m.radix[2] : 1;
+    for (const Mix2CtEntry &e : tab)
+        if (e.r0 == m.radix[0] && e.r1 == m.radix[1] && e.r2 == r2 && m.N == e.r0 * e.r1 * e.r2 &&
+            m.pad_sh == ((e.r0 & 1) ? 30 : 4))
+            return e.fn[occ == 3 ? 0 : 1];
+    return nullptr;
+}
+
 template <int A>
 static void mix2_launch_first(const Mix2FirstArgs &f, dim3 grid, cudaStream_t st) { mix2_cols_first_kernel<A><<<grid, 256, 0, st>>>(f); }
 static int mix2_first(int A, const Mix2FirstArgs &f, int batch, cudaStream_t st) {
@@ -1080,6 +1110,10 @@ static int fft_rows_impl(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *const *
             m2.lanes = rl; m2.lg_lanes = 0;
             dim3 grid((n_rows + rl - 1) / rl, batch);
             const size_t sm2 = mlb::mix2_smem(N, rl) / 2;
+            if (mlb::Mix2Kernel ct = (sm2 <= 48 * 1024) ? mlb::mix2_ct_find(mlb::mix2_ct_rows, m2, 1, mlb::g_mixed_occ) : nullptr) {
+                ct<<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
+                return mlb::check_launch("mlb_fft_rows(mixed radix, compiled plan)");
+            }
             if (mlb::g_mixed_occ == 4) mlb::mix2_reg_kernel<false, 4><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
             else if (mlb::g_mixed_occ == 3) mlb::mix2_reg_kernel<false, 3><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
             else mlb::mix2_reg_kernel<false, 2><<<grid, 256, sm2, (cudaStream_t)stream>>>(m2);
@@ -1379,6 +1413,10 @@ extern "C" int mlb_fft_cols(const mlb_c64 *const *h_in, int ld_in, mlb_c64 *cons
             m2.lanes = rl; m2.lg_lanes = mlb::ilog2(rl);   // one butterfly per thread and stage: register variant
             dim3 gr((n_cols + rl - 1) / rl, A, batch);
             const size_t sm2 = mlb::mix2_smem(B, rl) / 2;
+            if (mlb::Mix2Kernel ct = (sm2 <= 48 * 1024) ? mlb::mix2_ct_find(mlb::mix2_ct_cols, m2, mlb::MIX2_CT_COL_LANES, mlb::g_mixed_occ) : nullptr) {
+                ct<<<gr, 256, sm2, st>>>(m2);
+                return mlb::check_launch("mlb_fft_cols(mixed radix, compiled plan)");
+            }
             if (mlb::g_mixed_occ == 2) mlb::mix2_reg_kernel<true, 2><<<gr, 256, sm2, st>>>(m2);
             else if (mlb::g_mixed_occ == 3) mlb::mix2_reg_kernel<true, 3><<<gr, 256, sm2, st>>>(m2);
             else mlb::mix2_reg_kernel<true, 4><<<gr, 256, sm2, st>>>(m2);

@@ -414,4 +414,113 @@ __global__ void __launch_bounds__(256, MINB) mix2_reg_kernel(const Mix2Args a) {
     }
 }
 
+// ---- compile-time plans of the register variant ----------------------------------------------------------------------
+// The register kernels serve few plans -- rows: the 11 three-stage lengths 2160..3840 (one row per CTA); second column
+// pass: 14 two-stage sub-lengths 30..240 with 16 columns per CTA -- so every plan gets its own instantiation: radices,
+// sub-lengths, lane count and padding are constants, the per-stage switch, the multiply-high index arithmetic and the
+// spills of the generic kernel (128 registers and still 2 KB of spill stores for rows) are gone, and a stage is the
+// same code as mix2_reg_stage with those constants folded in.
+template <int L> struct MixLg { static constexpr int value = (L <= 1) ? 0 : 1 + MixLg<L / 2>::value; };
+
+template <int R, bool COLS, int N, int NS, int LANES, int SH, bool FIRST, bool LAST>
+__device__ __forceinline__ void mix2_ct_stage(const Mix2Args &a, float2 *__restrict__ sm, const float2 *__restrict__ in,
+                                              float2 *__restrict__ out, int first_unit, int g) {
+    constexpr int per = N / R, total = per * LANES, pitch = mixpad(N, SH) + 1, mul = COLS ? LANES : 1;
+    static_assert(total <= 256 && N % (NS * R) == 0, "one butterfly per thread and stage");
+    const int idx = threadIdx.x;
+    const bool act = idx < total;
+    int lane, j;
+    if constexpr (COLS) { lane = idx & (LANES - 1); j = idx >> MixLg<LANES>::value; }
+    else { lane = idx / per; j = idx - lane * per; }
+    const int unit = first_unit + lane;                   // row (rows kernel) or column (columns kernel) of this lane
+    const bool live = act && unit < a.other;
+    const int base = COLS ? lane : lane * pitch;
+    float2 v[R];
+    if constexpr (FIRST) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = make_float2(0.f, 0.f);
+        if (live) {
+            if constexpr (COLS) {
+                const float2 *src = in + ((g * a.in_gs + j * a.in_rs) * a.ld_in + unit);
+                const int stride = per * a.in_rs * a.ld_in;
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[r] = src[r * stride];
+            } else {
+                int rs = unit - a.in_roll_r; if (rs < 0) rs += a.other;
+                if (a.s1 == 1 && a.s2 == 1) {
+                    const float2 *row = in + (size_t)rs * a.ld_in;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        int cs = j + r * per - a.in_roll_c; if (cs < 0) cs += N;
+                        v[r] = __ldcs(row + cs);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int t1 = 0; t1 < a.s1; ++t1) {
+                        const float2 *row = in + (size_t)(rs + t1 * a.other) * a.ld_in;
+#pragma unroll 1
+                        for (int t2 = 0; t2 < a.s2; ++t2) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                int cs = j + r * per - a.in_roll_c; if (cs < 0) cs += N;
+                                const float2 x = __ldcs(row + (size_t)t2 * N + cs);
+                                v[r].x += x.x; v[r].y += x.y;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = sm[base + mixpad(j + r * per, SH) * mul];
+        }
+        __syncthreads();                                  // everyone has read the previous stage's output
+    }
+    const int k = (NS == 1) ? 0 : j % NS;
+    if (act) {
+        if constexpr (NS > 1) mix_twiddle<R>(v, __ldg(a.tw + k * ((N / (NS * R)) * a.tw_mul)));
+        dft_mix<R>(v);
+        const int o0 = (j - k) * R + k;
+        if constexpr (!LAST) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) sm[base + mixpad(o0 + q * NS, SH) * mul] = v[mix_slot<R>(q)];
+        } else if (live) {
+            if constexpr (COLS) {
+                float2 *dst = out + unit;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    int orow = g * a.out_gs + (o0 + q * NS) * a.out_rs + a.roll;
+                    if (orow >= a.Ntot) orow -= a.Ntot;
+                    dst[orow * a.ld_out] = v[mix_slot<R>(q)];
+                }
+            } else {
+                float2 *dst = out + (size_t)unit * a.ld_out;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    int n = o0 + q * NS + a.out_roll; if (n >= N) n -= N;
+                    dst[n] = v[mix_slot<R>(q)];
+                }
+            }
+        }
+    }
+    if constexpr (!LAST) __syncthreads();
+}
+
+constexpr int MIX2_CT_COL_LANES = 16;
+// N = R0 R1 R2 (R2 = 1: two stages); rows: one row per CTA, columns: 16 adjacent columns per CTA; a.lanes, a.pad_sh and
+// a.radix[] must describe exactly this plan (the host looks the instantiation up by them)
+template <bool COLS, int MINB, int R0, int R1, int R2>
+__global__ void __launch_bounds__(256, MINB) mix2_ct_kernel(const Mix2Args a) {
+    constexpr int N = R0 * R1 * R2, LANES = COLS ? MIX2_CT_COL_LANES : 1, SH = (R0 & 1) ? 30 : 4;
+    extern __shared__ __align__(16) float2 fsm_mix[];
+    const float2 *__restrict__ in = pick4(a.in, COLS ? blockIdx.z : blockIdx.y);
+    float2 *__restrict__ out = pick4(a.out, COLS ? blockIdx.z : blockIdx.y);
+    const int first_unit = blockIdx.x * LANES, g = COLS ? blockIdx.y : 0;
+    mix2_ct_stage<R0, COLS, N, 1, LANES, SH, true, false>(a, fsm_mix, in, out, first_unit, g);
+    mix2_ct_stage<R1, COLS, N, R0, LANES, SH, false, R2 == 1>(a, fsm_mix, in, out, first_unit, g);
+    if constexpr (R2 > 1) mix2_ct_stage<R2, COLS, N, R0 * R1, LANES, SH, false, true>(a, fsm_mix, in, out, first_unit, g);
+}
+
 }  // namespace mlb
