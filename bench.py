@@ -794,7 +794,7 @@ def ours(args):
         t3, _, _, _ = timed(lambda: p3.run(f3), 5, 2)
         other["ref_default_grid"] = {"workload": "3375x3375 aperture (good_fft_number size) -> all 3375x3375 FFT bins, 580 nm",
                                      "method": p3.method, "value": M3 * M3 * 5 / t3, "ms_per_step": t3 / 5 * 1e3,
-                                     "note": "big-radix mixed engine (3 x radix-15 stages in registers; columns as 15 x 225 in two passes)"}
+                                     "note": "big-radix mixed engine (rows: 3 x radix-15 stages in registers, kernel compiled for the plan; columns as 15 x 225 in two passes)"}
         # the strict drop-in (reference signature: host complex128 FFT'd fields in, host float64 P out; only the
         # epilogue runs on the GPU) on the same grid, wall clock
         from metalens_b200.farfield import farfield_from_nearfield
