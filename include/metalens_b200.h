@@ -134,6 +134,10 @@ int mlb_fft_tune(int rows_plain_loader, int rows_points_per_cta, int rows_thread
  * nearfield.py:30-36): returns the stage count (< 0 on error), radix8[0..7] = radices (0-padded), *pad_shift = the
  * shared-memory padding rule (4 = one pad per 16 elements, 30 = none). */
 int mlb_fft_mixed_plan(int N, int *radix8, int *pad_shift);
+/* Host only: 1 if the register kernels of the mixed engine have an instantiation compiled for the plan of length N
+ * (cols = 0: rows, one per CTA; cols = 1: a column (sub-)transform, 16 columns per CTA) and option mixed_compiled is on,
+ * else 0 (the generic run-time-plan kernel serves it). */
+int mlb_fft_mixed_compiled(int N, int cols);
 /* longest transform the shared-memory passes support (8192 complex64) */
 int mlb_fft_max_length(void);
 /*

@@ -43,6 +43,7 @@ SIGNATURES = {
     "mlb_fft_rows": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mlb_fft_mixed_plan": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "mlb_fft_mixed_compiled": (C.c_int, [C.c_int, C.c_int]),
     "mlb_fft_cols": (C.c_int, [_PP, C.c_int, _PP, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p]),
     "mlb_fft_cols_power_blocks": (C.c_int, [C.c_int, C.c_int]),

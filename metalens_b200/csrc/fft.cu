@@ -1060,6 +1060,17 @@ extern "C" int mlb_fft_mixed_plan(int N, int *radix8, int *pad_shift) {
     return ns;
 }
 
+/* host only: 1 if the register kernels have an instantiation compiled for the plan of length N (cols = 0: a row of N
+ * points, one row per CTA; cols = 1: a column (sub-)transform of N points, 16 columns per CTA), else 0 */
+extern "C" int mlb_fft_mixed_compiled(int N, int cols) {
+    mlb::Mix2Args m;
+    if (N < 2 || N > mlb::FFT_MAX_N || mlb::mix2_plan(m, N) <= 0) return 0;
+    m.lanes = cols ? mlb::MIX2_CT_COL_LANES : 1;
+    const mlb::Mix2Kernel k = cols ? mlb::mix2_ct_find(mlb::mix2_ct_cols, m, mlb::MIX2_CT_COL_LANES, 0)
+                                   : mlb::mix2_ct_find(mlb::mix2_ct_rows, m, 1, 0);
+    return k != nullptr ? 1 : 0;
+}
+
 extern "C" int mlb_fft_max_length(void) { return mlb::FFT_MAX_N; }
 
 extern "C" int mlb_fft_rows_can_transpose(int N) {

@@ -147,3 +147,37 @@ def test_library_planner_matches_the_emulated_one():
         odd = [v % 2 for v in want]
         assert odd == sorted(odd, reverse=True), (N, want)         # odd radices first
     assert lib.mlb_fft_mixed_plan(14, (ctypes.c_int * 8)(), None) < 0   # 2 * 7: not 5-smooth
+
+
+def test_every_register_kernel_plan_is_compiled():
+    """The dispatch of mlb_fft_rows / mlb_fft_cols (csrc/fft.cu) sends a transform to the one-butterfly-per-thread
+    register kernels when its busiest stage fills >= 80 % of a 256-thread CTA: rows of N >= 2048 points (one row per
+    CTA), column (sub-)transforms with 16 columns per CTA.  Every such plan must have its compile-time instantiation
+    (mix2_ct_kernel, fftmix.cuh) -- the generic run-time-plan kernel spills at 128 registers -- and no other plan may."""
+    from metalens_b200 import _lib
+    lib = _lib.load()
+    sizes = sorted({2 ** a * 3 ** b * 5 ** c for a in range(14) for b in range(9) for c in range(6)
+                    if 2 <= 2 ** a * 3 ** b * 5 ** c <= 8192})
+    rows, cols = [], []
+    for N in sizes:
+        if N & (N - 1) == 0:
+            assert lib.mlb_fft_mixed_compiled(N, 0) == 0 and lib.mlb_fft_mixed_compiled(N, 1) == 0   # radix-16 engine's lengths
+            continue
+        busiest = max(N // r for r in plan(N))
+        # rows (fft_rows_impl): rl = 256 // busiest rows per CTA, register variant if N >= 2048 and rl * busiest >= 205
+        rl = min(256 // busiest, 16) if busiest <= 256 else 0
+        want_row = rl >= 1 and N >= 2048 and rl * busiest >= 205
+        assert not want_row or rl == 1
+        assert lib.mlb_fft_mixed_compiled(N, 0) == (1 if want_row else 0), ("rows", N, plan(N))
+        rows += [N] if want_row else []
+        # columns (mlb_fft_cols, direct or second pass): rl = largest power of two <= 32 with rl * busiest <= 256
+        rl = 1
+        while rl < 32 and rl * 2 * busiest <= 256:
+            rl *= 2
+        want_col = rl * busiest <= 256 and rl >= 8 and rl * busiest >= 205
+        assert not want_col or rl == 16
+        assert lib.mlb_fft_mixed_compiled(N, 1) == (1 if want_col else 0), ("cols", N, plan(N))
+        cols += [N] if want_col else []
+    assert rows == [2160, 2250, 2304, 2400, 2560, 2700, 2880, 3072, 3375, 3600, 3840]
+    assert cols == [30, 45, 60, 75, 90, 120, 135, 144, 150, 160, 180, 192, 225, 240]
+    assert lib.mlb_fft_mixed_compiled(7, 0) == 0 and lib.mlb_fft_mixed_compiled(16384, 1) == 0
