@@ -477,6 +477,8 @@ _PLAN_CACHE = {}
 def _plan_for(wavelength, periphery, center, hexgridset):
     # the exact wavelength (k_vac, k_glass, the default grid depend on it; only the TABLE lookup uses the rounded nm,
     # nearfield.py:86) and the device the plan's buffers live on
+    if not torch.cuda.is_available():
+        raise _lib.MetalensB200Error("metalens_b200 needs a CUDA device (no CPU fallback)")
     key = (float(wavelength), torch.cuda.current_device(), id(periphery), id(center), id(hexgridset),
            id(getattr(hexgridset, "interpolators", None)),
            tuple(id(getattr(gc, "interpolators", None)) for gc in periphery['gratingcollection_list']))

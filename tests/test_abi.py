@@ -59,6 +59,23 @@ def test_no_cuda_fails_loudly():
     from metalens_b200 import farfield, MetalensB200Error
     with pytest.raises(MetalensB200Error):
         farfield.FarfieldPlan((8, 8), 1e-7, 1e-7, 532e-9, 1.46)
+    # the three reference-signature drop-ins: valid arguments, no device -> the package's own error, never a CPU result
+    import numpy as np
+    import synth_lens
+    from metalens_b200 import design, grating, lens_center, nearfield
+    x = np.arange(16) * 200e-9
+    F = np.zeros((16, 16), dtype=complex)
+    with pytest.raises(MetalensB200Error):
+        farfield.farfield_from_nearfield(F, F, F, F, x, x, 532e-9, 1.46)
+    with pytest.raises(MetalensB200Error):
+        farfield.farfield_from_fields(F, F, F, F, x, x, 532e-9, 1.46)
+    spec = synth_lens.SMALL_LENS
+    collections, hgs = synth_lens.make_library(grating, lens_center, spec)
+    periphery, center, _ = design.make_design(collections, spec["source_distance"], spec["radius"], hgs)
+    g = np.linspace(-spec["radius"], spec["radius"], 96)
+    for fn in (nearfield.build_nearfield, nearfield.build_nearfield_big):
+        with pytest.raises(MetalensB200Error):
+            fn(0.0, 0.0, -spec["source_distance"], "x", 580e-9, periphery, center, hgs, x_pts=g, y_pts=g)
 
 
 def test_product_never_imports_oracle():
