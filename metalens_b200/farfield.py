@@ -633,24 +633,6 @@ class FarfieldPlan:
         return self.Kx * self.Ky * self.P.element_size() + 8
 
 
-def _power_epilogue(lib, F, d_ux, d_uy, Kx, Ky, amp_scale, wavelength, n_glass, P, dudu):
-    """Launch mlb_ff_epilogue + the deterministic total_P reduction; returns the
-    device scalar total_P (float64)."""
-    dev = P.device
-    nblocks = lib.mlb_ff_epilogue_blocks(Kx, Ky)
-    block_sums = torch.empty(nblocks, dtype=torch.float64, device=dev)
-    total = torch.zeros(1, dtype=torch.float64, device=dev)
-    pf, _keep = _lib.ptr_array(F)
-    rc = lib.mlb_ff_epilogue(pf, F[0].shape[1], d_ux.data_ptr(), d_uy.data_ptr(), Kx, Ky,
-                             float(amp_scale), float(wavelength), float(n_glass), Z0,
-                             P.data_ptr(), P.shape[1], 1 if P.dtype == torch.float64 else 0,
-                             block_sums.data_ptr(), _stream_ptr())
-    _lib.check(rc, "mlb_ff_epilogue")
-    rc = lib.mlb_sum_f64(block_sums.data_ptr(), nblocks, float(dudu), total.data_ptr(), _stream_ptr())
-    _lib.check(rc, "mlb_sum_f64")
-    return total
-
-
 def farfield_from_fields(Ex, Ey, Hx, Hy, xp_list, yp_list, wavelength, n_glass, stride=1,
                          ux=None, uy=None, method="auto", p_dtype=torch.float64):
     """Real-space aperture fields (host arrays) -> far field, aperture sum included.
