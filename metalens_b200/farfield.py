@@ -21,7 +21,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, hostmem
 from .units import Z0
 
 
@@ -604,15 +604,16 @@ class FarfieldPlan:
         Returns (P numpy, total_P float)."""
         if self._pinned is None:
             self._dev_in = torch.empty((4, self.Mx, _even(self.My)), dtype=torch.complex64, device=self.device)
-            self._p_host = torch.empty((self.Kx, self.Ky), dtype=self.p_dtype).pin_memory()
-            self._t_host = torch.empty(1, dtype=torch.float64).pin_memory()
+            # pinned next to this GPU (hostmem.py): the copies of several ranks then do not share an inter-socket link
+            self._p_host = hostmem.pinned_empty((self.Kx, self.Ky), self.p_dtype, self.device.index)
+            self._t_host = hostmem.pinned_empty((1,), torch.float64, self.device.index)
             self._pinned = True
         if isinstance(Ex, torch.Tensor) and Ey is None:
             src = Ex
             assert src.dtype == torch.complex64 and tuple(src.shape) == (4, self.Mx, self.My)
         else:
             if getattr(self, "_pin_in", None) is None:
-                self._pin_in = torch.empty((4, self.Mx, self.My), dtype=torch.complex64).pin_memory()
+                self._pin_in = hostmem.pinned_empty((4, self.Mx, self.My), torch.complex64, self.device.index)
             pin = self._pin_in.numpy()
             for i, a in enumerate((Ex, Ey, Hx, Hy)):
                 pin[i] = a                  # dtype conversion to complex64 happens here
