@@ -87,3 +87,23 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_plain_c_client_links_and_runs(tmp_path):
+    """The boundary is a C ABI: a C99 program (examples/c_abi_host_only.c) compiles against include/metalens_b200.h with
+    gcc -pedantic, links against the shared library and runs its host-only calls (no GPU needed)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "metalens_b200")
+    if not os.path.exists(os.path.join(libdir, "libmetalens_b200.so")):
+        pytest.skip("library not built")
+    exe = str(tmp_path / "c_abi_host_only")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_abi_host_only.c"), "-L", libdir, "-lmetalens_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "3375 = 15 15 15" in out and "C-ABI" in out
