@@ -252,6 +252,45 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- hot path B
+def nearfield_cpu_baseline(M, spec, x, periph, center_rows, hgs, cpu_cols=384):
+    """Hot path B on the host, on a strip of the same grid (off-centre, so centre and rings are both represented).
+    kind "reference": the UNMODIFIED nearfield.build_nearfield from baseline/_ref, fed a library built with the
+    reference's own classes (its interpolators are scipy objects) and the same design rows; single-threaded as
+    shipped.  kind "port": oracle/nearfield_oracle.py when baseline/_ref is absent (or the reference run fails)."""
+    import contextlib
+    import io
+    import synth_lens
+    wl, f = 580e-9, spec["source_distance"]
+    j0 = M // 2 + M // 8
+    ys = x[j0:j0 + cpu_cols]
+    sys.path.insert(0, ROOT)
+    try:
+        from baseline import install_ref
+        ref = install_ref.load()
+        if ref is not None:
+            from metalens_b200.design import make_design
+            collections, r_hgs = synth_lens.make_library(ref["grating"], ref["lens_center"], spec)
+            r_periph, r_center, _ = make_design(collections, f, spec["radius"], r_hgs)      # host layout, same rows
+            assert len(r_center) == len(center_rows)
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):                                  # per-order progress prints
+                ref["nearfield"].build_nearfield(0.0, 0.0, -f, "x", wl, r_periph, r_center, r_hgs, x_pts=x, y_pts=ys)
+            tc = time.perf_counter() - t0
+            return dict(value=M * cpu_cols / tc, unit="aperture samples/s", cores=1, kind="reference",
+                        sample="%d x %d strip of the same grid, UNMODIFIED reference nearfield.build_nearfield "
+                               "(baseline/_ref; scipy interpolators + cKDTree), 1 thread as shipped, %.1f s" % (M, cpu_cols, tc))
+    except Exception as e:                                          # noqa: BLE001 -- fall back to the port, say why
+        print("bench: reference build_nearfield unavailable (%s: %s); timing the oracle port" % (type(e).__name__, str(e)[:200]),
+              file=sys.stderr)
+    from oracle import nearfield_oracle as no
+    t0 = time.perf_counter()
+    no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center_rows, hgs, x_pts=x, y_pts=ys)
+    tc = time.perf_counter() - t0
+    return dict(value=M * cpu_cols / tc, unit="aperture samples/s", cores=1, kind="port",
+                sample="%d x %d strip of the same grid, oracle/nearfield_oracle.py (numpy + scipy "
+                       "cKDTree), 1 thread, %.1f s" % (M, cpu_cols, tc))
+
+
 def bench_nearfield(M, torch, peaks, cpu_cols=384):
     """Aperture-field assembly (build_nearfield) on a synthetic round lens filling an M x M grid
     (SURVEY 8d cfg4 shape): samples/s and achieved write bandwidth of the fused kernel, next to the
@@ -300,16 +339,7 @@ def bench_nearfield(M, torch, peaks, cpu_cols=384):
                     "loop; algorithmic bytes = 32*M^2 written (4 complex64 fields)", design_seconds=t_design,
                plan_seconds=t_plan, design_note="make_design with the hex centre on the device (mlb_hex_count / mlb_hex_fill) and "
                                                 "NearfieldPlan (device binning, table packs, ring slices), wall clock")
-    # CPU oracle on a strip of the same grid (off-centre so centre and rings are both represented)
-    from oracle import nearfield_oracle as no
-    j0 = M // 2 + M // 8
-    ys = x[j0:j0 + cpu_cols]
-    t0 = time.perf_counter()
-    no.build_nearfield(0.0, 0.0, -f, "x", wl, periph, center.cpu().numpy(), hgs, x_pts=x, y_pts=ys)
-    tc = time.perf_counter() - t0
-    res["cpu_baseline"] = dict(value=M * cpu_cols / tc, unit="aperture samples/s", cores=1, kind="port",
-                               sample="%d x %d strip of the same grid, oracle/nearfield_oracle.py (numpy + scipy "
-                                      "cKDTree), 1 thread, %.1f s" % (M, cpu_cols, tc))
+    res["cpu_baseline"] = nearfield_cpu_baseline(M, spec, x, periph, center.cpu().numpy(), hgs, cpu_cols)
     return res
 
 
